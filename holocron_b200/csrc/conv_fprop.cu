@@ -1,0 +1,280 @@
+// Implicit-GEMM 2-D convolution (forward; also the data-gradient pass with transformed weights) on
+// the sm_100a tensor cores: NHWC bf16 activations, KRSC bf16 filters, fp32 accumulation in TMEM.
+//
+// GEMM view:  Y[m, co] = sum_{r,s,ci} X[pix(m) + (r,s), ci] * Wt[co, r, s, ci]
+//   M = N*Ho*Wo output pixels (tile 128 = the 128 TMEM lanes), N = Cout (tile BN <= 256 TMEM columns),
+//   K = R*S*Cin walked tap by tap in 64-channel blocks.
+// Replaces the cuDNN calls behind nn.Conv2d in holocron.models.utils.conv_sequence
+// (reference holocron/models/utils.py:28-86) and RepBlock (models/classification/repvgg.py:55-73).
+//
+// Pipeline (one persistent CTA per SM, 192 threads):
+//   warp 0      TMA producer: im2col-mode loads of the activation tile (hardware handles padding, stride,
+//               row/image wrap; out-of-range channels are zero-filled) + tiled loads of the filter slab,
+//               both landing 128B-swizzled in a multi-stage smem ring (mbarrier complete_tx).
+//   warp 1      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=BN, K=16) x4 per stage,
+//               tcgen05.commit releases the smem stage / publishes the accumulator.
+//   warps 2-5   epilogue: tcgen05.ld the accumulator (double-buffered in TMEM, so the epilogue of tile i
+//               overlaps the MMAs of tile i+1), fuse bias / residual / activation, store bf16 NHWC.
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "tmap.cuh"
+
+namespace {
+
+using namespace tc;
+
+constexpr int kBM = 128;          // output pixels per tile
+constexpr int kBK = 64;           // channels per K block (one 128-byte swizzle row)
+constexpr int kUmmaK = 16;        // K per tcgen05.mma for 16-bit inputs
+constexpr int kThreads = 192;     // producer warp, MMA warp, 4 epilogue warps
+constexpr int kTmemCols = 512;    // two accumulators of up to 256 columns
+constexpr int kABytes = kBM * kBK * 2;  // 16 KiB
+
+struct FpropParams {
+  int m_total;      // N*Ho*Wo
+  int Ho, Wo;
+  int stride, pad_h, pad_w, dil;
+  int R, S;
+  int Cin, Cout;
+  int BN;           // Cout tile
+  int num_m_tiles, num_n_tiles;
+  int cblocks;      // ceil(Cin / 64)
+  int stages;
+  int b_stage_bytes;  // BN*128 rounded up to 1024
+  int a_mode;         // 0: plain 2-D [M, C] matrix (1x1 s1 p0), 1: im2col
+  int act;            // 0 none, 1 relu
+  __nv_bfloat16* y;
+  const float* bias;              // [Cout] or null
+  const __nv_bfloat16* residual;  // [M, Cout] or null
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FpropParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages][A | B] then barriers
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stage_bytes = kABytes + p.b_stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tmem_full = empty_bar + p.stages;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;         // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_ptr, kTmemCols); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int kblocks = p.R * p.S * p.cblocks;
+  const uint32_t tx_bytes = kABytes + p.BN * 128;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.num_n_tiles, n_tile = tile % p.num_n_tiles;
+        const int m0 = m_tile * kBM;
+        const int q0 = m0 % p.Wo, p0 = (m0 / p.Wo) % p.Ho, n0 = m0 / (p.Wo * p.Ho);
+        const int base_w = q0 * p.stride - p.pad_w, base_h = p0 * p.stride - p.pad_h;
+        for (int tap = 0; tap < p.R * p.S; ++tap) {
+          const int r = tap / p.S, s = tap % p.S;
+          for (int cb = 0; cb < p.cblocks; ++cb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + (size_t)stage * stage_bytes;
+            uint8_t* sb = sa + kABytes;
+            mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+            if (p.a_mode == 1)
+              tma_load_im2col_4d(&tmA, &full_bar[stage], sa, cb * kBK, base_w, base_h, n0,
+                                 (uint16_t)(s * p.dil), (uint16_t)(r * p.dil));
+            else
+              tma_load_2d(&tmA, &full_bar[stage], sa, cb * kBK, m0);
+            tma_load_3d(&tmB, &full_bar[stage], sb, cb * kBK, tap, n_tile * p.BN);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(kBM, p.BN, 0, 0);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t sb = sa + kABytes;
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k) {
+            const uint64_t adesc = make_smem_desc(sa + k * kUmmaK * 2, 16, 1024, kLayoutSW128);
+            const uint64_t bdesc = make_smem_desc(sb + k * kUmmaK * 2, 16, 1024, kLayoutSW128);
+            umma_f16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs have read it
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);      // accumulator complete
+      }
+    }
+  } else {
+    // ================= epilogue (warps 2..5) =================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_tile = tile / p.num_n_tiles, n_tile = tile % p.num_n_tiles;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_tile * kBM + quarter * 32 + lane;
+      const bool row_ok = row < p.m_total;
+      const int col_base = n_tile * p.BN;
+      const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(quarter * 32) << 16);
+      for (int c = 0; c < p.BN; c += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(taddr + c, v);
+        tmem_ld_wait();
+        const int col = col_base + c;
+        if (row_ok && col < p.Cout) {
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] += __ldg(p.bias + col + j);
+          }
+          const size_t off = (size_t)row * p.Cout + col;
+          if (p.residual) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
+            uint4 r0 = rp[0], r1 = rp[1];
+            const __nv_bfloat16* rb0 = reinterpret_cast<const __nv_bfloat16*>(&r0);
+            const __nv_bfloat16* rb1 = reinterpret_cast<const __nv_bfloat16*>(&r1);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { f[j] += __bfloat162float(rb0[j]); f[8 + j] += __bfloat162float(rb1[j]); }
+          }
+          if (p.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.0f);
+          }
+          uint4 o[2];
+          __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(o);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) ob[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+          uint4* yp = reinterpret_cast<uint4*>(p.y + off);
+          yp[0] = o[0];
+          yp[1] = o[1];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
+}
+
+}  // namespace
+
+extern "C" {
+
+// Forward convolution, NHWC bf16.  x: [N,H,W,Cin]  w: [Cout,R,S,Cin]  y: [N,Ho,Wo,Cout]
+//   bias: fp32 [Cout] or NULL; residual: bf16 [N,Ho,Wo,Cout] or NULL; act: 0 none, 1 relu.
+// Requirements: Cin % 8 == 0, Cout % 16 == 0, all pointers 16-byte aligned.
+int hb_conv2d_fprop_bf16(const void* x, const void* w, void* y, const float* bias, const void* residual, int N, int H,
+                         int W, int Cin, int Cout, int R, int S, int stride, int pad, int dil, int act, int num_ctas,
+                         void* stream) {
+  if (Cin % 8 != 0 || Cout % 16 != 0) return (int)cudaErrorInvalidValue;
+  if (!hb::aligned16(x) || !hb::aligned16(w) || !hb::aligned16(y)) return (int)cudaErrorMisalignedAddress;
+  const int Ho = (H + 2 * pad - dil * (R - 1) - 1) / stride + 1;
+  const int Wo = (W + 2 * pad - dil * (S - 1) - 1) / stride + 1;
+  if (Ho <= 0 || Wo <= 0) return (int)cudaErrorInvalidValue;
+  const long long m_total_ll = (long long)N * Ho * Wo;
+  if (m_total_ll <= 0 || m_total_ll > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
+
+  FpropParams p{};
+  p.m_total = (int)m_total_ll;
+  p.Ho = Ho; p.Wo = Wo;
+  p.stride = stride; p.pad_h = pad; p.pad_w = pad; p.dil = dil;
+  p.R = R; p.S = S; p.Cin = Cin; p.Cout = Cout;
+  // Cout tile: whole Cout when it fits the 256 accumulator columns, else the largest multiple of 16
+  // <= 256 that divides Cout (falls back to 256 with a masked tail).
+  int BN = Cout;
+  if (Cout > 256) {
+    BN = 256;
+    for (int c = 256; c >= 64; c -= 16) if (Cout % c == 0) { BN = c; break; }
+  }
+  p.BN = BN;
+  p.num_m_tiles = (p.m_total + kBM - 1) / kBM;
+  p.num_n_tiles = (Cout + BN - 1) / BN;
+  p.cblocks = (Cin + kBK - 1) / kBK;
+  p.b_stage_bytes = ((BN * 128) + 1023) & ~1023;
+  const int stage_bytes = kABytes + p.b_stage_bytes;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2) return (int)cudaErrorInvalidValue;
+  p.stages = stages;
+  p.a_mode = (R == 1 && S == 1 && stride == 1 && pad == 0) ? 0 : 1;
+  p.act = act;
+  p.y = (__nv_bfloat16*)y;
+  p.bias = bias;
+  p.residual = (const __nv_bfloat16*)residual;
+
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (p.a_mode == 0) {
+    uint64_t dims[2] = {(uint64_t)Cin, (uint64_t)p.m_total};
+    uint64_t strides[1] = {(uint64_t)Cin * 2};
+    uint32_t box[2] = {kBK, kBM};
+    rc = tmap::encode_tiled_bf16(&tmA, x, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  } else {
+    rc = tmap::encode_im2col_bf16(&tmA, x, N, H, W, Cin, pad, pad, R, S, dil, stride, kBK, kBM,
+                                  CU_TENSOR_MAP_SWIZZLE_128B);
+  }
+  if (rc) return rc;
+  {
+    uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)(R * S), (uint64_t)Cout};
+    uint64_t strides[2] = {(uint64_t)Cin * 2, (uint64_t)R * S * Cin * 2};
+    uint32_t box[3] = {kBK, 1, (uint32_t)BN};
+    rc = tmap::encode_tiled_bf16(&tmB, w, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+
+  const size_t smem_bytes = (size_t)stages * stage_bytes + (2 * stages + 4) * sizeof(uint64_t) + 16 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  int grid = num_ctas > 0 ? num_ctas : HB_NUM_SMS;
+  if (grid > num_tiles) grid = num_tiles;
+  conv_fprop_kernel<<<grid, kThreads, smem_bytes, (cudaStream_t)stream>>>(tmA, tmB, p);
+  HB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

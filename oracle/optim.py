@@ -1,0 +1,68 @@
+"""Oracle restatements of the optimizer updates (reference: holocron/optim/{adabelief,lamb,tadam}.py).
+
+Each function performs ONE step in place on plain tensors (fp32, CPU) and returns nothing, mirroring the
+reference's per-tensor update formulas, quirks included.
+"""
+import math
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+
+@torch.no_grad()
+def adabelief_step(p: Tensor, g: Tensor, m: Tensor, s: Tensor, step: int, lr: float, beta1: float, beta2: float,
+                   eps: float, weight_decay: float = 0.0, amsgrad: bool = False,
+                   s_max: Optional[Tensor] = None) -> None:
+    """reference optim/adabelief.py:121-167. No +eps inside the belief EMA (unlike the paper)."""
+    if weight_decay != 0:
+        g = g + weight_decay * p
+    m.copy_(beta1 * m + (1 - beta1) * g)
+    r = g - m
+    s.copy_(beta2 * s + (1 - beta2) * r * r)
+    second = s
+    if amsgrad:
+        s_max.copy_(torch.maximum(s_max, s))
+        second = s_max
+    denom = second.sqrt() / math.sqrt(1 - beta2**step) + eps
+    p.sub_((lr / (1 - beta1**step)) * m / denom)
+
+
+@torch.no_grad()
+def lamb_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, lr: float, beta1: float, beta2: float, eps: float,
+              weight_decay: float = 0.0, scale_clip: Tuple[float, float] = (0.0, 10.0)) -> float:
+    """reference optim/lamb.py:79-137: Adam moments without bias correction, LARS-style trust ratio.
+    Returns the local learning-rate multiplier."""
+    m.copy_(beta1 * m + (1 - beta1) * g)
+    v.copy_(beta2 * v + (1 - beta2) * g * g)
+    update = m / (v.sqrt() + eps)
+    if weight_decay != 0:
+        update = update + weight_decay * p
+    p_norm = p.pow(2).sum().sqrt()
+    u_norm = update.pow(2).sum().sqrt()
+    phi = p_norm.clamp(*scale_clip)
+    local_lr = 1.0 if (phi == 0 or u_norm == 0) else float(phi / u_norm)
+    p.sub_(lr * local_lr * update)
+    return local_lr
+
+
+@torch.no_grad()
+def tadam_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, W: Tensor, step: int, lr: float, beta1: float,
+               beta2: float, eps: float, weight_decay: float = 0.0, dof: Optional[float] = None,
+               amsgrad: bool = False, v_max: Optional[Tensor] = None) -> None:
+    """reference optim/tadam.py:160-212. ``W`` is the 1-element running weight sum (init beta1/(1-beta1))."""
+    n = p.numel()
+    d = float(n) if dof is None else float(dof)
+    if weight_decay != 0:
+        g = g + weight_decay * p
+    w = ((g - m) ** 2 / (v + eps)).sum()
+    w = (d + n) / (w + d)
+    m.copy_(m * (W / (W + w)) + (w * g) / (W + w))
+    W.copy_(W * ((2 * beta1 - 1) / beta1) + w)
+    v.copy_(beta2 * v + (1 - beta2) * g * g)
+    second = v
+    if amsgrad:
+        v_max.copy_(torch.maximum(v_max, v))
+        second = v_max
+    denom = second.sqrt() / math.sqrt(1 - beta2**step) + eps
+    p.sub_((lr / (1 - beta1**step)) * m / denom)

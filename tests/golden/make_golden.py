@@ -1,0 +1,269 @@
+"""Generates the golden fixtures under tests/golden/ by running the UNMODIFIED reference (frgfm/Holocron,
+mounted read-only at /root/reference) on seeded CPU inputs.  Run in the build container only:
+
+    python tests/golden/make_golden.py
+
+Every fixture is a dict of small tensors (inputs + the reference's outputs / gradients / updated state); the
+tests compare the oracle (CPU) and the CUDA path (GPU) against them.
+"""
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+from oracle import reference_loader  # noqa: E402
+
+OUT = Path(__file__).resolve().parent
+holocron = reference_loader.load()
+F = holocron.nn.functional
+ops = holocron.ops.boxes
+
+
+def grad_of(fn, *inputs, skip=()):
+    """Runs fn on clones and returns (output, grads of output.sum()); inputs listed in `skip` get no grad
+    (the reference's in-place patch normalisation makes its own backward fail when x requires grad)."""
+    ins = [t.clone().requires_grad_(i not in skip) for i, t in enumerate(inputs)]
+    out = fn(*ins)
+    wrt = [t for t in ins if t.requires_grad]
+    gs = list(torch.autograd.grad(out.sum() if out.ndim else out, wrt, allow_unused=True))
+    full = [gs.pop(0) if t.requires_grad else None for t in ins]
+    return out.detach(), full
+
+
+def gen_activations():
+    torch.manual_seed(11)
+    x = torch.randn(4, 6, 9, 7) * 2.5
+    x.view(-1)[:8] = torch.tensor([-3.0, -2.0, -1.0, 0.0, 1.0, 2.0, -2.5, 0.5])
+    d = {"x": x}
+    y, (g,) = grad_of(lambda t: F.hard_mish(t), x)
+    d["hard_mish"], d["hard_mish_grad"] = y, g
+    for beta in (1.0, 0.5):
+        y, (g,) = grad_of(lambda t: F.nl_relu(t, beta=beta), x)
+        d[f"nl_relu_b{beta}"], d[f"nl_relu_b{beta}_grad"] = y, g
+    torch.save(d, OUT / "activations.pt")
+
+
+def gen_losses():
+    torch.manual_seed(12)
+    d = {}
+    # classification-shaped (N, K) and segmentation-shaped (N, K, H, W)
+    for tag, shape in (("cls", (16, 10)), ("seg", (2, 5, 6, 7))):
+        x = torch.randn(*shape) * 2
+        k = shape[1]
+        tshape = (shape[0],) + tuple(shape[2:])
+        t = torch.randint(0, k, tshape)
+        w = torch.rand(k) + 0.5
+        d[f"{tag}_x"], d[f"{tag}_t"], d[f"{tag}_w"] = x, t, w
+        for red in ("mean", "sum", "none"):
+            for ii in (-100, 1):
+                for use_w in (False, True):
+                    key = f"{tag}_{red}_ii{ii}_w{int(use_w)}"
+                    wt = w if use_w else None
+                    y, (g,) = grad_of(lambda a: F.focal_loss(a, t, wt, ii, red, 2.0), x)
+                    d["focal_" + key], d["focal_grad_" + key] = y, g
+                    y, (g,) = grad_of(lambda a: F.poly_loss(a, t, 2.0, wt, ii, red), x)
+                    d["poly_" + key], d["poly_grad_" + key] = y, g
+        y, (g,) = grad_of(lambda a: F.focal_loss(a, t, None, -100, "mean", 0.5), x)
+        d[f"focal_{tag}_gamma0.5"], d[f"focal_grad_{tag}_gamma0.5"] = y, g
+        # soft targets for poly
+        soft = torch.softmax(torch.randn(*shape), dim=1)
+        d[f"{tag}_soft"] = soft
+        for red in ("mean", "sum", "none"):
+            for ii in (-100, 1):
+                y, (g,) = grad_of(lambda a: F.poly_loss(a, soft, 2.0, None, ii, red), x)
+                d[f"polysoft_{tag}_{red}_ii{ii}"], d[f"polysoft_grad_{tag}_{red}_ii{ii}"] = y, g
+        if tag == "cls":
+            y, (g,) = grad_of(lambda a: F.poly_loss(a, soft, 1.5, w, -100, "mean"), x)
+            d["polysoft_cls_w"], d["polysoft_grad_cls_w"] = y, g
+        # dice on probabilities
+        prob = torch.softmax(x, dim=1)
+        onehot = torch.nn.functional.one_hot(t, k).movedim(-1, 1).float()
+        d[f"{tag}_prob"], d[f"{tag}_onehot"] = prob, onehot
+        for gamma in ((1.0, 2.0) if tag == "seg" else ()):  # dice needs >= 3 dims (flatten(2) in the reference)
+            for use_w in (False, True):
+                wt = w if use_w else None
+                y, (g,) = grad_of(lambda a: F.dice_loss(a, onehot, wt, gamma), prob)
+                d[f"dice_{tag}_g{gamma}_w{int(use_w)}"], d[f"dice_grad_{tag}_g{gamma}_w{int(use_w)}"] = y, g
+    torch.save(d, OUT / "losses.pt")
+
+
+def gen_boxes():
+    torch.manual_seed(13)
+    kat = torch.tensor([[0, 0, 100, 100], [50, 50, 100, 100], [50, 50, 150, 150], [100, 100, 200, 200]],
+                       dtype=torch.float32)  # reference tests/test_ops.py:9-13
+    xy = torch.rand(37, 2) * 80
+    wh = torch.rand(37, 2) * 40 + 1
+    b1 = torch.cat([xy, xy + wh], 1)
+    xy = torch.rand(23, 2) * 80
+    wh = torch.rand(23, 2) * 40 + 1
+    b2 = torch.cat([xy, xy + wh], 1)
+    d = {"kat": kat, "b1": b1, "b2": b2}
+    for name, (a, b) in (("kat", (kat, kat)), ("rnd", (b1, b2))):
+        d[f"{name}_giou"] = ops.box_giou(a, b)
+        d[f"{name}_penalty"] = ops.iou_penalty(a, b)
+        d[f"{name}_diou"] = ops.diou_loss(a, b)
+        d[f"{name}_ciou"] = ops.ciou_loss(a, b)
+        d[f"{name}_arc"] = ops.aspect_ratio_consistency(a, b)
+    d["kat_aspect"] = ops.aspect_ratio(kat)
+    for fn in ("box_giou", "diou_loss", "ciou_loss"):
+        _, gs = grad_of(lambda a, b: getattr(ops, fn)(a, b), b1, b2)
+        d[f"rnd_{fn}_grad1"], d[f"rnd_{fn}_grad2"] = gs
+    # weighted upstream gradient (not all-ones) for the loss used by YOLOv4
+    up = torch.rand(37, 23)
+    a = b1.clone().requires_grad_(True)
+    b = b2.clone().requires_grad_(True)
+    (ops.ciou_loss(a, b) * up).sum().backward()
+    d["up"], d["rnd_ciou_wgrad1"], d["rnd_ciou_wgrad2"] = up, a.grad, b.grad
+    torch.save(d, OUT / "boxes.pt")
+
+
+def gen_convs():
+    torch.manual_seed(14)
+    d = {}
+    x = torch.randn(2, 8, 9, 10)
+    w = torch.randn(16, 8, 3, 3) * 0.2
+    b = torch.randn(16) * 0.1
+    d.update(x=x, w=w, b=b)
+    for tag, kw in (("p1", dict(padding=1)), ("s2p1", dict(stride=2, padding=1)), ("d2p2", dict(dilation=2, padding=2)),
+                    ("p0", dict())):
+        y, gs = grad_of(lambda a, ww, bb: F.norm_conv2d(a, ww, bb, **kw), x, w, b, skip=(0,))
+        d[f"normconv_{tag}"] = y
+        d[f"normconv_{tag}_gw"], d[f"normconv_{tag}_gb"] = gs[1:]
+        for ns in (False, True):
+            y, gs = grad_of(lambda a, ww, bb: F.add2d(a, ww, bb, normalize_slices=ns, **kw), x, w, b,
+                            skip=(0,) if ns else ())
+            d[f"add2d_{tag}_n{int(ns)}"] = y
+            if not ns:
+                d[f"add2d_{tag}_n{int(ns)}_gx"] = gs[0]
+            d[f"add2d_{tag}_n{int(ns)}_gw"], d[f"add2d_{tag}_n{int(ns)}_gb"] = gs[1:]
+    # modules with seeded init: state_dict + output (+ input grad)
+    nn = holocron.nn
+    torch.manual_seed(15)
+    fr = nn.FReLU(8)
+    fr.bn.running_mean.normal_()
+    fr.bn.running_var.uniform_(0.5, 1.5)
+    fr.bn.weight.data.uniform_(0.5, 1.5)
+    fr.bn.bias.data.normal_()
+    d["frelu_state"] = {k: v.clone() for k, v in fr.state_dict().items()}
+    fr.eval()
+    y, (g,) = grad_of(lambda a: fr(a), x)
+    d["frelu_eval"], d["frelu_eval_gx"] = y, g
+    fr.train()
+    y, (g,) = grad_of(lambda a: fr(a), x)
+    d["frelu_train"], d["frelu_train_gx"] = y, g
+    d["frelu_train_running_mean"], d["frelu_train_running_var"] = fr.bn.running_mean.clone(), fr.bn.running_var.clone()
+    torch.manual_seed(16)
+    sl = nn.SlimConv2d(8, 3, padding=1, r=4, L=2)
+    d["slim_state"] = {k: v.clone() for k, v in sl.state_dict().items()}
+    sl.eval()
+    y, (g,) = grad_of(lambda a: sl(a), x)
+    d["slim_eval"], d["slim_eval_gx"] = y, g
+    # dropblock: noise drawn exactly like the reference (torch.rand((N, H, W)) on CPU under the seed)
+    xd = torch.randn(2, 3, 12, 12)
+    torch.manual_seed(17)
+    d["dropblock_x"] = xd
+    d["dropblock_out"] = F.dropblock2d(xd, 0.3, 3)
+    torch.manual_seed(17)
+    d["dropblock_noise"] = torch.rand((2, 12, 12))
+    torch.save(d, OUT / "convs.pt")
+
+
+def gen_optim():
+    optim = holocron.optim
+    d = {}
+    shapes = [(7, 5), (33,), (4, 3, 3, 3), (1,)]
+    torch.manual_seed(18)
+    p0 = [torch.randn(*s) for s in shapes]
+    grads = [[torch.randn(*s) * 0.3 for s in shapes] for _ in range(3)]
+    d["p0"], d["grads"] = p0, grads
+    cfgs = {
+        "adabelief": (optim.AdaBelief, dict(lr=1e-2, betas=(0.9, 0.99), eps=1e-8)),
+        "adabelief_wd_ams": (optim.AdaBelief, dict(lr=1e-2, betas=(0.95, 0.99), eps=1e-6, weight_decay=1e-2, amsgrad=True)),
+        "lamb": (optim.LAMB, dict(lr=1e-2, betas=(0.9, 0.99), eps=1e-8)),
+        "lamb_wd": (optim.LAMB, dict(lr=1e-2, betas=(0.9, 0.99), eps=1e-6, weight_decay=1e-2, scale_clip=(0.1, 2.0))),
+        "tadam": (optim.TAdam, dict(lr=1e-2, betas=(0.9, 0.99), eps=1e-8)),
+        "tadam_wd_ams_dof": (optim.TAdam, dict(lr=1e-2, betas=(0.9, 0.99), eps=1e-6, weight_decay=1e-2, amsgrad=True, dof=5.0)),
+    }
+    for name, (cls, kw) in cfgs.items():
+        params = [torch.nn.Parameter(p.clone()) for p in p0]
+        opt = cls(params, **kw)
+        traj = []
+        for step in range(3):
+            for p, g in zip(params, grads[step]):
+                p.grad = g.clone()
+            opt.step()
+            traj.append([p.detach().clone() for p in params])
+        d[name] = traj
+        d[name + "_kw"] = kw
+    torch.save(d, OUT / "optim.pt")
+
+
+def gen_models():
+    models = holocron.models
+    d = {}
+    # fuse_conv_bn identity (reference tests/test_models.py:55-83)
+    torch.manual_seed(19)
+    conv = torch.nn.Conv2d(6, 8, 3, padding=1, bias=False)
+    bn = torch.nn.BatchNorm2d(8).eval()
+    bn.weight.data.uniform_(0.5, 1.5)
+    bn.bias.data.normal_()
+    bn.running_mean.normal_()
+    bn.running_var.uniform_(0.5, 1.5)
+    k, b = models.utils.fuse_conv_bn(conv, bn)
+    d["fuse"] = dict(conv_w=conv.weight.detach().clone(), gamma=bn.weight.detach().clone(), beta=bn.bias.detach().clone(),
+                     mean=bn.running_mean.clone(), var=bn.running_var.clone(), eps=bn.eps, k=k.clone(), b=b.clone())
+    # RepBlock train-mode forward/backward on a small shape (stride 1 with identity, stride 2 without)
+    from holocron.models.classification.repvgg import RepBlock
+    for tag, (cin, cout, stride, ident) in (("s1", (16, 16, 1, True)), ("s2", (16, 32, 2, False))):
+        torch.manual_seed(20)
+        blk = RepBlock(cin, cout, stride, ident)
+        for m in blk.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.data.uniform_(0.5, 1.5)
+                m.bias.data.normal_(0, 0.2)
+        state = {k_: v.clone() for k_, v in blk.state_dict().items()}
+        x = torch.randn(4, cin, 10, 10)
+        blk.train()
+        xin = x.clone().requires_grad_(True)
+        y = blk(xin)
+        up = torch.randn_like(y)
+        (y * up).sum().backward()
+        grads = {n: p.grad.clone() for n, p in blk.named_parameters()}
+        d[f"repblock_{tag}"] = dict(state=state, x=x, up=up, y=y.detach(), gx=xin.grad.clone(), grads=grads,
+                                     state_after={k_: v.clone() for k_, v in blk.state_dict().items()})
+        blk.eval()
+        y_eval = blk(x).detach()
+        blk.reparametrize()
+        d[f"repblock_{tag}"]["y_eval"] = y_eval
+        d[f"repblock_{tag}"]["y_reparam"] = blk(x).detach()
+        d[f"repblock_{tag}"]["rep_w"] = blk.branches.weight.detach().clone()
+        d[f"repblock_{tag}"]["rep_b"] = blk.branches.bias.detach().clone()
+    # config 1: repvgg_a0, seed 0, 1x3x224x224 CPU input (BASELINE.json configs[0])
+    torch.manual_seed(0)
+    m = models.repvgg_a0(num_classes=1000).eval()
+    x = torch.rand(1, 3, 224, 224)
+    with torch.no_grad():
+        logits = m(x)
+        m.reparametrize()
+        logits_rep = m(x)
+    d["cfg1"] = dict(logits=logits, logits_rep=logits_rep, argmax=int(logits.argmax()), argmax_rep=int(logits_rep.argmax()),
+                     x_sum=float(x.double().sum()), n_params=sum(p.numel() for p in m.parameters()))
+    torch.manual_seed(0)
+    m = models.repvgg_a0(num_classes=1000)
+    d["cfg1"]["param_sum"] = float(sum(p.double().sum() for p in m.parameters()))
+    d["cfg1"]["param_abs_sum"] = float(sum(p.double().abs().sum() for p in m.parameters()))
+    d["cfg1"]["n_params_train"] = sum(p.numel() for p in m.parameters())
+    torch.save(d, OUT / "models.pt")
+
+
+if __name__ == "__main__":
+    gen_activations()
+    gen_losses()
+    gen_boxes()
+    gen_convs()
+    gen_optim()
+    gen_models()
+    for f in sorted(OUT.glob("*.pt")):
+        print(f.name, f.stat().st_size)
