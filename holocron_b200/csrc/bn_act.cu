@@ -1,0 +1,517 @@
+// Training-mode BatchNorm + branch-sum + activation, fused for NHWC bf16 activations.
+//
+// The unit being fused is the reference's "conv -> BatchNorm2d -> act" sequence
+// (holocron/models/utils.py:28-86 conv_sequence) and the RepVGG block
+//   out = act( BN3(conv3x3(x)) + BN1(conv1x1(x)) [+ BNid(x)] )        (models/classification/repvgg.py:71-73)
+// generalised to B <= 3 normalised branches u_b of identical shape [M, C] plus an optional un-normalised
+// residual. The reference runs one cuDNN/ATen kernel per BN, add and activation (>= 8 HBM passes per
+// RepBlock); here the whole thing is
+//   stats      : one pass over the branch inputs  -> per-channel sum / sum-of-squares (fp32 partials, fp64 merge)
+//   finalize   : C-sized: mean, rstd, scale = gamma*rstd, shift = beta - mean*scale, running-stat update
+//   forward    : one pass: out = act(sum_b (scale_b * u_b + shift_b) + residual)
+//   bwd reduce : one pass: sum(dz), sum(dz * xhat_b)    with dz = dOut * act'(z), z recomputed (not stored)
+//   bwd apply  : one pass: du_b = scale_b * (dz - mean(dz) - xhat_b * mean(dz*xhat_b)), dresidual = dz
+// Every thread owns 8 consecutive channels (one 128-bit bf16 vector) of a row; rows are walked with a stride
+// that keeps the thread's channel group fixed, so per-channel parameters live in registers.
+#include "common.cuh"
+
+namespace {
+
+using namespace hb;
+
+constexpr int kThreads = 256;
+constexpr int kMaxBranches = 3;
+
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_RELU6 = 2, ACT_SILU = 3, ACT_LEAKY = 4, ACT_MISH = 5, ACT_HARDMISH = 6 };
+
+__device__ __forceinline__ float act_fwd(int act, float z, float slope) {
+  switch (act) {
+    case ACT_RELU: return fmaxf(z, 0.f);
+    case ACT_RELU6: return fminf(fmaxf(z, 0.f), 6.f);
+    case ACT_SILU: return z / (1.f + __expf(-z));
+    case ACT_LEAKY: return z > 0.f ? z : z * slope;
+    case ACT_MISH: {
+      // x * tanh(softplus(x)); softplus threshold 20 as in torch
+      float sp = z > 20.f ? z : log1pf(__expf(z));
+      return z * tanhf(sp);
+    }
+    case ACT_HARDMISH: return (0.5f * z) * fminf(fmaxf(z + 2.f, 0.f), 2.f);
+    default: return z;
+  }
+}
+__device__ __forceinline__ float act_grad(int act, float z, float slope) {
+  switch (act) {
+    case ACT_RELU: return z > 0.f ? 1.f : 0.f;
+    case ACT_RELU6: return (z > 0.f && z < 6.f) ? 1.f : 0.f;
+    case ACT_SILU: {
+      float s = 1.f / (1.f + __expf(-z));
+      return s * (1.f + z * (1.f - s));
+    }
+    case ACT_LEAKY: return z > 0.f ? 1.f : slope;
+    case ACT_MISH: {
+      float sp = z > 20.f ? z : log1pf(__expf(z));
+      float t = tanhf(sp);
+      float sg = 1.f / (1.f + __expf(-z));
+      return t + z * (1.f - t * t) * sg;
+    }
+    case ACT_HARDMISH: {
+      float t = z + 2.f;
+      float c = fminf(fmaxf(t, 0.f), 2.f);
+      return 0.5f * c + ((t >= 0.f && t <= 2.f) ? 0.5f * z : 0.f);
+    }
+    default: return 1.f;
+  }
+}
+
+struct Branches {
+  const __nv_bfloat16* u[kMaxBranches];
+  int n;
+};
+
+// thread geometry shared by all kernels: tx = channel group inside the block's channel slab, ty = row lane
+struct Geo {
+  int cg_total;  // C / 8
+  int cg_t;      // channel groups per block (<= 32)
+  int rows_t;    // row lanes per block
+  __host__ static Geo make(int C) {
+    Geo g;
+    g.cg_total = C / 8;
+    g.cg_t = g.cg_total < 32 ? g.cg_total : 32;
+    g.rows_t = kThreads / g.cg_t;
+    return g;
+  }
+};
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float* f) {
+  Vec16<__nv_bfloat16> v = ld16_stream(p);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = __bfloat162float(v.v[j]);
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float* f) {
+  Vec16<__nv_bfloat16> v;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v.v[j] = __float2bfloat16_rn(f[j]);
+  st16(p, v);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// stats: sums[b][0][c] = sum_m u_b[m,c], sums[b][1][c] = sum_m u_b[m,c]^2     (fp64 global accumulators)
+// grid = (row blocks, channel slabs, branches)
+__global__ void __launch_bounds__(kThreads) bn_stats_kernel(Branches br, int M, int C, Geo g, double* sums) {
+  __shared__ float red[2][kThreads * 8];
+  const int tx = threadIdx.x % g.cg_t, ty = threadIdx.x / g.cg_t;
+  const int cg = blockIdx.y * g.cg_t + tx;
+  const bool active = ty < g.rows_t && cg < g.cg_total;
+  const __nv_bfloat16* u = br.u[blockIdx.z];
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+  if (active) {
+    const size_t row_stride = (size_t)gridDim.x * g.rows_t;
+    size_t m = (size_t)blockIdx.x * g.rows_t + ty;
+    // two rows in flight per trip
+    for (; m + row_stride < (size_t)M; m += 2 * row_stride) {
+      float a[8], b[8];
+      load8(u + m * C + cg * 8, a);
+      load8(u + (m + row_stride) * C + cg * 8, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j] += a[j] + b[j]; q[j] += a[j] * a[j] + b[j] * b[j]; }
+    }
+    if (m < (size_t)M) {
+      float a[8];
+      load8(u + m * C + cg * 8, a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j] += a[j]; q[j] += a[j] * a[j]; }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { red[0][threadIdx.x * 8 + j] = s[j]; red[1][threadIdx.x * 8 + j] = q[j]; }
+  __syncthreads();
+  // threads 0 .. cg_t*8-1 each own one channel of the slab: sum over row lanes in fp64
+  const int nch = g.cg_t * 8;
+  for (int c = threadIdx.x; c < 2 * nch; c += kThreads) {
+    const int which = c / nch, ch = c % nch;
+    const int ctx = ch / 8, j = ch % 8;
+    const int gcg = blockIdx.y * g.cg_t + ctx;
+    if (gcg >= g.cg_total) continue;
+    double acc = 0.0;
+    for (int r = 0; r < g.rows_t; ++r) acc += (double)red[which][(r * g.cg_t + ctx) * 8 + j];
+    atomicAdd(&sums[((size_t)blockIdx.z * 2 + which) * C + gcg * 8 + j], acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// finalize: per branch b and channel c
+struct FinalizeParams {
+  const double* sums;      // [B][2][C]
+  const float* gamma[kMaxBranches];
+  const float* beta[kMaxBranches];
+  float* running_mean[kMaxBranches];  // may be null
+  float* running_var[kMaxBranches];
+  float* mean;   // [B][C] out
+  float* rstd;   // [B][C] out
+  float* scale;  // [B][C] out
+  float* shift;  // [B][C] out
+  int B, C, M;
+  float eps, momentum;
+};
+__global__ void bn_finalize_kernel(FinalizeParams p) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (c >= p.C) return;
+  const double s = p.sums[((size_t)b * 2 + 0) * p.C + c];
+  const double q = p.sums[((size_t)b * 2 + 1) * p.C + c];
+  const double mean = s / p.M;
+  double var = q / p.M - mean * mean;
+  if (var < 0) var = 0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)p.eps));
+  const float g = p.gamma[b] ? p.gamma[b][c] : 1.f;
+  const float be = p.beta[b] ? p.beta[b][c] : 0.f;
+  const float sc = g * rstd;
+  const size_t o = (size_t)b * p.C + c;
+  p.mean[o] = (float)mean;
+  p.rstd[o] = rstd;
+  p.scale[o] = sc;
+  p.shift[o] = be - (float)mean * sc;
+  if (p.running_mean[b]) {
+    const double unbiased = p.M > 1 ? var * ((double)p.M / (double)(p.M - 1)) : var;
+    p.running_mean[b][c] = (1.f - p.momentum) * p.running_mean[b][c] + p.momentum * (float)mean;
+    p.running_var[b][c] = (1.f - p.momentum) * p.running_var[b][c] + p.momentum * (float)unbiased;
+  }
+}
+
+// eval-mode affine from running statistics: scale = gamma / sqrt(var + eps), shift = beta - mean * scale
+__global__ void bn_eval_affine_kernel(const float* gamma, const float* beta, const float* rmean, const float* rvar,
+                                      float eps, int C, float* scale, float* shift, float* mean, float* rstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float r = 1.f / sqrtf(rvar[c] + eps);
+  const float sc = (gamma ? gamma[c] : 1.f) * r;
+  scale[c] = sc;
+  shift[c] = (beta ? beta[c] : 0.f) - rmean[c] * sc;
+  if (mean) mean[c] = rmean[c];
+  if (rstd) rstd[c] = r;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// forward: out = act(sum_b scale_b*u_b + shift_b (+ residual))
+struct FwdParams {
+  Branches br;
+  const float* scale;  // [B][C]
+  const float* shift;  // [B][C]
+  const __nv_bfloat16* residual;
+  __nv_bfloat16* out;
+  int M, C, act;
+  float slope;
+};
+__global__ void __launch_bounds__(kThreads) bn_act_fwd_kernel(FwdParams p, Geo g) {
+  const int tx = threadIdx.x % g.cg_t, ty = threadIdx.x / g.cg_t;
+  const int cg = blockIdx.y * g.cg_t + tx;
+  if (ty >= g.rows_t || cg >= g.cg_total) return;
+  float sc[kMaxBranches][8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sh[j] = 0.f;
+#pragma unroll
+  for (int b = 0; b < kMaxBranches; ++b) {
+    if (b < p.br.n) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        sc[b][j] = p.scale[(size_t)b * p.C + cg * 8 + j];
+        sh[j] += p.shift[(size_t)b * p.C + cg * 8 + j];
+      }
+    }
+  }
+  const size_t row_stride = (size_t)gridDim.x * g.rows_t;
+  for (size_t m = (size_t)blockIdx.x * g.rows_t + ty; m < (size_t)p.M; m += row_stride) {
+    const size_t off = m * p.C + cg * 8;
+    float z[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) z[j] = sh[j];
+#pragma unroll
+    for (int b = 0; b < kMaxBranches; ++b) {
+      if (b < p.br.n) {
+        float u[8];
+        load8(p.br.u[b] + off, u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) z[j] = fmaf(sc[b][j], u[j], z[j]);
+      }
+    }
+    if (p.residual) {
+      float r[8];
+      load8(p.residual + off, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) z[j] += r[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) z[j] = act_fwd(p.act, z[j], p.slope);
+    store8(p.out + off, z);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// backward
+struct BwdParams {
+  Branches br;
+  const __nv_bfloat16* dout;
+  const __nv_bfloat16* residual;
+  const float* scale;  // [B][C]
+  const float* shift;
+  const float* mean;
+  const float* rstd;
+  double* sums;        // [1 + B][C]: sum dz, sum dz*xhat_b
+  __nv_bfloat16* du[kMaxBranches];
+  __nv_bfloat16* dres;  // may be null
+  int M, C, act;
+  float slope;
+  int train;  // 1: batch statistics (full BN backward); 0: running statistics (du = scale * dz)
+};
+
+// Per-channel constants of the block's channel slab live in shared memory (keeps the kernels at
+// <= 128 registers so two 256-thread CTAs fit per SM).
+struct SlabConsts {
+  float scale[kMaxBranches][256];
+  float mean[kMaxBranches][256];
+  float rstd[kMaxBranches][256];
+  float shift[256];   // sum over branches
+  float mdz[256];     // mean(dz)            (apply pass)
+  float mdzx[kMaxBranches][256];  // mean(dz * xhat_b) (apply pass)
+};
+
+template <int NB>
+__device__ __forceinline__ void load_slab_consts(SlabConsts& k, const BwdParams& p, const Geo& g, bool with_means) {
+  const int nch = g.cg_t * 8;
+  const float invM = 1.f / (float)p.M;
+  for (int ch = threadIdx.x; ch < nch; ch += kThreads) {
+    const int c = blockIdx.y * nch + ch;
+    float sh = 0.f;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const bool ok = c < p.C;
+      const size_t o = (size_t)b * p.C + c;
+      k.scale[b][ch] = ok ? p.scale[o] : 0.f;
+      k.mean[b][ch] = ok ? p.mean[o] : 0.f;
+      k.rstd[b][ch] = ok ? p.rstd[o] : 0.f;
+      sh += ok ? p.shift[o] : 0.f;
+      k.mdzx[b][ch] = (with_means && p.train && ok) ? (float)(p.sums[(size_t)(1 + b) * p.C + c] * (double)invM) : 0.f;
+    }
+    k.shift[ch] = sh;
+    k.mdz[ch] = (with_means && p.train && c < p.C) ? (float)(p.sums[c] * (double)invM) : 0.f;
+  }
+  __syncthreads();
+}
+
+template <int NB>
+__device__ __forceinline__ void recompute_dz(const BwdParams& p, const SlabConsts& k, int ch0, size_t off,
+                                             float (*u)[8], float* dz) {
+  float z[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) z[j] = k.shift[ch0 + j];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    load8(p.br.u[b] + off, u[b]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) z[j] = fmaf(k.scale[b][ch0 + j], u[b][j], z[j]);
+  }
+  if (p.residual) {
+    float r[8];
+    load8(p.residual + off, r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) z[j] += r[j];
+  }
+  float d[8];
+  load8(p.dout + off, d);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) dz[j] = d[j] * act_grad(p.act, z[j], p.slope);
+}
+
+template <int NB>
+__global__ void __launch_bounds__(kThreads, 2) bn_act_bwd_reduce_kernel(BwdParams p, Geo g) {
+  __shared__ SlabConsts k;
+  __shared__ float red[kThreads * 8];
+  load_slab_consts<NB>(k, p, g, false);
+  const int tx = threadIdx.x % g.cg_t, ty = threadIdx.x / g.cg_t;
+  const int cg = blockIdx.y * g.cg_t + tx;
+  const bool active = ty < g.rows_t && cg < g.cg_total;
+  float acc[1 + NB][8];
+#pragma unroll
+  for (int i = 0; i < 1 + NB; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  if (active) {
+    const size_t row_stride = (size_t)gridDim.x * g.rows_t;
+    for (size_t m = (size_t)blockIdx.x * g.rows_t + ty; m < (size_t)p.M; m += row_stride) {
+      float u[NB > 0 ? NB : 1][8], dz[8];
+      recompute_dz<NB>(p, k, tx * 8, m * p.C + cg * 8, u, dz);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[0][j] += dz[j];
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          acc[1 + b][j] += dz[j] * ((u[b][j] - k.mean[b][tx * 8 + j]) * k.rstd[b][tx * 8 + j]);
+      }
+    }
+  }
+  const int nch = g.cg_t * 8;
+#pragma unroll
+  for (int i = 0; i < 1 + NB; ++i) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[threadIdx.x * 8 + j] = acc[i][j];
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < nch; ch += kThreads) {
+      const int ctx = ch / 8, j = ch % 8;
+      const int gcg = blockIdx.y * g.cg_t + ctx;
+      if (gcg >= g.cg_total) continue;
+      double a = 0.0;
+      for (int r = 0; r < g.rows_t; ++r) a += (double)red[(r * g.cg_t + ctx) * 8 + j];
+      atomicAdd(&p.sums[(size_t)i * p.C + gcg * 8 + j], a);
+    }
+  }
+}
+
+template <int NB>
+__global__ void __launch_bounds__(kThreads, 2) bn_act_bwd_apply_kernel(BwdParams p, Geo g) {
+  __shared__ SlabConsts k;
+  load_slab_consts<NB>(k, p, g, true);
+  const int tx = threadIdx.x % g.cg_t, ty = threadIdx.x / g.cg_t;
+  const int cg = blockIdx.y * g.cg_t + tx;
+  if (ty >= g.rows_t || cg >= g.cg_total) return;
+  const size_t row_stride = (size_t)gridDim.x * g.rows_t;
+  for (size_t m = (size_t)blockIdx.x * g.rows_t + ty; m < (size_t)p.M; m += row_stride) {
+    const size_t off = m * p.C + cg * 8;
+    float u[NB > 0 ? NB : 1][8], dz[8];
+    recompute_dz<NB>(p, k, tx * 8, off, u, dz);
+    if (p.dres) store8(p.dres + off, dz);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      if (p.du[b]) {
+        float d[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int ch = tx * 8 + j;
+          const float xh = (u[b][j] - k.mean[b][ch]) * k.rstd[b][ch];
+          d[j] = k.scale[b][ch] * (dz[j] - k.mdz[ch] - xh * k.mdzx[b][ch]);
+        }
+        store8(p.du[b] + off, d);
+      }
+    }
+  }
+}
+
+// dgamma_b = sum dz*xhat_b, dbeta_b = sum dz  (fp32 outputs from the fp64 sums)
+__global__ void bn_param_grads_kernel(const double* sums, int B, int C, float* dgamma, float* dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (c >= C) return;
+  dgamma[(size_t)b * C + c] = (float)sums[(size_t)(1 + b) * C + c];
+  dbeta[(size_t)b * C + c] = (float)sums[c];
+}
+
+inline dim3 make_grid(const Geo& g, int M, int z) {
+  const int slabs = (g.cg_total + g.cg_t - 1) / g.cg_t;
+  long long row_blocks = ((long long)M + g.rows_t - 1) / g.rows_t;
+  long long cap = (HB_NUM_SMS * 4) / slabs;
+  if (cap < 1) cap = 1;
+  // give every block at least ~8 rows per lane when there is enough work
+  long long want = (row_blocks + 7) / 8;
+  if (want < 1) want = 1;
+  if (want > cap) want = cap;
+  return dim3((unsigned)want, (unsigned)slabs, (unsigned)z);
+}
+
+}  // namespace
+
+extern "C" {
+
+// sums must be zero on entry: double [B][2][C].
+int hb_bn_stats_bf16(const void* u0, const void* u1, const void* u2, int B, int M, int C, double* sums, void* stream) {
+  if (C % 8 != 0 || B < 1 || B > kMaxBranches) return (int)cudaErrorInvalidValue;
+  Branches br{{(const __nv_bfloat16*)u0, (const __nv_bfloat16*)u1, (const __nv_bfloat16*)u2}, B};
+  Geo g = Geo::make(C);
+  bn_stats_kernel<<<make_grid(g, M, B), kThreads, 0, (cudaStream_t)stream>>>(br, M, C, g, sums);
+  HB_LAUNCH_CHECK();
+  return 0;
+}
+
+int hb_bn_finalize(const double* sums, const float* const* gamma, const float* const* beta, float* const* running_mean,
+                   float* const* running_var, float* mean, float* rstd, float* scale, float* shift, int B, int C, int M,
+                   float eps, float momentum, void* stream) {
+  if (B < 1 || B > kMaxBranches) return (int)cudaErrorInvalidValue;
+  FinalizeParams p{};
+  p.sums = sums;
+  for (int b = 0; b < B; ++b) {
+    p.gamma[b] = gamma ? gamma[b] : nullptr;
+    p.beta[b] = beta ? beta[b] : nullptr;
+    p.running_mean[b] = running_mean ? running_mean[b] : nullptr;
+    p.running_var[b] = running_var ? running_var[b] : nullptr;
+  }
+  p.mean = mean; p.rstd = rstd; p.scale = scale; p.shift = shift;
+  p.B = B; p.C = C; p.M = M; p.eps = eps; p.momentum = momentum;
+  bn_finalize_kernel<<<dim3((C + 127) / 128, B), 128, 0, (cudaStream_t)stream>>>(p);
+  HB_LAUNCH_CHECK();
+  return 0;
+}
+
+int hb_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                      float eps, int C, float* scale, float* shift, float* mean, float* rstd, void* stream) {
+  bn_eval_affine_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gamma, beta, running_mean, running_var, eps,
+                                                                            C, scale, shift, mean, rstd);
+  HB_LAUNCH_CHECK();
+  return 0;
+}
+
+int hb_bn_act_fwd_bf16(const void* u0, const void* u1, const void* u2, int B, const float* scale, const float* shift,
+                       const void* residual, void* out, int M, int C, int act, float slope, void* stream) {
+  if (C % 8 != 0 || B < 0 || B > kMaxBranches) return (int)cudaErrorInvalidValue;
+  FwdParams p{};
+  p.br = Branches{{(const __nv_bfloat16*)u0, (const __nv_bfloat16*)u1, (const __nv_bfloat16*)u2}, B};
+  p.scale = scale; p.shift = shift; p.residual = (const __nv_bfloat16*)residual; p.out = (__nv_bfloat16*)out;
+  p.M = M; p.C = C; p.act = act; p.slope = slope;
+  Geo g = Geo::make(C);
+  bn_act_fwd_kernel<<<make_grid(g, M, 1), kThreads, 0, (cudaStream_t)stream>>>(p, g);
+  HB_LAUNCH_CHECK();
+  return 0;
+}
+
+// Backward. sums: double [1+B][C], zero on entry (train=1). du_b / dres may be NULL when not needed.
+// dgamma/dbeta: fp32 [B][C] outputs (optional; when given the reduction pass also runs for train=0).
+int hb_bn_act_bwd_bf16(const void* dout, const void* u0, const void* u1, const void* u2, int B, const float* scale,
+                       const float* shift, const float* mean, const float* rstd, const void* residual, double* sums,
+                       void* du0, void* du1, void* du2, void* dres, float* dgamma, float* dbeta, int M, int C, int act,
+                       float slope, int train, void* stream) {
+  if (C % 8 != 0 || B < 0 || B > kMaxBranches) return (int)cudaErrorInvalidValue;
+  BwdParams p{};
+  p.br = Branches{{(const __nv_bfloat16*)u0, (const __nv_bfloat16*)u1, (const __nv_bfloat16*)u2}, B};
+  p.dout = (const __nv_bfloat16*)dout; p.residual = (const __nv_bfloat16*)residual;
+  p.scale = scale; p.shift = shift; p.mean = mean; p.rstd = rstd; p.sums = sums;
+  p.du[0] = (__nv_bfloat16*)du0; p.du[1] = (__nv_bfloat16*)du1; p.du[2] = (__nv_bfloat16*)du2;
+  p.dres = (__nv_bfloat16*)dres;
+  p.M = M; p.C = C; p.act = act; p.slope = slope; p.train = train;
+  Geo g = Geo::make(C);
+  cudaStream_t st = (cudaStream_t)stream;
+  const dim3 grid = make_grid(g, M, 1);
+  if (train || (dgamma && dbeta)) {
+    switch (B) {
+      case 0: bn_act_bwd_reduce_kernel<0><<<grid, kThreads, 0, st>>>(p, g); break;
+      case 1: bn_act_bwd_reduce_kernel<1><<<grid, kThreads, 0, st>>>(p, g); break;
+      case 2: bn_act_bwd_reduce_kernel<2><<<grid, kThreads, 0, st>>>(p, g); break;
+      default: bn_act_bwd_reduce_kernel<3><<<grid, kThreads, 0, st>>>(p, g); break;
+    }
+    HB_LAUNCH_CHECK();
+    if (dgamma && dbeta && B > 0) {
+      bn_param_grads_kernel<<<dim3((C + 127) / 128, B), 128, 0, st>>>(sums, B, C, dgamma, dbeta);
+      HB_LAUNCH_CHECK();
+    }
+  }
+  switch (B) {
+    case 0: bn_act_bwd_apply_kernel<0><<<grid, kThreads, 0, st>>>(p, g); break;
+    case 1: bn_act_bwd_apply_kernel<1><<<grid, kThreads, 0, st>>>(p, g); break;
+    case 2: bn_act_bwd_apply_kernel<2><<<grid, kThreads, 0, st>>>(p, g); break;
+    default: bn_act_bwd_apply_kernel<3><<<grid, kThreads, 0, st>>>(p, g); break;
+  }
+  HB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

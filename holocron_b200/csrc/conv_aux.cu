@@ -1,0 +1,191 @@
+// Small layout / helper kernels around the tensor-core convolutions (all HBM streaming passes):
+//   * filter packing: fp32 KRSC master weights -> bf16 KRSC (channel padded) and the flipped+transposed
+//     bf16 filter used by the data-gradient pass,
+//   * zero insertion (stride-s transposed convolution input),
+//   * NCHW fp32/bf16 image -> NHWC bf16 with channel padding (network input),
+//   * global average pooling forward / backward over NHWC (reference holocron/nn/modules/downsample.py:58-74).
+#include "common.cuh"
+
+namespace {
+
+using namespace hb;
+
+// w: [Cout][R][S][Cin] fp32.  wf: [Cout][R][S][CinP] bf16 (zero padded).  wd: [CinD][R][S][CoutP] bf16 with
+// wd[ci][r][s][co] = w[co][R-1-r][S-1-s][ci] (rows ci >= Cin and columns co >= Cout are zero).
+__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
+                                    __nv_bfloat16* __restrict__ wd, int Cout, int Cin, int R, int S, int CinP, int CinD,
+                                    int CoutP) {
+  const size_t nf = (size_t)Cout * R * S * CinP;
+  const size_t nd = wd ? (size_t)CinD * R * S * CoutP : 0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nf + nd; i += stride) {
+    if (i < nf) {
+      const int ci = i % CinP;
+      size_t t = i / CinP;
+      const int s = t % S; t /= S;
+      const int r = t % R;
+      const int co = t / R;
+      const float v = ci < Cin ? w[(((size_t)co * R + r) * S + s) * Cin + ci] : 0.f;
+      wf[i] = __float2bfloat16_rn(v);
+    } else {
+      const size_t k = i - nf;
+      const int co = k % CoutP;
+      size_t t = k / CoutP;
+      const int s = t % S; t /= S;
+      const int r = t % R;
+      const int ci = t / R;
+      const float v = (co < Cout && ci < Cin) ? w[(((size_t)co * R + (R - 1 - r)) * S + (S - 1 - s)) * Cin + ci] : 0.f;
+      wd[k] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+// y[n, sp*p, sp*q, :] = x[n, p, q, :]; everything else zero. One thread per 16-byte channel vector of y.
+__global__ void zero_insert_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int Hi,
+                                   int Wi, int Ho, int Wo, int C, int sp) {
+  const int cv = C / 8;
+  const size_t total = (size_t)N * Ho * Wo * cv;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c = i % cv;
+    size_t t = i / cv;
+    const int w = t % Wo; t /= Wo;
+    const int h = t % Ho;
+    const int n = t / Ho;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (h % sp == 0 && w % sp == 0) {
+      const int p = h / sp, q = w / sp;
+      if (p < Hi && q < Wi) v = *reinterpret_cast<const uint4*>(x + (((size_t)n * Hi + p) * Wi + q) * C + c * 8);
+    }
+    *reinterpret_cast<uint4*>(y + i * 8) = v;
+  }
+}
+
+template <typename T>
+__global__ void nchw_to_nhwc_pad_kernel(const T* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int C, int HW,
+                                        int CP) {
+  // one thread per output pixel: reads C strided planes (coalesced across threads), writes CP contiguous bf16
+  const size_t total = (size_t)N * HW;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const size_t n = i / HW, p = i % HW;
+    for (int c0 = 0; c0 < CP; c0 += 8) {
+      Vec16<__nv_bfloat16> o;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = c0 + j;
+        o.v[j] = c < C ? from_f<__nv_bfloat16>(to_f(x[(n * C + c) * HW + p])) : __float2bfloat16_rn(0.f);
+      }
+      st16(y + i * CP + c0, o);
+    }
+  }
+}
+
+// GAP forward: x [N, HW, C] bf16 -> y [N, C] (fp32 accumulation, output bf16). One warp-free design:
+// thread owns 8 channels of one image and walks the HW rows.
+__global__ void gap_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int HW, int C) {
+  const int cv = C / 8;
+  const size_t total = (size_t)N * cv;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const size_t n = i / cv, c = i % cv;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  const __nv_bfloat16* p = x + n * HW * C + c * 8;
+  for (int r = 0; r < HW; ++r) {
+    Vec16<__nv_bfloat16> v = ld16(p + (size_t)r * C);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += __bfloat162float(v.v[j]);
+  }
+  Vec16<__nv_bfloat16> o;
+  const float inv = 1.f / (float)HW;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o.v[j] = __float2bfloat16_rn(acc[j] * inv);
+  st16(y + n * C + c * 8, o);
+}
+
+// GAP backward: dx[n, r, c] = dy[n, c] / HW
+__global__ void gap_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int N, int HW, int C) {
+  const int cv = C / 8;
+  const size_t total = (size_t)N * HW * cv;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const float inv = 1.f / (float)HW;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const size_t c = i % cv;
+    const size_t n = i / ((size_t)HW * cv);
+    Vec16<__nv_bfloat16> v = ld16(dy + n * C + c * 8), o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o.v[j] = __float2bfloat16_rn(__bfloat162float(v.v[j]) * inv);
+    st16(dx + i * 8, o);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int hb_pack_conv_weights(const float* w, void* wf, void* wd, int Cout, int Cin, int R, int S, int CinP, int CinD,
+                         int CoutP, void* stream) {
+  const size_t n = (size_t)Cout * R * S * CinP + (wd ? (size_t)CinD * R * S * CoutP : 0);
+  if (n == 0) return 0;
+  pack_weights_kernel<<<stream_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)wf, (__nv_bfloat16*)wd,
+                                                                             Cout, Cin, R, S, CinP, CinD, CoutP);
+  HB_LAUNCH_CHECK();
+  return 0;
+}
+
+int hb_zero_insert_bf16(const void* x, void* y, int N, int Hi, int Wi, int Ho, int Wo, int C, int sp, void* stream) {
+  if (C % 8 != 0) return (int)cudaErrorInvalidValue;
+  const size_t n = (size_t)N * Ho * Wo * (C / 8);
+  if (n == 0) return 0;
+  zero_insert_kernel<<<stream_grid(n, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y,
+                                                                            N, Hi, Wi, Ho, Wo, C, sp);
+  HB_LAUNCH_CHECK();
+  return 0;
+}
+
+int hb_nchw_to_nhwc_pad_bf16(const void* x, void* y, int N, int C, int H, int W, int CP, int dtype, void* stream) {
+  if (CP % 8 != 0 || CP < C) return (int)cudaErrorInvalidValue;
+  const size_t n = (size_t)N * H * W;
+  if (n == 0) return 0;
+  const int grid = stream_grid(n, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case HB_DTYPE_F32:
+      nchw_to_nhwc_pad_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (__nv_bfloat16*)y, N, C, H * W, CP);
+      break;
+    case HB_DTYPE_BF16:
+      nchw_to_nhwc_pad_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, C,
+                                                                   H * W, CP);
+      break;
+    case HB_DTYPE_F16:
+      nchw_to_nhwc_pad_kernel<__half><<<grid, 256, 0, st>>>((const __half*)x, (__nv_bfloat16*)y, N, C, H * W, CP);
+      break;
+    default: return (int)cudaErrorInvalidValue;
+  }
+  HB_LAUNCH_CHECK();
+  return 0;
+}
+
+int hb_gap_fwd_bf16(const void* x, void* y, int N, int HW, int C, void* stream) {
+  if (C % 8 != 0) return (int)cudaErrorInvalidValue;
+  const size_t n = (size_t)N * (C / 8);
+  if (n == 0) return 0;
+  gap_fwd_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x,
+                                                                                (__nv_bfloat16*)y, N, HW, C);
+  HB_LAUNCH_CHECK();
+  return 0;
+}
+
+int hb_gap_bwd_bf16(const void* dy, void* dx, int N, int HW, int C, void* stream) {
+  if (C % 8 != 0) return (int)cudaErrorInvalidValue;
+  const size_t n = (size_t)N * HW * (C / 8);
+  if (n == 0) return 0;
+  gap_bwd_kernel<<<stream_grid(n, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, N,
+                                                                        HW, C);
+  HB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

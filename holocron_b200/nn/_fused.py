@@ -1,0 +1,327 @@
+"""Autograd bindings of the tensor-core convolution and the fused BatchNorm/branch-sum/activation kernels.
+
+Activations travel between these ops as NCHW-logical ``bfloat16`` tensors in ``torch.channels_last`` memory format
+(physically NHWC, which is what the TMA descriptors of the kernels address). Parameters stay fp32 with the
+reference's shapes (``Cout x Cin x kh x kw``) so ``state_dict`` is interchangeable with the reference's modules.
+
+Reference call sites being replaced: ``nn.Conv2d`` / ``nn.BatchNorm2d`` / activation modules emitted by
+``holocron.models.utils.conv_sequence`` (holocron/models/utils.py:28-86) and ``RepBlock.forward``
+(holocron/models/classification/repvgg.py:71-73).
+"""
+import ctypes
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor, nn
+
+from .._lib import check, lib, ptr, require_cuda, stream_ptr
+
+ACT_NONE, ACT_RELU, ACT_RELU6, ACT_SILU, ACT_LEAKY, ACT_MISH, ACT_HARDMISH = range(7)
+
+_c_float = ctypes.c_float
+_VP3 = ctypes.c_void_p * 3
+
+
+def act_code(act: Optional[nn.Module]) -> Tuple[int, float]:
+    """Maps an activation module instance to the kernels' activation code (+ negative slope)."""
+    if act is None or isinstance(act, nn.Identity):
+        return ACT_NONE, 0.0
+    if isinstance(act, nn.ReLU6):
+        return ACT_RELU6, 0.0
+    if isinstance(act, nn.ReLU):
+        return ACT_RELU, 0.0
+    if isinstance(act, nn.SiLU):
+        return ACT_SILU, 0.0
+    if isinstance(act, nn.LeakyReLU):
+        return ACT_LEAKY, float(act.negative_slope)
+    if isinstance(act, nn.Mish):
+        return ACT_MISH, 0.0
+    if type(act).__name__ == "HardMish":
+        return ACT_HARDMISH, 0.0
+    raise NotImplementedError(f"no fused kernel for activation {type(act).__name__}")
+
+
+def round_up(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+def to_channels_last_bf16(x: Tensor, c_pad: Optional[int] = None) -> Tensor:
+    """NCHW-logical tensor of any float dtype / layout -> bf16 channels_last, channels optionally zero-padded.
+    Already-conforming tensors are returned as is (no copy)."""
+    require_cuda(x)
+    n, c, h, w = x.shape
+    cp = c if c_pad is None else c_pad
+    if cp == c and x.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last):
+        return x
+    if x.is_contiguous() and x.dtype in (torch.float32, torch.bfloat16, torch.float16) and (cp != c or c < 8):
+        from .._lib import dtype_code
+        out = torch.empty((n, cp, h, w), device=x.device, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        check(lib().hb_nchw_to_nhwc_pad_bf16(ptr(x), ptr(out), n, c, h, w, cp, dtype_code(x), stream_ptr()),
+              "hb_nchw_to_nhwc_pad_bf16")
+        return out
+    y = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    if cp != c:
+        out = torch.zeros((n, cp, h, w), device=x.device, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        out[:, :c] = y
+        return out
+    return y
+
+
+def _empty_cl(n: int, c: int, h: int, w: int, device, dtype=torch.bfloat16) -> Tensor:
+    return torch.empty((n, h, w, c), device=device, dtype=dtype).permute(0, 3, 1, 2)
+
+
+# ------------------------------------------------------------------------------------------------------
+# filter packing cache: fp32 master (any layout) -> bf16 KRSC for fprop, flipped+transposed bf16 for dgrad
+class PackedFilter:
+    __slots__ = ("wf", "wd", "key", "cin_p", "cout", "cin", "r", "s")
+
+
+_pack_cache = {}
+
+
+def pack_filter(weight: Tensor, need_dgrad: bool) -> PackedFilter:
+    cout, cin, r, s = weight.shape
+    key = (weight.data_ptr(), weight._version, need_dgrad, tuple(weight.stride()))
+    ent = _pack_cache.get(id(weight))
+    if ent is not None and ent.key == key:
+        return ent
+    cin_p = round_up(cin, 8)
+    w = weight.detach()
+    if w.dtype != torch.float32:
+        w = w.float()
+    # physical KRSC fp32 view (zero-copy when the parameter is stored channels_last)
+    w_krsc = w.permute(0, 2, 3, 1)
+    if not w_krsc.is_contiguous():
+        w_krsc = w_krsc.contiguous()
+    ent = PackedFilter()
+    ent.key, ent.cin_p, ent.cout, ent.cin, ent.r, ent.s = key, cin_p, cout, cin, r, s
+    ent.wf = torch.empty((cout, r, s, cin_p), device=w.device, dtype=torch.bfloat16)
+    cout_p = round_up(cout, 8)
+    cin_d = round_up(cin, 16)
+    ent.wd = torch.empty((cin_d, r, s, cout_p), device=w.device, dtype=torch.bfloat16) if need_dgrad else None
+    check(lib().hb_pack_conv_weights(ptr(w_krsc), ptr(ent.wf), ptr(ent.wd), cout, cin, r, s, cin_p, cin_d, cout_p,
+                                     stream_ptr()), "hb_pack_conv_weights")
+    _pack_cache[id(weight)] = ent
+    return ent
+
+
+def conv_out_size(h: int, k: int, stride: int, pad: int, dil: int) -> int:
+    return (h + 2 * pad - dil * (k - 1) - 1) // stride + 1
+
+
+def conv2d_forward_raw(x: Tensor, wf: Tensor, cout: int, r: int, s: int, stride: int, pad: int, dil: int,
+                       bias: Optional[Tensor] = None, residual: Optional[Tensor] = None, act: int = ACT_NONE) -> Tensor:
+    """x: bf16 channels_last [N, Cin_p, H, W]; wf: bf16 [Cout, R, S, Cin_p] -> bf16 channels_last [N, Cout, Ho, Wo]."""
+    n, cin_p, h, w = x.shape
+    ho, wo = conv_out_size(h, r, stride, pad, dil), conv_out_size(w, s, stride, pad, dil)
+    y = _empty_cl(n, cout, ho, wo, x.device)
+    check(lib().hb_conv2d_fprop_bf16(ptr(x), ptr(wf), ptr(y), ptr(bias), ptr(residual), n, h, w, cin_p, cout, r, s,
+                                     stride, pad, dil, act, 0, stream_ptr()), "hb_conv2d_fprop_bf16")
+    return y
+
+
+class _Conv2dFn(torch.autograd.Function):
+    """y = conv2d(x, weight) (+ bias) on the tcgen05 implicit-GEMM kernels; backward = dgrad + wgrad kernels."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, weight: Tensor, bias: Optional[Tensor], stride: int, pad: int, dil: int) -> Tensor:
+        cout, cin, r, s = weight.shape
+        if cout % 16 != 0:
+            raise NotImplementedError("tensor-core conv needs out_channels % 16 == 0 (pad the layer)")
+        need_dx = ctx.needs_input_grad[0]
+        pk = pack_filter(weight, need_dx)
+        xb = to_channels_last_bf16(x, pk.cin_p)
+        bias_f = None if bias is None else bias.detach().float().contiguous()
+        y = conv2d_forward_raw(xb, pk.wf, cout, r, s, stride, pad, dil, bias_f)
+        ctx.save_for_backward(xb, weight)
+        ctx.cfg = (stride, pad, dil, pk.wd, bias is not None, x.shape[1])
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        xb, weight = ctx.saved_tensors
+        stride, pad, dil, wd, has_bias, cin_logical = ctx.cfg
+        cout, cin, r, s = weight.shape
+        n, cin_p, h, w = xb.shape
+        dyb = to_channels_last_bf16(dy)
+        ho, wo = dyb.shape[2], dyb.shape[3]
+        L = lib()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            if dil != 1:
+                raise NotImplementedError("dgrad with dilation > 1")
+            cin_d, cout_p = wd.shape[0], wd.shape[3]
+            if cout_p != cout:
+                raise NotImplementedError("dgrad needs out_channels % 8 == 0")
+            src = dyb
+            if stride > 1:
+                src = _empty_cl(n, cout, h, w, dyb.device)
+                check(L.hb_zero_insert_bf16(ptr(dyb), ptr(src), n, ho, wo, h, w, cout, stride, stream_ptr()),
+                      "hb_zero_insert_bf16")
+            dxp = _empty_cl(n, cin_d, h, w, dyb.device)
+            check(L.hb_conv2d_fprop_bf16(ptr(src), ptr(wd), ptr(dxp), ptr(None), ptr(None), n, h, w, cout, cin_d, r, s, 1,
+                                         (r - 1) * dil - pad, 1, ACT_NONE, 0, stream_ptr()), "hb_conv2d_fprop_bf16[dgrad]")
+            dx = dxp if cin_d == cin_logical else dxp[:, :cin_logical]
+        if ctx.needs_input_grad[1]:
+            dwp = torch.empty((cout, r, s, cin_p), device=dyb.device, dtype=torch.float32)
+            check(L.hb_conv2d_wgrad_bf16(ptr(xb), ptr(dyb), ptr(dwp), n, h, w, cin_p, cout, r, s, stride, pad, dil, 0,
+                                         stream_ptr()), "hb_conv2d_wgrad_bf16")
+            dw = dwp.permute(0, 3, 1, 2)
+            if cin_p != cin:
+                dw = dw[:, :cin].contiguous(memory_format=torch.channels_last)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = dyb.float().sum((0, 2, 3))
+        return dx, dw, db, None, None, None
+
+
+def conv2d(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, stride: int = 1, padding: int = 0,
+           dilation: int = 1) -> Tensor:
+    """Dense (groups=1) 2-D convolution on the sm_100a tensor cores; returns bf16 channels_last."""
+    require_cuda(x, weight)
+    return _Conv2dFn.apply(x, weight, bias, int(stride), int(padding), int(dilation))
+
+
+# ------------------------------------------------------------------------------------------------------
+class BNBranch:
+    """Non-tensor view of one BatchNorm2d's buffers/hyper-parameters handed to the fused function."""
+    __slots__ = ("running_mean", "running_var", "eps", "momentum", "num_batches_tracked")
+
+    def __init__(self, bn: nn.BatchNorm2d) -> None:
+        self.running_mean = bn.running_mean
+        self.running_var = bn.running_var
+        self.eps = bn.eps
+        self.momentum = bn.momentum
+        self.num_batches_tracked = bn.num_batches_tracked
+
+
+def _arr3(ts: Sequence[Optional[Tensor]]):
+    vals = [0 if t is None else t.data_ptr() for t in ts]
+    return _VP3(*(vals + [0] * (3 - len(vals))))
+
+
+class _BNActFn(torch.autograd.Function):
+    """out = act(sum_b BN_b(u_b) [+ residual]); training (batch statistics) or eval (running statistics)."""
+
+    @staticmethod
+    def forward(ctx, cfg, *tensors: Tensor) -> Tensor:
+        branches, act, slope, training, has_res = cfg
+        nb = len(branches)
+        us = [to_channels_last_bf16(t) for t in tensors[:nb]]
+        gammas = tensors[nb:2 * nb]
+        betas = tensors[2 * nb:3 * nb]
+        res = to_channels_last_bf16(tensors[3 * nb]) if has_res else None
+        n, c, h, w = us[0].shape
+        if c % 8 != 0:
+            raise NotImplementedError("fused BN kernels need channels % 8 == 0")
+        m = n * h * w
+        dev = us[0].device
+        L = lib()
+        stats = torch.empty((4, nb, c), device=dev, dtype=torch.float32)  # mean, rstd, scale, shift
+        mean, rstd, scale, shift = stats[0], stats[1], stats[2], stats[3]
+        g32 = [g.detach().float() for g in gammas]
+        b32 = [b.detach().float() for b in betas]
+        up = [ptr(us[i]) if i < nb else ptr(None) for i in range(3)]
+        if training:
+            sums = torch.zeros((nb, 2, c), device=dev, dtype=torch.float64)
+            check(L.hb_bn_stats_bf16(up[0], up[1], up[2], nb, m, c, ptr(sums), stream_ptr()), "hb_bn_stats_bf16")
+            eps = branches[0].eps
+            mom = branches[0].momentum
+            if any(b.eps != eps or b.momentum != mom for b in branches):
+                raise NotImplementedError("branches with different eps/momentum")
+            if mom is None:
+                raise NotImplementedError("cumulative moving average (momentum=None)")
+            track = branches[0].running_mean is not None
+            check(L.hb_bn_finalize(ptr(sums), _arr3(g32), _arr3(b32),
+                                   _arr3([b.running_mean for b in branches]) if track else None,
+                                   _arr3([b.running_var for b in branches]) if track else None,
+                                   ptr(mean), ptr(rstd), ptr(scale), ptr(shift), nb, c, m, _c_float(eps), _c_float(mom),
+                                   stream_ptr()), "hb_bn_finalize")
+            for b in branches:
+                if b.num_batches_tracked is not None:
+                    b.num_batches_tracked += 1
+        else:
+            for i, b in enumerate(branches):
+                check(L.hb_bn_eval_affine(ptr(g32[i]), ptr(b32[i]), ptr(b.running_mean), ptr(b.running_var),
+                                          _c_float(b.eps), c, ptr(scale[i]), ptr(shift[i]), ptr(mean[i]), ptr(rstd[i]),
+                                          stream_ptr()), "hb_bn_eval_affine")
+        out = _empty_cl(n, c, h, w, dev)
+        check(L.hb_bn_act_fwd_bf16(up[0], up[1], up[2], nb, ptr(scale), ptr(shift), ptr(res), ptr(out), m, c, act,
+                                   _c_float(slope), stream_ptr()), "hb_bn_act_fwd_bf16")
+        ctx.save_for_backward(stats, *us, *([res] if has_res else []))
+        ctx.cfg = (nb, act, slope, training, has_res)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout: Tensor):
+        nb, act, slope, training, has_res = ctx.cfg
+        saved = ctx.saved_tensors
+        stats, us = saved[0], saved[1:1 + nb]
+        res = saved[1 + nb] if has_res else None
+        mean, rstd, scale, shift = stats[0], stats[1], stats[2], stats[3]
+        n, c, h, w = us[0].shape
+        m = n * h * w
+        dev = dout.device
+        dob = to_channels_last_bf16(dout)
+        L = lib()
+        need_u = [ctx.needs_input_grad[1 + i] for i in range(nb)]
+        need_gb = any(ctx.needs_input_grad[1 + nb:1 + 3 * nb])
+        need_res = has_res and ctx.needs_input_grad[1 + 3 * nb]
+        dus = [_empty_cl(n, c, h, w, dev) if need_u[i] else None for i in range(nb)]
+        dres = _empty_cl(n, c, h, w, dev) if need_res else None
+        sums = torch.zeros((1 + nb, c), device=dev, dtype=torch.float64)
+        dgb = torch.empty((2, nb, c), device=dev, dtype=torch.float32) if need_gb else None
+        up = [ptr(us[i]) if i < nb else ptr(None) for i in range(3)]
+        dup = [ptr(dus[i]) if i < nb else ptr(None) for i in range(3)]
+        check(L.hb_bn_act_bwd_bf16(ptr(dob), up[0], up[1], up[2], nb, ptr(scale), ptr(shift), ptr(mean), ptr(rstd),
+                                   ptr(res), ptr(sums), dup[0], dup[1], dup[2], ptr(dres),
+                                   ptr(dgb[0]) if need_gb else ptr(None), ptr(dgb[1]) if need_gb else ptr(None), m, c,
+                                   act, _c_float(slope), 1 if training else 0, stream_ptr()), "hb_bn_act_bwd_bf16")
+        grads: List[Optional[Tensor]] = [None]
+        grads += dus
+        grads += [dgb[0][i] if need_gb else None for i in range(nb)]
+        grads += [dgb[1][i] if need_gb else None for i in range(nb)]
+        if has_res:
+            grads.append(dres)
+        return tuple(grads)
+
+
+def bn_act(us: Sequence[Tensor], bns: Sequence[nn.BatchNorm2d], act: int = ACT_NONE, slope: float = 0.0,
+           residual: Optional[Tensor] = None, training: Optional[bool] = None) -> Tensor:
+    """act(sum_b BatchNorm_b(u_b) + residual) as one fused pass (plus one statistics pass in training)."""
+    if not 1 <= len(us) <= 3 or len(us) != len(bns):
+        raise ValueError("between 1 and 3 (input, BatchNorm2d) pairs are supported")
+    require_cuda(*us)
+    if training is None:
+        training = bns[0].training
+    use_batch_stats = training or bns[0].running_mean is None
+    cfg = ([BNBranch(b) for b in bns], int(act), float(slope), bool(use_batch_stats), residual is not None)
+    args = list(us) + [b.weight for b in bns] + [b.bias for b in bns]
+    if residual is not None:
+        args.append(residual)
+    return _BNActFn.apply(cfg, *args)
+
+
+# ------------------------------------------------------------------------------------------------------
+class _GapFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: Tensor) -> Tensor:
+        xb = to_channels_last_bf16(x)
+        n, c, h, w = xb.shape
+        y = torch.empty((n, c), device=xb.device, dtype=torch.bfloat16)
+        check(lib().hb_gap_fwd_bf16(ptr(xb), ptr(y), n, h * w, c, stream_ptr()), "hb_gap_fwd_bf16")
+        ctx.shape = (n, c, h, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        n, c, h, w = ctx.shape
+        dyb = dy.to(torch.bfloat16).contiguous()
+        dx = _empty_cl(n, c, h, w, dy.device)
+        check(lib().hb_gap_bwd_bf16(ptr(dyb), ptr(dx), n, h * w, c, stream_ptr()), "hb_gap_bwd_bf16")
+        return dx
+
+
+def global_avg_pool_flat(x: Tensor) -> Tensor:
+    """(N, C, H, W) -> (N, C) mean over space (bf16 channels_last in, bf16 out; fp32 accumulation)."""
+    return _GapFn.apply(x)
