@@ -24,6 +24,45 @@ def lib_path() -> Path:
     return _LIB_PATH
 
 
+# Argument signatures of every entry point declared in include/holocron_b200.h
+# (p = pointer, i = int, z = size_t, q = long long, f = float). Kept in sync with the header by tests/test_cabi.py.
+SIGNATURES = {
+    "hb_hard_mish_fwd": "ppzip",
+    "hb_hard_mish_bwd": "pppzip",
+    "hb_nl_relu_fwd": "ppzfip",
+    "hb_nl_relu_bwd": "pppzfip",
+    "hb_nl_relu_bwd_from_out": "pppzfip",
+    "hb_conv2d_fprop_bf16": "ppppp" + "i" * 12 + "p",
+    "hb_conv2d_wgrad_bf16": "ppp" + "i" * 11 + "p",
+    "hb_pack_conv_weights": "ppp" + "i" * 7 + "p",
+    "hb_zero_insert_bf16": "pp" + "i" * 7 + "p",
+    "hb_nchw_to_nhwc_pad_bf16": "pp" + "i" * 6 + "p",
+    "hb_bn_stats_bf16": "pppiiipp",
+    "hb_bn_finalize": "ppppp" + "pppp" + "iiiffp",
+    "hb_bn_eval_affine": "ppppfippppp",
+    "hb_bn_act_fwd_bf16": "pppipppp" + "iiifp",
+    "hb_bn_act_bwd_bf16": "ppppi" + "pppppp" + "pppppp" + "iiifip",
+    "hb_gap_fwd_bf16": "ppiiip",
+    "hb_gap_bwd_bf16": "ppiiip",
+    "hb_box_pairwise": "pppiiip",
+    "hb_box_degenerate": "pipp",
+    "hb_box_pairwise_bwd": "pppppiiip",
+    "hb_loss_max_partials": "",
+    "hb_cls_loss_hard_fwd": "pppppp" + "iiiiiffip",
+    "hb_cls_loss_hard_bwd": "pppppp" + "iiiiiffiip",
+    "hb_poly_soft_fwd": "pppppp" + "iiiifip",
+    "hb_poly_soft_bwd": "ppppp" + "iiiifiip",
+    "hb_dice_fwd": "pppppp" + "iiqffip",
+    "hb_dice_bwd": "pppp" + "iiqip",
+    "hb_optim_chunk_elems": "",
+    "hb_adabelief_step": "ppifffffiipp",
+    "hb_lamb_step": "ppiifffffffpp",
+    "hb_tadam_step": "ppiifffffifipp" + "p",
+    "hb_step_increment": "pp",
+}
+_CTYPE = {"p": ctypes.c_void_p, "i": ctypes.c_int, "z": ctypes.c_size_t, "f": ctypes.c_float, "q": ctypes.c_longlong}
+
+
 def lib() -> ctypes.CDLL:
     """Returns the loaded C-ABI library, loading it on first use. Fails loudly if it has not been built."""
     global _lib
@@ -33,7 +72,12 @@ def lib() -> ctypes.CDLL:
                 f"{_LIB_PATH} is missing: build it with `python -m holocron_b200.csrc.build` "
                 "(there is no CPU / PyTorch fallback for the holocron_b200 kernels)"
             )
-        _lib = ctypes.CDLL(os.fspath(_LIB_PATH))
+        handle = ctypes.CDLL(os.fspath(_LIB_PATH))
+        for name, sig in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError here = the library is stale: rebuild it
+            fn.argtypes = [_CTYPE[c] for c in sig]
+            fn.restype = ctypes.c_int
+        _lib = handle
     return _lib
 
 

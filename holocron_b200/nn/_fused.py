@@ -182,6 +182,27 @@ def conv2d(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, stride: int
     return _Conv2dFn.apply(x, weight, bias, int(stride), int(padding), int(dilation))
 
 
+def conv2d_bias_act(x: Tensor, weight: Tensor, bias: Optional[Tensor], stride: int, padding: int, act: int = ACT_NONE,
+                    slope: float = 0.0) -> Tensor:
+    """conv + bias + activation. Without autograd (inference) bias and ReLU are fused in the conv epilogue;
+    with autograd the activation is applied by the fused pointwise pass."""
+    require_cuda(x, weight)
+    needs_grad = torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or
+                                              (bias is not None and bias.requires_grad))
+    if not needs_grad and act in (ACT_NONE, ACT_RELU):
+        cout, cin, r, s = weight.shape
+        if cout % 16 != 0:
+            raise NotImplementedError("tensor-core conv needs out_channels % 16 == 0 (pad the layer)")
+        pk = pack_filter(weight, False)
+        xb = to_channels_last_bf16(x, pk.cin_p)
+        bias_f = None if bias is None else bias.detach().float().contiguous()
+        return conv2d_forward_raw(xb, pk.wf, cout, r, s, stride, padding, 1, bias_f, None, act)
+    y = _Conv2dFn.apply(x, weight, bias, int(stride), int(padding), 1)
+    if act == ACT_NONE:
+        return y
+    return act_only(y, act, slope)
+
+
 # ------------------------------------------------------------------------------------------------------
 class BNBranch:
     """Non-tensor view of one BatchNorm2d's buffers/hyper-parameters handed to the fused function."""
@@ -211,18 +232,20 @@ class _BNActFn(torch.autograd.Function):
         gammas = tensors[nb:2 * nb]
         betas = tensors[2 * nb:3 * nb]
         res = to_channels_last_bf16(tensors[3 * nb]) if has_res else None
-        n, c, h, w = us[0].shape
+        n, c, h, w = us[0].shape if nb else res.shape
         if c % 8 != 0:
             raise NotImplementedError("fused BN kernels need channels % 8 == 0")
         m = n * h * w
-        dev = us[0].device
+        dev = us[0].device if nb else res.device
         L = lib()
-        stats = torch.empty((4, nb, c), device=dev, dtype=torch.float32)  # mean, rstd, scale, shift
+        stats = torch.empty((4, max(nb, 1), c), device=dev, dtype=torch.float32)  # mean, rstd, scale, shift
         mean, rstd, scale, shift = stats[0], stats[1], stats[2], stats[3]
         g32 = [g.detach().float() for g in gammas]
         b32 = [b.detach().float() for b in betas]
         up = [ptr(us[i]) if i < nb else ptr(None) for i in range(3)]
-        if training:
+        if nb == 0:
+            pass
+        elif training:
             sums = torch.zeros((nb, 2, c), device=dev, dtype=torch.float64)
             check(L.hb_bn_stats_bf16(up[0], up[1], up[2], nb, m, c, ptr(sums), stream_ptr()), "hb_bn_stats_bf16")
             eps = branches[0].eps
@@ -259,7 +282,7 @@ class _BNActFn(torch.autograd.Function):
         stats, us = saved[0], saved[1:1 + nb]
         res = saved[1 + nb] if has_res else None
         mean, rstd, scale, shift = stats[0], stats[1], stats[2], stats[3]
-        n, c, h, w = us[0].shape
+        n, c, h, w = us[0].shape if nb else res.shape
         m = n * h * w
         dev = dout.device
         dob = to_channels_last_bf16(dout)
@@ -300,6 +323,12 @@ def bn_act(us: Sequence[Tensor], bns: Sequence[nn.BatchNorm2d], act: int = ACT_N
     if residual is not None:
         args.append(residual)
     return _BNActFn.apply(cfg, *args)
+
+
+def act_only(x: Tensor, act: int, slope: float = 0.0) -> Tensor:
+    """Stand-alone activation through the fused pass (zero BN branches, x as the residual input)."""
+    cfg = ([], int(act), float(slope), False, True)
+    return _BNActFn.apply(cfg, x)
 
 
 # ------------------------------------------------------------------------------------------------------

@@ -1,0 +1,3 @@
+from .adabelief import *  # noqa: F401,F403
+from .lamb import *  # noqa: F401,F403
+from .tadam import *  # noqa: F401,F403

@@ -1,0 +1,125 @@
+/* holocron_b200 — C ABI of the B200 (sm_100a) kernels behind the holocron.nn / holocron.ops / holocron.optim
+ * hot path of frgfm/Holocron.
+ *
+ * The reference is pure Python/PyTorch and has no FFI of its own: every entry point below replaces
+ * the chain of ATen/cuDNN kernels that a reference *Python* function launches; the reference file:line each one
+ * stands in for is cited per declaration (paths relative to the reference repository root).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary;
+ *   - every pointer is a DEVICE pointer unless stated otherwise; `stream` is a cudaStream_t;
+ *   - return value: 0 on success, otherwise a cudaError_t (launch-configuration errors included);
+ *   - re-entrant, no global mutable state apart from one-time kernel attribute setup;
+ *   - dtype codes: 0 = float32, 1 = bfloat16, 2 = float16;
+ *   - activation tensors of the convolution / BatchNorm entry points are NHWC bf16 ("channels_last"),
+ *     filters are KRSC ([Cout][R][S][Cin]).
+ */
+#ifndef HOLOCRON_B200_H
+#define HOLOCRON_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- activations: holocron/nn/functional.py:30-41 (hard_mish), :44-56 (nl_relu) ------------------------ */
+int hb_hard_mish_fwd(const void* x, void* y, size_t n, int dtype, void* stream);
+int hb_hard_mish_bwd(const void* x, const void* dy, void* dx, size_t n, int dtype, void* stream);
+int hb_nl_relu_fwd(const void* x, void* y, size_t n, float beta, int dtype, void* stream);
+int hb_nl_relu_bwd(const void* x, const void* dy, void* dx, size_t n, float beta, int dtype, void* stream);
+/* backward of the in-place variant, from the OUTPUT y = log(1 + beta*relu(x)) */
+int hb_nl_relu_bwd_from_out(const void* y, const void* dy, void* dx, size_t n, float beta, int dtype, void* stream);
+
+/* ---- dense convolutions (tcgen05 implicit GEMM): nn.Conv2d call sites of holocron/models/utils.py:71-76
+ *      (conv_sequence), models/classification/repvgg.py:55-73 (RepBlock) and their autograd backward -------- */
+/* y[N,Ho,Wo,Cout] = act(conv(x[N,H,W,Cin], w[Cout,R,S,Cin]) + bias + residual); Cin % 8 == 0, Cout % 16 == 0.
+ * bias: fp32 [Cout] or NULL; residual: bf16 like y or NULL; act: 0 none, 1 relu; num_ctas: 0 = one per SM. */
+int hb_conv2d_fprop_bf16(const void* x, const void* w, void* y, const float* bias, const void* residual, int N, int H,
+                         int W, int Cin, int Cout, int R, int S, int stride, int pad, int dil, int act, int num_ctas,
+                         void* stream);
+/* dw[Cout,R,S,Cin] (fp32, overwritten) = sum over pixels of dy[N,Ho,Wo,Cout] x im2col(x[N,H,W,Cin]) */
+int hb_conv2d_wgrad_bf16(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int R, int S,
+                         int stride, int pad, int dil, int num_ctas, void* stream);
+/* fp32 KRSC master filter -> bf16 KRSC (Cin zero-padded to CinP) and, if wd != NULL, the flipped + transposed
+ * bf16 filter [CinD][R][S][CoutP] used by the data-gradient pass */
+int hb_pack_conv_weights(const float* w, void* wf, void* wd, int Cout, int Cin, int R, int S, int CinP, int CinD,
+                         int CoutP, void* stream);
+/* y[N,Ho,Wo,C] = zeros, y[n, sp*p, sp*q, :] = x[n,p,q,:]  (input of a stride-sp transposed convolution) */
+int hb_zero_insert_bf16(const void* x, void* y, int N, int Hi, int Wi, int Ho, int Wo, int C, int sp, void* stream);
+/* NCHW image (dtype code) -> NHWC bf16 with channels zero-padded to CP (CP % 8 == 0) */
+int hb_nchw_to_nhwc_pad_bf16(const void* x, void* y, int N, int C, int H, int W, int CP, int dtype, void* stream);
+
+/* ---- BatchNorm2d + branch sum + activation, fused: BatchNorm2d/act emitted by conv_sequence
+ *      (holocron/models/utils.py:73-78) and the branch sum of RepBlock.forward (repvgg.py:71-73) ------------- */
+/* per-channel sum / sum of squares of up to 3 tensors [M,C] bf16 into sums (double [B][2][C], pre-zeroed) */
+int hb_bn_stats_bf16(const void* u0, const void* u1, const void* u2, int B, int M, int C, double* sums, void* stream);
+/* gamma/beta/running_*: HOST arrays of B device pointers (entries may be NULL). Outputs fp32 [B][C]. Updates the
+ * running statistics with `momentum` (unbiased variance), like nn.BatchNorm2d in training mode. */
+int hb_bn_finalize(const double* sums, const float* const* gamma, const float* const* beta, float* const* running_mean,
+                   float* const* running_var, float* mean, float* rstd, float* scale, float* shift, int B, int C, int M,
+                   float eps, float momentum, void* stream);
+int hb_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                      float eps, int C, float* scale, float* shift, float* mean, float* rstd, void* stream);
+/* out = act(sum_b (scale_b * u_b + shift_b) + residual); act: 0 none 1 relu 2 relu6 3 silu 4 leaky(slope) 5 mish
+ * 6 hard_mish */
+int hb_bn_act_fwd_bf16(const void* u0, const void* u1, const void* u2, int B, const float* scale, const float* shift,
+                       const void* residual, void* out, int M, int C, int act, float slope, void* stream);
+/* backward of the above; sums: double [1+B][C] pre-zeroed scratch; du_b/dres/dgamma/dbeta may be NULL */
+int hb_bn_act_bwd_bf16(const void* dout, const void* u0, const void* u1, const void* u2, int B, const float* scale,
+                       const float* shift, const float* mean, const float* rstd, const void* residual, double* sums,
+                       void* du0, void* du1, void* du2, void* dres, float* dgamma, float* dbeta, int M, int C, int act,
+                       float slope, int train, void* stream);
+
+/* ---- global average pooling: holocron/nn/modules/downsample.py:58-74 ----------------------------------- */
+int hb_gap_fwd_bf16(const void* x, void* y, int N, int HW, int C, void* stream);
+int hb_gap_bwd_bf16(const void* dy, void* dx, int N, int HW, int C, void* stream);
+
+/* ---- box operators: holocron/ops/boxes.py:16-211 (+ torchvision.ops.boxes.box_iou, boxes.py:11) ---------- */
+/* mode: 0 IoU, 1 GIoU, 2 DIoU penalty rho^2/c^2, 3 DIoU loss (== the reference's ciou_loss, boxes.py:208-209),
+ * 4 aspect-ratio consistency. boxes fp32 [M,4]/[N,4] xyxy; out fp32 [M,N]. */
+int hb_box_pairwise(const float* boxes1, const float* boxes2, float* out, int M, int N, int mode, void* stream);
+/* sets *flag (device int) to 1 when a box has x2 < x1 or y2 < y1 (box_giou's AssertionError, boxes.py:56-57) */
+int hb_box_degenerate(const float* boxes, int n, int* flag, void* stream);
+/* g1 [M,4], g2 [N,4] (either may be NULL) = gradients of sum(gout * op) for modes 0-3 */
+int hb_box_pairwise_bwd(const float* boxes1, const float* boxes2, const float* gout, float* g1, float* g2, int M, int N,
+                        int mode, void* stream);
+
+/* ---- losses: holocron/nn/functional.py:59-113 (focal_loss), :540-613 (poly_loss), :503-537 (dice_loss) --- */
+/* logits x are [N, K, S] (S = prod of spatial dims); kind 0 focal / 1 poly-1; loss_pos: float[N*S];
+ * partials: double[2 * hb_loss_max_partials()] scratch; fwd_out: float[3] = {sum, #valid, mean}. */
+int hb_loss_max_partials(void);
+int hb_cls_loss_hard_fwd(const void* x, const long long* target, const float* weight, float* loss_pos, double* partials,
+                         float* fwd_out, int N, int K, int S, int ignore_index, int kind, float gamma, float eps,
+                         int dtype, void* stream);
+/* reduction: 0 none (gout[N*S]), 1 mean, 2 sum (gout[1]); dx like x */
+int hb_cls_loss_hard_bwd(const void* x, const long long* target, const float* weight, const float* gout,
+                         const float* fwd_out, void* dx, int N, int K, int S, int ignore_index, int kind, float gamma,
+                         float eps, int reduction, int dtype, void* stream);
+int hb_poly_soft_fwd(const void* x, const void* soft, const float* weight, float* loss_pos, double* partials,
+                     float* fwd_out, int N, int K, int S, int ignore_index, float eps, int dtype, void* stream);
+int hb_poly_soft_bwd(const void* x, const void* soft, const float* weight, const float* gout, void* dx, int N, int K,
+                     int S, int ignore_index, float eps, int reduction, int dtype, void* stream);
+/* sums: double[2K] scratch; out: float[1]; coef: float[2K] (input of hb_dice_bwd) */
+int hb_dice_fwd(const void* x, const void* target, const float* weight, double* sums, float* out, float* coef, int N,
+                int K, long long S, float gamma, float eps, int dtype, void* stream);
+int hb_dice_bwd(const void* target, const float* coef, const float* gout, void* dx, int N, int K, long long S, int dtype,
+                void* stream);
+
+/* ---- optimizers: holocron/optim/adabelief.py:121-167, lamb.py:79-137, tadam.py:160-212 ----------------- */
+/* metas: device table of T records {p, g, m, v, vmax, aux, numel} (7 x 8 bytes each, fp32 tensors);
+ * chunks: device int2[num_chunks] = {tensor index, chunk index}, chunk = hb_optim_chunk_elems() elements. */
+int hb_optim_chunk_elems(void);
+int hb_adabelief_step(const void* metas, const void* chunks, int num_chunks, float lr, float beta1, float beta2,
+                      float eps, float weight_decay, int amsgrad, int step, const int* step_dev, void* stream);
+int hb_lamb_step(const void* metas, const void* chunks, int num_chunks, int T, float lr, float beta1, float beta2,
+                 float eps, float weight_decay, float clip_lo, float clip_hi, double* scratch, void* stream);
+int hb_tadam_step(const void* metas, const void* chunks, int num_chunks, int T, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int amsgrad, float dof, int step, const int* step_dev, double* scratch,
+                  void* stream);
+int hb_step_increment(int* step_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HOLOCRON_B200_H */

@@ -9,13 +9,13 @@ from torch import Tensor
 
 def hard_mish(x: Tensor) -> Tensor:
     """x/2 * min(max(x+2, 0), 2)  — reference nn/functional.py:30-41."""
-    gate = torch.minimum(torch.maximum(x + 2, torch.zeros_like(x)), torch.full_like(x, 2.0))
+    gate = torch.clamp(x + 2, min=0, max=2)  # clamp's inclusive sub-gradient at the kinks is part of the semantics
     return x * 0.5 * gate
 
 
 def nl_relu(x: Tensor, beta: float = 1.0) -> Tensor:
     """log(1 + beta * max(x, 0))  — reference nn/functional.py:44-56."""
-    return torch.log(1 + beta * torch.clamp_min(x, 0))
+    return torch.log(1 + beta * torch.relu(x))  # relu (sub-gradient 0 at x = 0), as in the reference
 
 
 def _rows(x: Tensor) -> Tensor:
