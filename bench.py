@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""Headline benchmark: RepVGG-A0 224x224 bf16 TRAINING throughput (images/s) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5                       # this repo's CUDA path (default arm)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --steps 2 --warmup 1                # reference algorithm on the host CPU cores
+
+One "step" = forward + cross-entropy (label smoothing 0.1, references/classification/train.py:194 of the reference) +
+backward + gradient all-reduce (N > 1) + AdaBelief(lr=1e-3, betas=(0.95, 0.99), eps=1e-6) update on a synthetic
+ImageNet-shaped batch of 256 images per GPU (weak scaling). Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "images/sec RepVGG-A0 224^2 bf16 train"
+BATCH_PER_GPU = 256
+NUM_CLASSES = 1000
+IMAGENET_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def measured_peaks():
+    """Roofline denominators: MEASURED_PEAKS.json (driver-written) or the profiling guide's fallback."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int) -> None:
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        clocks, maxes, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                clocks.append(float(parts[0])); maxes.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        clocks.sort()
+        med = clocks[len(clocks) // 2] if clocks else None
+        return {"sm_mhz": med, "sm_max_mhz": max(maxes) if maxes else None, "reasons": sorted(reasons), "samples": len(clocks)}
+
+
+def synthetic_batch(batch: int, seed: int, device):
+    """ImageNet-like synthetic batch: U[0,1) pixels normalised with the ImageNet mean/std, uniform random labels."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.rand(batch, 3, 224, 224, generator=g)
+    mean = torch.tensor(IMAGENET_MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(IMAGENET_STD).view(1, 3, 1, 1)
+    x = (x - mean) / std
+    t = torch.randint(0, NUM_CLASSES, (batch,), generator=g)
+    return x.to(device), t.to(device)
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, rank):
+    """The reference algorithm for the same step (oracle = CPU restatement of Holocron's RepVGG + AdaBelief on stock
+    torch CPU kernels, pinned to the reference by tests/golden) timed on the host cores. Each step is a bounded
+    sample of the workload (a 16-image batch instead of 256)."""
+    if rank != 0:
+        return
+    from oracle.models import RepVGGOracle
+    from oracle.optim import adabelief_step
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sample = 16
+    torch.manual_seed(0)
+    model = RepVGGOracle("repvgg_a0", num_classes=NUM_CLASSES).train()
+    params = [p for p in model.parameters()]
+    state = [(torch.zeros_like(p), torch.zeros_like(p)) for p in params]
+    x, t = synthetic_batch(sample, 0, "cpu")
+
+    def step(i):
+        loss = F.cross_entropy(model(x), t, label_smoothing=0.1)
+        loss.backward()
+        for p, (m, s) in zip(params, state):
+            adabelief_step(p.data, p.grad, m, s, i, 1e-3, 0.95, 0.99, 1e-6)
+            p.grad = None
+        return loss.item()
+
+    for i in range(args.warmup):
+        step(i + 1)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(args.warmup + i + 1)
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    value = sample / dt
+    print(json.dumps({
+        "metric": METRIC, "value": value, "unit": "images/s", "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "repvgg_a0 224x224 train step (fwd + CE(ls=0.1) + bwd + AdaBelief), CPU reference path",
+                   "batch_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample}-image batches, {args.steps} steps (full workload: 256/GPU)"},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def cpu_baseline(budget_s: float = 20.0):
+    """Bounded CPU sample of the same train step (oracle), for the `cpu_baseline` object of the main arm."""
+    from oracle.models import RepVGGOracle
+    from oracle.optim import adabelief_step
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sample = 8
+    torch.manual_seed(0)
+    model = RepVGGOracle("repvgg_a0", num_classes=NUM_CLASSES).train()
+    params = list(model.parameters())
+    state = [(torch.zeros_like(p), torch.zeros_like(p)) for p in params]
+    x, t = synthetic_batch(sample, 0, "cpu")
+    n, t_total = 0, 0.0
+    for i in range(1, 8):
+        t0 = time.perf_counter()
+        F.cross_entropy(model(x), t, label_smoothing=0.1).backward()
+        for p, (m, s) in zip(params, state):
+            adabelief_step(p.data, p.grad, m, s, i, 1e-3, 0.95, 0.99, 1e-6)
+            p.grad = None
+        dt = time.perf_counter() - t0
+        if i > 1:  # first step = warm-up
+            n += 1
+            t_total += dt
+        if t_total > budget_s or (i > 2 and t_total + dt > budget_s):
+            break
+    value = sample * n / t_total if n else sample / dt
+    return {"value": value, "unit": "images/s", "cores": threads, "kind": "port",
+            "sample": f"{max(n, 1)} steps of an {sample}-image batch (oracle: RepVGG-A0 train step, fp32, torch CPU)"}
+
+
+# ------------------------------------------------------------------------------------------------ main arm
+def conv_algorithmic(info, kind):
+    """FLOPs and HBM bytes of one conv launch: 2*M*Cout*Cin*R*S; (in + out)*2 B + weights."""
+    m_out = info["N"] * info["Ho"] * info["Wo"]
+    flops = 2.0 * m_out * info["Cout"] * info["Cin"] * info["R"] * info["S"]
+    in_b = info["N"] * info["H"] * info["W"] * info["Cin"] * 2
+    out_b = m_out * info["Cout"] * 2
+    w_elems = info["Cout"] * info["Cin"] * info["R"] * info["S"]
+    if kind == "wgrad":
+        byts = in_b + out_b + w_elems * 4     # reads x and dy (bf16), writes fp32 dW
+    else:
+        byts = in_b + out_b + w_elems * 2
+    return flops, byts
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+    import holocron_b200 as hb
+    from holocron_b200.nn import _fused as K
+    from holocron_b200.distributed import GradBucket, broadcast_parameters
+    from holocron_b200._lib import lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl b200) needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    warmup = max(args.warmup, 3)
+
+    torch.manual_seed(0)
+    model = hb.models.repvgg_a0(num_classes=NUM_CLASSES).to(dev).to(memory_format=torch.channels_last).train()
+    broadcast_parameters(model)
+    bucket = GradBucket(model.parameters())
+    opt = hb.optim.AdaBelief(model.parameters(), lr=1e-3, betas=(0.95, 0.99), eps=1e-6)
+    batch = args.batch
+    x_dev, t_dev = synthetic_batch(batch, 1000 + rank, dev)
+    # end-to-end leg: host-resident batch in pinned memory
+    x_host = x_dev.cpu().pin_memory()
+    t_host = t_dev.cpu().pin_memory()
+
+    def train_step(x, t):
+        loss = F.cross_entropy(model(x), t, label_smoothing=0.1)
+        loss.backward()
+        bucket.all_reduce_mean()
+        opt.step()
+        bucket.zero_()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        train_step(x_dev, t_dev)
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM ----------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    lib().hb_launch_count_reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = train_step(x_dev, t_dev)
+    e1.record()
+    barrier()
+    launches = lib().hb_launch_count()
+    ms = e0.elapsed_time(e1) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- timed region 2: end to end through the public API with host buffers -----------------------
+    copy_stream = torch.cuda.Stream()
+    bufs = [(torch.empty_like(x_dev), torch.empty_like(t_dev)) for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            bufs[i][0].copy_(x_host, non_blocking=True)
+            bufs[i][1].copy_(t_host, non_blocking=True)
+            ready[i].record(copy_stream)
+
+    loss_host = 0.0
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    prefetch(0)
+    for i in range(args.steps):
+        cur = i & 1
+        torch.cuda.current_stream().wait_event(ready[cur])
+        if i + 1 < args.steps:
+            copy_stream.wait_stream(torch.cuda.current_stream())   # the other buffer is free once step i-1 is queued behind
+            prefetch(cur ^ 1)
+        loss = train_step(*bufs[cur])
+        loss_host = loss.item()                                     # device -> host read of the step's result
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3) / args.steps
+
+    # max over ranks
+    if world > 1:
+        tt = torch.tensor([ms, ms_e2e], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = tt.tolist()
+
+    result = None
+    if rank == 0:
+        # ---- roofline leg: per-launch CUDA-event timing of the tensor-core conv kernels (one extra step) ----
+        K.KERNEL_TIMER = []
+        train_step(x_dev, t_dev)
+        torch.cuda.synchronize()
+        recs = K.KERNEL_TIMER
+        K.KERNEL_TIMER = None
+        agg = {}
+        for kind, info, a, b in recs:
+            fl, by = conv_algorithmic(info, kind)
+            kname = "conv_wgrad_kernel" if kind == "wgrad" else "conv_fprop_kernel"
+            d = agg.setdefault(kname, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+            d["ms"] += a.elapsed_time(b); d["flops"] += fl; d["bytes"] += by; d["launches"] += 1
+        peaks = measured_peaks()
+        dom = max(agg, key=lambda k: agg[k]["ms"])
+        d = agg[dom]
+        t_flops = d["flops"] / (peaks["bf16_tflops"] * 1e12) * 1e3
+        t_bytes = d["bytes"] / (peaks["hbm_gbs"] * 1e9) * 1e3
+        if t_bytes >= t_flops:
+            roof = {"bound": "hbm", "achieved": d["bytes"] / d["ms"] / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s"}
+        else:
+            roof = {"bound": "tensor", "achieved": d["flops"] / d["ms"] / 1e9, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s"}
+        roof["frac"] = roof["achieved"] / roof["peak"]
+        roof["traffic"] = None
+        roof["kernel"] = dom
+        roof["peak_source"] = peaks["src"]
+        roof["per_step"] = {k: {"ms": round(v["ms"], 3), "launches": v["launches"], "TFLOP/s": round(v["flops"] / v["ms"] / 1e9, 1),
+                                "GB/s": round(v["bytes"] / v["ms"] / 1e6, 1)} for k, v in agg.items()}
+        cpu = None if args.no_cpu_baseline or world > 1 else cpu_baseline()
+        images = batch * world
+        result = {
+            "metric": METRIC, "value": images / ms * 1e3, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "repvgg_a0 (train form, 1000 classes) 224x224 bf16 train step: fwd + CE(label_smoothing=0.1)"
+                                   " + bwd + AdaBelief(lr=1e-3, betas=(0.95,0.99), eps=1e-6)",
+                       "batch_per_gpu": batch, "global_batch": images, "parallelism": f"dp{world}",
+                       "l2": "per-step working set (>4 GB of activations) exceeds the 126 MB L2; no explicit flush"},
+            "e2e": {"value": images / ms_e2e * 1e3, "unit": "images/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": x_host.numel() * 4 + t_host.numel() * 8, "d2h_bytes_per_step": 4,
+                    "last_loss": loss_host},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof,
+        }
+        if cpu is not None:
+            result["cpu_baseline"] = cpu
+        print(json.dumps(result), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -38,15 +38,23 @@ SIGNATURES = {
     "hb_zero_insert_bf16": "pp" + "i" * 7 + "p",
     "hb_nchw_to_nhwc_pad_bf16": "pp" + "i" * 6 + "p",
     "hb_bn_stats_bf16": "pppiiipp",
-    "hb_bn_finalize": "ppppp" + "pppp" + "iiiffp",
+    "hb_bn_finalize": "pppppp" + "pppp" + "iiiffp",
     "hb_bn_eval_affine": "ppppfippppp",
     "hb_bn_act_fwd_bf16": "pppipppp" + "iiifp",
     "hb_bn_act_bwd_bf16": "ppppi" + "pppppp" + "pppppp" + "iiifip",
+    "hb_dwconv_fwd_bf16": "pppp" + "iiiiiiip",
+    "hb_dwconv_bwd_data_bf16": "ppp" + "iiiiiiip",
+    "hb_dwconv_bwd_weight_bf16": "ppppp" + "iiiiiiip",
     "hb_gap_fwd_bf16": "ppiiip",
     "hb_gap_bwd_bf16": "ppiiip",
     "hb_box_pairwise": "pppiiip",
     "hb_box_degenerate": "pipp",
     "hb_box_pairwise_bwd": "pppppiiip",
+    "hb_xcorr2d_fwd": "pppppp" + "i" * 12 + "fp",
+    "hb_xcorr2d_wgrad": "pppppp" + "i" * 12 + "fp",
+    "hb_add2d_dgrad": "pppp" + "i" * 10 + "p",
+    "hb_dropblock_mask": "pppiiiifp",
+    "hb_dropblock_apply": "ppppiiiiiip",
     "hb_loss_max_partials": "",
     "hb_cls_loss_hard_fwd": "pppppp" + "iiiiiffip",
     "hb_cls_loss_hard_bwd": "pppppp" + "iiiiiffiip",
@@ -77,6 +85,12 @@ def lib() -> ctypes.CDLL:
             fn = getattr(handle, name)  # AttributeError here = the library is stale: rebuild it
             fn.argtypes = [_CTYPE[c] for c in sig]
             fn.restype = ctypes.c_int
+        handle.hb_launch_count.argtypes = []
+        handle.hb_launch_count.restype = ctypes.c_longlong
+        handle.hb_launch_count_reset.argtypes = []
+        handle.hb_launch_count_reset.restype = None
+        handle.hb_version.argtypes = []
+        handle.hb_version.restype = ctypes.c_char_p
         _lib = handle
     return _lib
 

@@ -22,7 +22,8 @@ using namespace hb;
 constexpr int kThreads = 256;
 constexpr int kMaxBranches = 3;
 
-enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_RELU6 = 2, ACT_SILU = 3, ACT_LEAKY = 4, ACT_MISH = 5, ACT_HARDMISH = 6 };
+// ACT_FRELU: out = max(z, residual) with z the normalised branch sum (funnel activation, reference activation.py:58-82)
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_RELU6 = 2, ACT_SILU = 3, ACT_LEAKY = 4, ACT_MISH = 5, ACT_HARDMISH = 6, ACT_FRELU = 7 };
 
 __device__ __forceinline__ float act_fwd(int act, float z, float slope) {
   switch (act) {
@@ -148,6 +149,7 @@ struct FinalizeParams {
   const float* beta[kMaxBranches];
   float* running_mean[kMaxBranches];  // may be null
   float* running_var[kMaxBranches];
+  long long* num_batches_tracked[kMaxBranches];  // int64 scalar per branch, may be null
   float* mean;   // [B][C] out
   float* rstd;   // [B][C] out
   float* scale;  // [B][C] out
@@ -173,6 +175,7 @@ __global__ void bn_finalize_kernel(FinalizeParams p) {
   p.rstd[o] = rstd;
   p.scale[o] = sc;
   p.shift[o] = be - (float)mean * sc;
+  if (c == 0 && p.num_batches_tracked[b]) *p.num_batches_tracked[b] += 1;
   if (p.running_mean[b]) {
     const double unbiased = p.M > 1 ? var * ((double)p.M / (double)(p.M - 1)) : var;
     p.running_mean[b][c] = (1.f - p.momentum) * p.running_mean[b][c] + p.momentum * (float)mean;
@@ -239,8 +242,13 @@ __global__ void __launch_bounds__(kThreads) bn_act_fwd_kernel(FwdParams p, Geo g
     if (p.residual) {
       float r[8];
       load8(p.residual + off, r);
+      if (p.act == ACT_FRELU) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) z[j] += r[j];
+        for (int j = 0; j < 8; ++j) z[j] = fmaxf(z[j], r[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) z[j] += r[j];
+      }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) z[j] = act_fwd(p.act, z[j], p.slope);
@@ -300,9 +308,10 @@ __device__ __forceinline__ void load_slab_consts(SlabConsts& k, const BwdParams&
   __syncthreads();
 }
 
+// dz = d out / d z (z = normalised branch sum [+ residual]); dr = gradient reaching the residual input
 template <int NB>
 __device__ __forceinline__ void recompute_dz(const BwdParams& p, const SlabConsts& k, int ch0, size_t off,
-                                             float (*u)[8], float* dz) {
+                                             float (*u)[8], float* dz, float* dr) {
   float z[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) z[j] = k.shift[ch0 + j];
@@ -312,16 +321,26 @@ __device__ __forceinline__ void recompute_dz(const BwdParams& p, const SlabConst
 #pragma unroll
     for (int j = 0; j < 8; ++j) z[j] = fmaf(k.scale[b][ch0 + j], u[b][j], z[j]);
   }
+  float d[8];
+  load8(p.dout + off, d);
   if (p.residual) {
     float r[8];
     load8(p.residual + off, r);
+    if (p.act == ACT_FRELU) {
+      // binary max: the gradient goes to the larger argument, ties are split evenly (PyTorch semantics)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float gate = z[j] > r[j] ? 1.f : (z[j] == r[j] ? 0.5f : 0.f);
+        dz[j] = d[j] * gate;
+        dr[j] = d[j] - dz[j];
+      }
+      return;
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) z[j] += r[j];
   }
-  float d[8];
-  load8(p.dout + off, d);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) dz[j] = d[j] * act_grad(p.act, z[j], p.slope);
+  for (int j = 0; j < 8; ++j) { dz[j] = d[j] * act_grad(p.act, z[j], p.slope); dr[j] = dz[j]; }
 }
 
 template <int NB>
@@ -340,8 +359,8 @@ __global__ void __launch_bounds__(kThreads, 2) bn_act_bwd_reduce_kernel(BwdParam
   if (active) {
     const size_t row_stride = (size_t)gridDim.x * g.rows_t;
     for (size_t m = (size_t)blockIdx.x * g.rows_t + ty; m < (size_t)p.M; m += row_stride) {
-      float u[NB > 0 ? NB : 1][8], dz[8];
-      recompute_dz<NB>(p, k, tx * 8, m * p.C + cg * 8, u, dz);
+      float u[NB > 0 ? NB : 1][8], dz[8], dr[8];
+      recompute_dz<NB>(p, k, tx * 8, m * p.C + cg * 8, u, dz, dr);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[0][j] += dz[j];
 #pragma unroll
@@ -380,9 +399,9 @@ __global__ void __launch_bounds__(kThreads, 2) bn_act_bwd_apply_kernel(BwdParams
   const size_t row_stride = (size_t)gridDim.x * g.rows_t;
   for (size_t m = (size_t)blockIdx.x * g.rows_t + ty; m < (size_t)p.M; m += row_stride) {
     const size_t off = m * p.C + cg * 8;
-    float u[NB > 0 ? NB : 1][8], dz[8];
-    recompute_dz<NB>(p, k, tx * 8, off, u, dz);
-    if (p.dres) store8(p.dres + off, dz);
+    float u[NB > 0 ? NB : 1][8], dz[8], dr[8];
+    recompute_dz<NB>(p, k, tx * 8, off, u, dz, dr);
+    if (p.dres) store8(p.dres + off, dr);
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
       if (p.du[b]) {
@@ -435,8 +454,8 @@ int hb_bn_stats_bf16(const void* u0, const void* u1, const void* u2, int B, int 
 }
 
 int hb_bn_finalize(const double* sums, const float* const* gamma, const float* const* beta, float* const* running_mean,
-                   float* const* running_var, float* mean, float* rstd, float* scale, float* shift, int B, int C, int M,
-                   float eps, float momentum, void* stream) {
+                   float* const* running_var, long long* const* num_batches_tracked, float* mean, float* rstd,
+                   float* scale, float* shift, int B, int C, int M, float eps, float momentum, void* stream) {
   if (B < 1 || B > kMaxBranches) return (int)cudaErrorInvalidValue;
   FinalizeParams p{};
   p.sums = sums;
@@ -445,6 +464,7 @@ int hb_bn_finalize(const double* sums, const float* const* gamma, const float* c
     p.beta[b] = beta ? beta[b] : nullptr;
     p.running_mean[b] = running_mean ? running_mean[b] : nullptr;
     p.running_var[b] = running_var ? running_var[b] : nullptr;
+    p.num_batches_tracked[b] = num_batches_tracked ? num_batches_tracked[b] : nullptr;
   }
   p.mean = mean; p.rstd = rstd; p.scale = scale; p.shift = shift;
   p.B = B; p.C = C; p.M = M; p.eps = eps; p.momentum = momentum;

@@ -12,8 +12,13 @@
 
 #define HB_NUM_SMS 148
 
+#include <atomic>
+extern std::atomic<long long> g_hb_launches;  // defined in runtime.cu
+
+// after every kernel launch: count it and surface launch-configuration errors as the return code
 #define HB_LAUNCH_CHECK()                          \
   do {                                             \
+    g_hb_launches.fetch_add(1, std::memory_order_relaxed); \
     cudaError_t e__ = cudaGetLastError();          \
     if (e__ != cudaSuccess) return (int)e__;       \
   } while (0)

@@ -1,0 +1,237 @@
+// Depth-wise k x k convolution (groups == channels) over NHWC bf16 activations: forward, data gradient, weight/bias
+// gradient. CUDA-core, HBM-bound (9 MAC per element for k = 3): every thread owns 8 consecutive channels
+// (one 128-bit vector) of one output pixel; neighbouring threads share their taps through L1/L2.
+// Used by FReLU (reference holocron/nn/modules/activation.py:58-82: conv k x k, groups = C, bias) and by the ReXNet
+// blocks (reference holocron/models/classification/rexnet.py:112-125: dw 3x3, stride 1|2, no bias).
+#include "common.cuh"
+
+namespace {
+
+using namespace hb;
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float* f) {
+  Vec16<__nv_bfloat16> v = ld16(p);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = __bfloat162float(v.v[j]);
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float* f) {
+  Vec16<__nv_bfloat16> v;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v.v[j] = __float2bfloat16_rn(f[j]);
+  st16(p, v);
+}
+
+struct DwParams {
+  int N, H, W, C, Ho, Wo, K, stride, pad;
+};
+
+// w: fp32 [C][K][K] (the nn.Conv2d weight [C,1,K,K]); bias fp32 [C] or null
+__global__ void __launch_bounds__(kThreads) dw_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
+                                                          DwParams p) {
+  const int cv = p.C / 8;
+  const long long total = (long long)p.N * p.Ho * p.Wo * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % cv);
+    long long t = i / cv;
+    const int wo = (int)(t % p.Wo); t /= p.Wo;
+    const int ho = (int)(t % p.Ho);
+    const int n = (int)(t / p.Ho);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = bias ? bias[cg * 8 + j] : 0.f;
+    for (int r = 0; r < p.K; ++r) {
+      const int hi = ho * p.stride + r - p.pad;
+      if (hi < 0 || hi >= p.H) continue;
+      for (int s = 0; s < p.K; ++s) {
+        const int wi = wo * p.stride + s - p.pad;
+        if (wi < 0 || wi >= p.W) continue;
+        float xv[8];
+        load8(x + (((long long)n * p.H + hi) * p.W + wi) * p.C + cg * 8, xv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv[j], __ldg(w + ((cg * 8 + j) * p.K + r) * p.K + s), acc[j]);
+      }
+    }
+    store8(y + i * 8, acc);
+  }
+}
+
+// dx[n,h,w,c] = sum_{r,s} dy[n,(h+pad-r)/stride,(w+pad-s)/stride,c] * w[c,r,s]   (only exact divisions)
+__global__ void __launch_bounds__(kThreads) dw_bwd_data_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                               const float* __restrict__ w,
+                                                               __nv_bfloat16* __restrict__ dx, DwParams p) {
+  const int cv = p.C / 8;
+  const long long total = (long long)p.N * p.H * p.W * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % cv);
+    long long t = i / cv;
+    const int wi = (int)(t % p.W); t /= p.W;
+    const int hi = (int)(t % p.H);
+    const int n = (int)(t / p.H);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int r = 0; r < p.K; ++r) {
+      const int hn = hi + p.pad - r;
+      if (hn < 0 || hn % p.stride != 0) continue;
+      const int ho = hn / p.stride;
+      if (ho >= p.Ho) continue;
+      for (int s = 0; s < p.K; ++s) {
+        const int wn = wi + p.pad - s;
+        if (wn < 0 || wn % p.stride != 0) continue;
+        const int wo = wn / p.stride;
+        if (wo >= p.Wo) continue;
+        float g[8];
+        load8(dy + (((long long)n * p.Ho + ho) * p.Wo + wo) * p.C + cg * 8, g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(g[j], __ldg(w + ((cg * 8 + j) * p.K + r) * p.K + s), acc[j]);
+      }
+    }
+    store8(dx + i * 8, acc);
+  }
+}
+
+// dw[c,r,s] = sum_{n,ho,wo} dy * x_shifted ; db[c] = sum dy.  sums: double [C][KK+1] (last column = bias grad)
+// block geometry as in the BN kernels: tx = channel group within a 32-group slab, ty = pixel lane
+template <int KS>
+__global__ void __launch_bounds__(kThreads) dw_bwd_weight_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                 const __nv_bfloat16* __restrict__ dy, double* sums,
+                                                                 DwParams p, int cg_t, int rows_t) {
+  constexpr int KK = KS * KS;
+  __shared__ float red[kThreads * 8];
+  const int cv = p.C / 8;
+  const int tx = threadIdx.x % cg_t, ty = threadIdx.x / cg_t;
+  const int cg = blockIdx.y * cg_t + tx;
+  const bool active = ty < rows_t && cg < cv;
+  float acc[KK + 1][8];
+#pragma unroll
+  for (int k = 0; k <= KK; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
+  if (active) {
+    const long long M = (long long)p.N * p.Ho * p.Wo;
+    const long long stride_m = (long long)gridDim.x * rows_t;
+    for (long long m = (long long)blockIdx.x * rows_t + ty; m < M; m += stride_m) {
+      const int wo = (int)(m % p.Wo);
+      const int ho = (int)((m / p.Wo) % p.Ho);
+      const int n = (int)(m / ((long long)p.Wo * p.Ho));
+      float g[8];
+      load8(dy + m * p.C + cg * 8, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[KK][j] += g[j];
+#pragma unroll
+      for (int r = 0; r < KS; ++r) {
+        const int hi = ho * p.stride + r - p.pad;
+        if (hi < 0 || hi >= p.H) continue;
+#pragma unroll
+        for (int s = 0; s < KS; ++s) {
+          const int wi = wo * p.stride + s - p.pad;
+          if (wi < 0 || wi >= p.W) continue;
+          float xv[8];
+          load8(x + (((long long)n * p.H + hi) * p.W + wi) * p.C + cg * 8, xv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[r * KS + s][j] = fmaf(g[j], xv[j], acc[r * KS + s][j]);
+        }
+      }
+    }
+  }
+  const int nch = cg_t * 8;
+#pragma unroll
+  for (int k = 0; k <= KK; ++k) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[threadIdx.x * 8 + j] = acc[k][j];
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < nch; ch += kThreads) {
+      const int ctx = ch / 8, j = ch % 8;
+      const int gcg = blockIdx.y * cg_t + ctx;
+      if (gcg >= cv) continue;
+      double a = 0.0;
+      for (int r = 0; r < rows_t; ++r) a += (double)red[(r * cg_t + ctx) * 8 + j];
+      atomicAdd(&sums[(size_t)(gcg * 8 + j) * (KK + 1) + k], a);
+    }
+  }
+}
+
+__global__ void dw_weight_finalize_kernel(const double* sums, float* dw, float* db, int C, int KK) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * (KK + 1)) return;
+  const int c = i / (KK + 1), k = i % (KK + 1);
+  if (k < KK) dw[c * KK + k] = (float)sums[i];
+  else if (db) db[c] = (float)sums[i];
+}
+
+DwParams make_params(int N, int H, int W, int C, int K, int stride, int pad) {
+  DwParams p{N, H, W, C, 0, 0, K, stride, pad};
+  p.Ho = (H + 2 * pad - K) / stride + 1;
+  p.Wo = (W + 2 * pad - K) / stride + 1;
+  return p;
+}
+
+}  // namespace
+
+extern "C" {
+
+// y[N,Ho,Wo,C] = dwconv(x[N,H,W,C], w fp32 [C,K,K]) + bias; C % 8 == 0
+int hb_dwconv_fwd_bf16(const void* x, const float* w, const float* bias, void* y, int N, int H, int W, int C, int K,
+                       int stride, int pad, void* stream) {
+  if (C % 8 != 0) return (int)cudaErrorInvalidValue;
+  DwParams p = make_params(N, H, W, C, K, stride, pad);
+  const long long total = (long long)N * p.Ho * p.Wo * (C / 8);
+  if (total <= 0) return 0;
+  dw_fwd_kernel<<<stream_grid((size_t)total, kThreads, 16), kThreads, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, w, bias, (__nv_bfloat16*)y, p);
+  HB_LAUNCH_CHECK();
+  return 0;
+}
+
+int hb_dwconv_bwd_data_bf16(const void* dy, const float* w, void* dx, int N, int H, int W, int C, int K, int stride,
+                            int pad, void* stream) {
+  if (C % 8 != 0) return (int)cudaErrorInvalidValue;
+  DwParams p = make_params(N, H, W, C, K, stride, pad);
+  const long long total = (long long)N * H * W * (C / 8);
+  if (total <= 0) return 0;
+  dw_bwd_data_kernel<<<stream_grid((size_t)total, kThreads, 16), kThreads, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)dy, w, (__nv_bfloat16*)dx, p);
+  HB_LAUNCH_CHECK();
+  return 0;
+}
+
+// dw fp32 [C,K,K], db fp32 [C] (or NULL); sums: double scratch [C * (K*K + 1)], zeroed here. K in {1, 3, 5, 7}.
+int hb_dwconv_bwd_weight_bf16(const void* x, const void* dy, float* dw, float* db, double* sums, int N, int H, int W,
+                              int C, int K, int stride, int pad, void* stream) {
+  if (C % 8 != 0) return (int)cudaErrorInvalidValue;
+  cudaStream_t st = (cudaStream_t)stream;
+  DwParams p = make_params(N, H, W, C, K, stride, pad);
+  const int KK = K * K;
+  cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * C * (KK + 1), st);
+  if (e != cudaSuccess) return (int)e;
+  const int cv = C / 8;
+  const int cg_t = cv < 32 ? cv : 32;
+  const int rows_t = kThreads / cg_t;
+  const int slabs = (cv + cg_t - 1) / cg_t;
+  const long long M = (long long)N * p.Ho * p.Wo;
+  long long gx = (M + rows_t * 8 - 1) / (rows_t * 8);
+  long long cap = (HB_NUM_SMS * 4) / slabs;
+  if (cap < 1) cap = 1;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  dim3 grid((unsigned)gx, (unsigned)slabs);
+  const __nv_bfloat16* xb = (const __nv_bfloat16*)x;
+  const __nv_bfloat16* dyb = (const __nv_bfloat16*)dy;
+  switch (K) {
+    case 1: dw_bwd_weight_kernel<1><<<grid, kThreads, 0, st>>>(xb, dyb, sums, p, cg_t, rows_t); break;
+    case 3: dw_bwd_weight_kernel<3><<<grid, kThreads, 0, st>>>(xb, dyb, sums, p, cg_t, rows_t); break;
+    case 5: dw_bwd_weight_kernel<5><<<grid, kThreads, 0, st>>>(xb, dyb, sums, p, cg_t, rows_t); break;
+    case 7: dw_bwd_weight_kernel<7><<<grid, kThreads, 0, st>>>(xb, dyb, sums, p, cg_t, rows_t); break;
+    default: return (int)cudaErrorInvalidValue;
+  }
+  HB_LAUNCH_CHECK();
+  dw_weight_finalize_kernel<<<(C * (KK + 1) + 127) / 128, 128, 0, st>>>(sums, dw, db, C, KK);
+  HB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

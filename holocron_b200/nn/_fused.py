@@ -16,10 +16,25 @@ from torch import Tensor, nn
 
 from .._lib import check, lib, ptr, require_cuda, stream_ptr
 
-ACT_NONE, ACT_RELU, ACT_RELU6, ACT_SILU, ACT_LEAKY, ACT_MISH, ACT_HARDMISH = range(7)
+ACT_NONE, ACT_RELU, ACT_RELU6, ACT_SILU, ACT_LEAKY, ACT_MISH, ACT_HARDMISH, ACT_FRELU = range(8)
 
 _c_float = ctypes.c_float
 _VP3 = ctypes.c_void_p * 3
+
+# Optional per-launch timing of the tensor-core kernels (bench.py's roofline leg): when set to a list, every conv
+# launch appends (kind, shape dict, start_event, end_event) recorded on the launching stream.
+KERNEL_TIMER = None
+
+
+def _timed(kind: str, info: dict, fn):
+    if KERNEL_TIMER is None:
+        return fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = fn()
+    e1.record()
+    KERNEL_TIMER.append((kind, info, e0, e1))
+    return out
 
 
 def act_code(act: Optional[nn.Module]) -> Tuple[int, float]:
@@ -116,8 +131,10 @@ def conv2d_forward_raw(x: Tensor, wf: Tensor, cout: int, r: int, s: int, stride:
     n, cin_p, h, w = x.shape
     ho, wo = conv_out_size(h, r, stride, pad, dil), conv_out_size(w, s, stride, pad, dil)
     y = _empty_cl(n, cout, ho, wo, x.device)
-    check(lib().hb_conv2d_fprop_bf16(ptr(x), ptr(wf), ptr(y), ptr(bias), ptr(residual), n, h, w, cin_p, cout, r, s,
-                                     stride, pad, dil, act, 0, stream_ptr()), "hb_conv2d_fprop_bf16")
+    info = dict(N=n, H=h, W=w, Cin=cin_p, Cout=cout, R=r, S=s, stride=stride, Ho=ho, Wo=wo)
+    _timed("fprop", info, lambda: check(
+        lib().hb_conv2d_fprop_bf16(ptr(x), ptr(wf), ptr(y), ptr(bias), ptr(residual), n, h, w, cin_p, cout, r, s,
+                                   stride, pad, dil, act, 0, stream_ptr()), "hb_conv2d_fprop_bf16"))
     return y
 
 
@@ -160,13 +177,17 @@ class _Conv2dFn(torch.autograd.Function):
                 check(L.hb_zero_insert_bf16(ptr(dyb), ptr(src), n, ho, wo, h, w, cout, stride, stream_ptr()),
                       "hb_zero_insert_bf16")
             dxp = _empty_cl(n, cin_d, h, w, dyb.device)
-            check(L.hb_conv2d_fprop_bf16(ptr(src), ptr(wd), ptr(dxp), ptr(None), ptr(None), n, h, w, cout, cin_d, r, s, 1,
-                                         (r - 1) * dil - pad, 1, ACT_NONE, 0, stream_ptr()), "hb_conv2d_fprop_bf16[dgrad]")
+            info = dict(N=n, H=h, W=w, Cin=cout, Cout=cin_d, R=r, S=s, stride=1, Ho=h, Wo=w, dgrad_of_stride=stride)
+            _timed("dgrad", info, lambda: check(
+                L.hb_conv2d_fprop_bf16(ptr(src), ptr(wd), ptr(dxp), ptr(None), ptr(None), n, h, w, cout, cin_d, r, s, 1,
+                                       (r - 1) * dil - pad, 1, ACT_NONE, 0, stream_ptr()), "hb_conv2d_fprop_bf16[dgrad]"))
             dx = dxp if cin_d == cin_logical else dxp[:, :cin_logical]
         if ctx.needs_input_grad[1]:
             dwp = torch.empty((cout, r, s, cin_p), device=dyb.device, dtype=torch.float32)
-            check(L.hb_conv2d_wgrad_bf16(ptr(xb), ptr(dyb), ptr(dwp), n, h, w, cin_p, cout, r, s, stride, pad, dil, 0,
-                                         stream_ptr()), "hb_conv2d_wgrad_bf16")
+            info = dict(N=n, H=h, W=w, Cin=cin_p, Cout=cout, R=r, S=s, stride=stride, Ho=ho, Wo=wo)
+            _timed("wgrad", info, lambda: check(
+                L.hb_conv2d_wgrad_bf16(ptr(xb), ptr(dyb), ptr(dwp), n, h, w, cin_p, cout, r, s, stride, pad, dil, 0,
+                                       stream_ptr()), "hb_conv2d_wgrad_bf16"))
             dw = dwp.permute(0, 3, 1, 2)
             if cin_p != cin:
                 dw = dw[:, :cin].contiguous(memory_format=torch.channels_last)
@@ -258,11 +279,9 @@ class _BNActFn(torch.autograd.Function):
             check(L.hb_bn_finalize(ptr(sums), _arr3(g32), _arr3(b32),
                                    _arr3([b.running_mean for b in branches]) if track else None,
                                    _arr3([b.running_var for b in branches]) if track else None,
+                                   _arr3([b.num_batches_tracked for b in branches]) if track else None,
                                    ptr(mean), ptr(rstd), ptr(scale), ptr(shift), nb, c, m, _c_float(eps), _c_float(mom),
                                    stream_ptr()), "hb_bn_finalize")
-            for b in branches:
-                if b.num_batches_tracked is not None:
-                    b.num_batches_tracked += 1
         else:
             for i, b in enumerate(branches):
                 check(L.hb_bn_eval_affine(ptr(g32[i]), ptr(b32[i]), ptr(b.running_mean), ptr(b.running_var),

@@ -8,12 +8,17 @@ from torch import Tensor
 from .._lib import lib, require_cuda
 
 
+def effective_strides(t: Tensor):
+    """Strides of the dims that matter (size-1 dims can carry any stride, e.g. 1x1 filters in channels_last)."""
+    return tuple(s for s, n in zip(t.stride(), t.shape) if n != 1)
+
+
 def _same_dense_layout(ts: Sequence[Optional[Tensor]]) -> bool:
     ref = next(t for t in ts if t is not None)
     for t in ts:
         if t is None:
             continue
-        if t.shape != ref.shape or t.stride() != ref.stride():
+        if t.shape != ref.shape or effective_strides(t) != effective_strides(ref):
             return False
     return ref.is_contiguous() or (ref.ndim == 4 and ref.is_contiguous(memory_format=torch.channels_last)) or \
         ref.is_non_overlapping_and_dense()

@@ -7,7 +7,7 @@ from torch import Tensor
 from torch.optim import Optimizer
 
 from .._lib import check, lib, ptr, stream_ptr
-from ._multi_tensor import TensorTable, bump_versions
+from ._multi_tensor import TensorTable, bump_versions, effective_strides
 
 __all__ = ["AdaBelief", "adabelief"]
 
@@ -93,7 +93,7 @@ def _as_layout(g: Tensor, p: Tensor) -> Tensor:
     """Gradient with the parameter's strides (copy only when autograd produced a different layout)."""
     if g.dtype != torch.float32:
         g = g.float()
-    if g.stride() == p.stride():
+    if g.shape == p.shape and effective_strides(g) == effective_strides(p):
         return g
     out = torch.empty_like(p)
     out.copy_(g)

@@ -54,15 +54,16 @@ int hb_nchw_to_nhwc_pad_bf16(const void* x, void* y, int N, int C, int H, int W,
  *      (holocron/models/utils.py:73-78) and the branch sum of RepBlock.forward (repvgg.py:71-73) ------------- */
 /* per-channel sum / sum of squares of up to 3 tensors [M,C] bf16 into sums (double [B][2][C], pre-zeroed) */
 int hb_bn_stats_bf16(const void* u0, const void* u1, const void* u2, int B, int M, int C, double* sums, void* stream);
-/* gamma/beta/running_*: HOST arrays of B device pointers (entries may be NULL). Outputs fp32 [B][C]. Updates the
- * running statistics with `momentum` (unbiased variance), like nn.BatchNorm2d in training mode. */
+/* gamma/beta/running_*/num_batches_tracked: HOST arrays of B device pointers (entries may be NULL). Outputs fp32
+ * [B][C]. Updates the running statistics with `momentum` (unbiased variance) and increments the int64
+ * num_batches_tracked counters, like nn.BatchNorm2d in training mode. */
 int hb_bn_finalize(const double* sums, const float* const* gamma, const float* const* beta, float* const* running_mean,
-                   float* const* running_var, float* mean, float* rstd, float* scale, float* shift, int B, int C, int M,
-                   float eps, float momentum, void* stream);
+                   float* const* running_var, long long* const* num_batches_tracked, float* mean, float* rstd,
+                   float* scale, float* shift, int B, int C, int M, float eps, float momentum, void* stream);
 int hb_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                       float eps, int C, float* scale, float* shift, float* mean, float* rstd, void* stream);
 /* out = act(sum_b (scale_b * u_b + shift_b) + residual); act: 0 none 1 relu 2 relu6 3 silu 4 leaky(slope) 5 mish
- * 6 hard_mish */
+ * 6 hard_mish, 7 funnel: out = max(sum_b(...), residual) (FReLU, holocron/nn/modules/activation.py:58-82) */
 int hb_bn_act_fwd_bf16(const void* u0, const void* u1, const void* u2, int B, const float* scale, const float* shift,
                        const void* residual, void* out, int M, int C, int act, float slope, void* stream);
 /* backward of the above; sums: double [1+B][C] pre-zeroed scratch; du_b/dres/dgamma/dbeta may be NULL */
@@ -70,6 +71,16 @@ int hb_bn_act_bwd_bf16(const void* dout, const void* u0, const void* u1, const v
                        const float* shift, const float* mean, const float* rstd, const void* residual, double* sums,
                        void* du0, void* du1, void* du2, void* dres, float* dgamma, float* dbeta, int M, int C, int act,
                        float slope, int train, void* stream);
+
+/* ---- depth-wise k x k convolution (NHWC bf16; weights fp32 [C,K,K]): FReLU's conv (activation.py:71-73) and the
+ *      ReXNet depth-wise stage (holocron/models/classification/rexnet.py:112-125) ------------------------- */
+int hb_dwconv_fwd_bf16(const void* x, const float* w, const float* bias, void* y, int N, int H, int W, int C, int K,
+                       int stride, int pad, void* stream);
+int hb_dwconv_bwd_data_bf16(const void* dy, const float* w, void* dx, int N, int H, int W, int C, int K, int stride,
+                            int pad, void* stream);
+/* dw fp32 [C,K,K], db fp32 [C] or NULL; sums: double scratch [C*(K*K+1)]; K in {1,3,5,7} */
+int hb_dwconv_bwd_weight_bf16(const void* x, const void* dy, float* dw, float* db, double* sums, int N, int H, int W,
+                              int C, int K, int stride, int pad, void* stream);
 
 /* ---- global average pooling: holocron/nn/modules/downsample.py:58-74 ----------------------------------- */
 int hb_gap_fwd_bf16(const void* x, void* y, int N, int HW, int C, void* stream);
@@ -84,6 +95,26 @@ int hb_box_degenerate(const float* boxes, int n, int* flag, void* stream);
 /* g1 [M,4], g2 [N,4] (either may be NULL) = gradients of sum(gout * op) for modes 0-3 */
 int hb_box_pairwise_bwd(const float* boxes1, const float* boxes2, const float* gout, float* g1, float* g2, int M, int N,
                         int mode, void* stream);
+
+/* ---- NormConv2d / Add2d: holocron/nn/functional.py:322-462 (_xcorr2d, norm_conv2d, add2d) ---------------- */
+/* x fp32 NCHW, w fp32 [Cout,Cin,KH,KW], out fp32 [N,Cout,Ho,Wo]; mode 0 multiply-accumulate, 1 adder (-L1);
+ * normalize: standardise every im2col patch (biased var + eps); mean/rstd: fp32 [N*Ho*Wo] (written when normalize). */
+int hb_xcorr2d_fwd(const float* x, const float* w, const float* bias, float* out, float* mean, float* rstd, int N, int Cin,
+                   int H, int W, int Cout, int KH, int KW, int stride, int pad, int dil, int mode, int normalize,
+                   float eps, void* stream);
+int hb_xcorr2d_wgrad(const float* x, const float* w, const float* g, const float* mean, const float* rstd, float* dw,
+                     int N, int Cin, int H, int W, int Cout, int KH, int KW, int stride, int pad, int dil, int mode,
+                     int normalize, float eps, void* stream);
+int hb_add2d_dgrad(const float* x, const float* w, const float* g, float* dx, int N, int Cin, int H, int W, int Cout,
+                   int KH, int KW, int stride, int pad, int dil, void* stream);
+
+/* ---- DropBlock: holocron/nn/functional.py:465-500, nn/modules/dropblock.py:14-41 ------------------------ */
+/* mask[N,H,W] = 1 - maxpool_bs(noise <= gamma); *kept (device float) = sum(mask). block_size must be odd. */
+int hb_dropblock_mask(const float* noise, float* mask, float* kept, int N, int H, int W, int block_size, float gamma,
+                      void* stream);
+/* out = x * mask * (N*H*W / *kept) (no rescale when *kept == 0); x: [N,C,H,W] logical, physical NHWC if channels_last */
+int hb_dropblock_apply(const void* x, void* out, const float* mask, const float* kept, int N, int C, int H, int W,
+                       int channels_last, int dtype, void* stream);
 
 /* ---- losses: holocron/nn/functional.py:59-113 (focal_loss), :540-613 (poly_loss), :503-537 (dice_loss) --- */
 /* logits x are [N, K, S] (S = prod of spatial dims); kind 0 focal / 1 poly-1; loss_pos: float[N*S];
@@ -118,6 +149,11 @@ int hb_tadam_step(const void* metas, const void* chunks, int num_chunks, int T, 
                   float eps, float weight_decay, int amsgrad, float dof, int step, const int* step_dev, double* scratch,
                   void* stream);
 int hb_step_increment(int* step_dev, void* stream);
+
+/* ---- bookkeeping (not part of the reference surface) ------------------------------------------------ */
+long long hb_launch_count(void);      /* kernels launched through this library since the last reset */
+void hb_launch_count_reset(void);
+const char* hb_version(void);
 
 #ifdef __cplusplus
 }

@@ -85,7 +85,7 @@ def run_bn(M, C, B, act, residual):
     shift = torch.empty(B, C, device=dev)
     VP = ctypes.c_void_p * 3
     arr = lambda ts: VP(*[t.data_ptr() if t is not None else 0 for t in (list(ts) + [None] * 3)[:3]])
-    rc |= L.hb_bn_finalize(ptr(sums), arr(gam), arr(bet), arr(rm), arr(rv), ptr(mean), ptr(rstd), ptr(scale), ptr(shift),
+    rc |= L.hb_bn_finalize(ptr(sums), arr(gam), arr(bet), arr(rm), arr(rv), None, ptr(mean), ptr(rstd), ptr(scale), ptr(shift),
                            B, C, M, ctypes.c_float(1e-5), ctypes.c_float(0.1), stream_ptr())
     out = torch.full((M, C), float("nan"), device=dev, dtype=torch.bfloat16)
     rc |= L.hb_bn_act_fwd_bf16(up[0], up[1], up[2], B, ptr(scale), ptr(shift), ptr(res), ptr(out), M, C, act,
