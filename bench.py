@@ -107,9 +107,9 @@ def run_reference(args, rank):
         return
     from oracle.models import RepVGGOracle
     from oracle.optim import adabelief_step
-    threads = os.cpu_count() or 1
+    threads = cpu_threads()
     torch.set_num_threads(threads)
-    sample = 16
+    sample = 8
     torch.manual_seed(0)
     model = RepVGGOracle("repvgg_a0", num_classes=NUM_CLASSES).train()
     params = [p for p in model.parameters()]
@@ -143,11 +143,21 @@ def run_reference(args, rank):
     }), flush=True)
 
 
+def cpu_threads() -> int:
+    """Threads for the CPU legs. Measured on the 128-thread GPU host (tools/cpu_thread_probe.py, fwd+bwd of an 8-image
+    batch): 8 threads 0.26 s, 16 threads 0.21 s, 32 threads 0.30 s, 64 threads 0.70 s - torch's CPU convolutions stop
+    scaling at ~16 threads for this workload, so the CPU legs use min(16, cpu_count). Override: HB_CPU_THREADS."""
+    env = os.environ.get("HB_CPU_THREADS")
+    if env:
+        return max(1, int(env))
+    return max(1, min(os.cpu_count() or 1, 16))
+
+
 def cpu_baseline(budget_s: float = 20.0):
     """Bounded CPU sample of the same train step (oracle), for the `cpu_baseline` object of the main arm."""
     from oracle.models import RepVGGOracle
     from oracle.optim import adabelief_step
-    threads = os.cpu_count() or 1
+    threads = cpu_threads()
     torch.set_num_threads(threads)
     sample = 8
     torch.manual_seed(0)

@@ -34,14 +34,14 @@ SIGNATURES = {
     "hb_nl_relu_bwd_from_out": "pppzfip",
     "hb_conv2d_fprop_bf16": "ppppp" + "i" * 12 + "p",
     "hb_conv2d_wgrad_bf16": "ppp" + "i" * 11 + "p",
-    "hb_pack_conv_weights": "ppp" + "i" * 7 + "p",
+    "hb_pack_conv_weights": "ppp" + "i" * 8 + "p",
     "hb_zero_insert_bf16": "pp" + "i" * 7 + "p",
     "hb_nchw_to_nhwc_pad_bf16": "pp" + "i" * 6 + "p",
     "hb_bn_stats_bf16": "pppiiipp",
-    "hb_bn_finalize": "pppppp" + "pppp" + "iiiffp",
-    "hb_bn_eval_affine": "ppppfippppp",
-    "hb_bn_act_fwd_bf16": "pppipppp" + "iiifp",
-    "hb_bn_act_bwd_bf16": "ppppi" + "pppppp" + "pppppp" + "iiifip",
+    "hb_bn_finalize": "pppppp" + "pppp" + "iiiiffp",
+    "hb_bn_eval_affine": "ppppfiippppp",
+    "hb_bn_act_fwd_bf16": "pppipppp" + "iiifip",
+    "hb_bn_act_bwd_bf16": "ppppi" + "pppppp" + "pppppp" + "iiifiip",
     "hb_dwconv_fwd_bf16": "pppp" + "iiiiiiip",
     "hb_dwconv_bwd_data_bf16": "ppp" + "iiiiiiip",
     "hb_dwconv_bwd_weight_bf16": "ppppp" + "iiiiiiip",

@@ -155,12 +155,18 @@ struct FinalizeParams {
   float* scale;  // [B][C] out
   float* shift;  // [B][C] out
   int B, C, M;
+  int C_logical;  // channels >= C_logical are padding: scale = shift = 0, no parameter / running-stat access
   float eps, momentum;
 };
 __global__ void bn_finalize_kernel(FinalizeParams p) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (c >= p.C) return;
+  if (c >= p.C_logical) {
+    const size_t o = (size_t)b * p.C + c;
+    p.mean[o] = 0.f; p.rstd[o] = 0.f; p.scale[o] = 0.f; p.shift[o] = 0.f;
+    return;
+  }
   const double s = p.sums[((size_t)b * 2 + 0) * p.C + c];
   const double q = p.sums[((size_t)b * 2 + 1) * p.C + c];
   const double mean = s / p.M;
@@ -185,9 +191,16 @@ __global__ void bn_finalize_kernel(FinalizeParams p) {
 
 // eval-mode affine from running statistics: scale = gamma / sqrt(var + eps), shift = beta - mean * scale
 __global__ void bn_eval_affine_kernel(const float* gamma, const float* beta, const float* rmean, const float* rvar,
-                                      float eps, int C, float* scale, float* shift, float* mean, float* rstd) {
+                                      float eps, int C, int C_logical, float* scale, float* shift, float* mean,
+                                      float* rstd) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
+  if (c >= C_logical) {
+    scale[c] = 0.f; shift[c] = 0.f;
+    if (mean) mean[c] = 0.f;
+    if (rstd) rstd[c] = 0.f;
+    return;
+  }
   const float r = 1.f / sqrtf(rvar[c] + eps);
   const float sc = (gamma ? gamma[c] : 1.f) * r;
   scale[c] = sc;
@@ -206,6 +219,7 @@ struct FwdParams {
   __nv_bfloat16* out;
   int M, C, act;
   float slope;
+  int res_after;  // 1: out = act(z) + residual (ResNet-style shortcut after the activation); 0: act(z + residual)
 };
 __global__ void __launch_bounds__(kThreads) bn_act_fwd_kernel(FwdParams p, Geo g) {
   const int tx = threadIdx.x % g.cg_t, ty = threadIdx.x / g.cg_t;
@@ -239,9 +253,9 @@ __global__ void __launch_bounds__(kThreads) bn_act_fwd_kernel(FwdParams p, Geo g
         for (int j = 0; j < 8; ++j) z[j] = fmaf(sc[b][j], u[j], z[j]);
       }
     }
-    if (p.residual) {
-      float r[8];
-      load8(p.residual + off, r);
+    float r[8];
+    if (p.residual) load8(p.residual + off, r);
+    if (p.residual && !p.res_after) {
       if (p.act == ACT_FRELU) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) z[j] = fmaxf(z[j], r[j]);
@@ -252,6 +266,10 @@ __global__ void __launch_bounds__(kThreads) bn_act_fwd_kernel(FwdParams p, Geo g
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) z[j] = act_fwd(p.act, z[j], p.slope);
+    if (p.residual && p.res_after) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) z[j] += r[j];
+    }
     store8(p.out + off, z);
   }
 }
@@ -272,6 +290,7 @@ struct BwdParams {
   int M, C, act;
   float slope;
   int train;  // 1: batch statistics (full BN backward); 0: running statistics (du = scale * dz)
+  int res_after;
 };
 
 // Per-channel constants of the block's channel slab live in shared memory (keeps the kernels at
@@ -323,6 +342,11 @@ __device__ __forceinline__ void recompute_dz(const BwdParams& p, const SlabConst
   }
   float d[8];
   load8(p.dout + off, d);
+  if (p.residual && p.res_after) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { dz[j] = d[j] * act_grad(p.act, z[j], p.slope); dr[j] = d[j]; }
+    return;
+  }
   if (p.residual) {
     float r[8];
     load8(p.residual + off, r);
@@ -455,7 +479,8 @@ int hb_bn_stats_bf16(const void* u0, const void* u1, const void* u2, int B, int 
 
 int hb_bn_finalize(const double* sums, const float* const* gamma, const float* const* beta, float* const* running_mean,
                    float* const* running_var, long long* const* num_batches_tracked, float* mean, float* rstd,
-                   float* scale, float* shift, int B, int C, int M, float eps, float momentum, void* stream) {
+                   float* scale, float* shift, int B, int C, int C_logical, int M, float eps, float momentum,
+                   void* stream) {
   if (B < 1 || B > kMaxBranches) return (int)cudaErrorInvalidValue;
   FinalizeParams p{};
   p.sums = sums;
@@ -467,27 +492,29 @@ int hb_bn_finalize(const double* sums, const float* const* gamma, const float* c
     p.num_batches_tracked[b] = num_batches_tracked ? num_batches_tracked[b] : nullptr;
   }
   p.mean = mean; p.rstd = rstd; p.scale = scale; p.shift = shift;
-  p.B = B; p.C = C; p.M = M; p.eps = eps; p.momentum = momentum;
+  p.B = B; p.C = C; p.M = M; p.C_logical = C_logical; p.eps = eps; p.momentum = momentum;
   bn_finalize_kernel<<<dim3((C + 127) / 128, B), 128, 0, (cudaStream_t)stream>>>(p);
   HB_LAUNCH_CHECK();
   return 0;
 }
 
 int hb_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
-                      float eps, int C, float* scale, float* shift, float* mean, float* rstd, void* stream) {
+                      float eps, int C, int C_logical, float* scale, float* shift, float* mean, float* rstd,
+                      void* stream) {
   bn_eval_affine_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gamma, beta, running_mean, running_var, eps,
-                                                                            C, scale, shift, mean, rstd);
+                                                                            C, C_logical, scale, shift, mean, rstd);
   HB_LAUNCH_CHECK();
   return 0;
 }
 
 int hb_bn_act_fwd_bf16(const void* u0, const void* u1, const void* u2, int B, const float* scale, const float* shift,
-                       const void* residual, void* out, int M, int C, int act, float slope, void* stream) {
+                       const void* residual, void* out, int M, int C, int act, float slope, int res_after,
+                       void* stream) {
   if (C % 8 != 0 || B < 0 || B > kMaxBranches) return (int)cudaErrorInvalidValue;
   FwdParams p{};
   p.br = Branches{{(const __nv_bfloat16*)u0, (const __nv_bfloat16*)u1, (const __nv_bfloat16*)u2}, B};
   p.scale = scale; p.shift = shift; p.residual = (const __nv_bfloat16*)residual; p.out = (__nv_bfloat16*)out;
-  p.M = M; p.C = C; p.act = act; p.slope = slope;
+  p.M = M; p.C = C; p.act = act; p.slope = slope; p.res_after = res_after;
   Geo g = Geo::make(C);
   bn_act_fwd_kernel<<<make_grid(g, M, 1), kThreads, 0, (cudaStream_t)stream>>>(p, g);
   HB_LAUNCH_CHECK();
@@ -499,7 +526,7 @@ int hb_bn_act_fwd_bf16(const void* u0, const void* u1, const void* u2, int B, co
 int hb_bn_act_bwd_bf16(const void* dout, const void* u0, const void* u1, const void* u2, int B, const float* scale,
                        const float* shift, const float* mean, const float* rstd, const void* residual, double* sums,
                        void* du0, void* du1, void* du2, void* dres, float* dgamma, float* dbeta, int M, int C, int act,
-                       float slope, int train, void* stream) {
+                       float slope, int train, int res_after, void* stream) {
   if (C % 8 != 0 || B < 0 || B > kMaxBranches) return (int)cudaErrorInvalidValue;
   BwdParams p{};
   p.br = Branches{{(const __nv_bfloat16*)u0, (const __nv_bfloat16*)u1, (const __nv_bfloat16*)u2}, B};
@@ -507,7 +534,7 @@ int hb_bn_act_bwd_bf16(const void* dout, const void* u0, const void* u1, const v
   p.scale = scale; p.shift = shift; p.mean = mean; p.rstd = rstd; p.sums = sums;
   p.du[0] = (__nv_bfloat16*)du0; p.du[1] = (__nv_bfloat16*)du1; p.du[2] = (__nv_bfloat16*)du2;
   p.dres = (__nv_bfloat16*)dres;
-  p.M = M; p.C = C; p.act = act; p.slope = slope; p.train = train;
+  p.M = M; p.C = C; p.act = act; p.slope = slope; p.train = train; p.res_after = res_after;
   Geo g = Geo::make(C);
   cudaStream_t st = (cudaStream_t)stream;
   const dim3 grid = make_grid(g, M, 1);

@@ -10,12 +10,12 @@ namespace {
 
 using namespace hb;
 
-// w: [Cout][R][S][Cin] fp32.  wf: [Cout][R][S][CinP] bf16 (zero padded).  wd: [CinD][R][S][CoutP] bf16 with
+// w: [Cout][R][S][Cin] fp32.  wf: [CoutF][R][S][CinP] bf16 (zero padded).  wd: [CinD][R][S][CoutP] bf16 with
 // wd[ci][r][s][co] = w[co][R-1-r][S-1-s][ci] (rows ci >= Cin and columns co >= Cout are zero).
 __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
                                     __nv_bfloat16* __restrict__ wd, int Cout, int Cin, int R, int S, int CinP, int CinD,
-                                    int CoutP) {
-  const size_t nf = (size_t)Cout * R * S * CinP;
+                                    int CoutP, int CoutF) {
+  const size_t nf = (size_t)CoutF * R * S * CinP;
   const size_t nd = wd ? (size_t)CinD * R * S * CoutP : 0;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nf + nd; i += stride) {
@@ -25,7 +25,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
       const int s = t % S; t /= S;
       const int r = t % R;
       const int co = t / R;
-      const float v = ci < Cin ? w[(((size_t)co * R + r) * S + s) * Cin + ci] : 0.f;
+      const float v = (ci < Cin && co < Cout) ? w[(((size_t)co * R + r) * S + s) * Cin + ci] : 0.f;
       wf[i] = __float2bfloat16_rn(v);
     } else {
       const size_t k = i - nf;
@@ -126,11 +126,12 @@ __global__ void gap_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat
 extern "C" {
 
 int hb_pack_conv_weights(const float* w, void* wf, void* wd, int Cout, int Cin, int R, int S, int CinP, int CinD,
-                         int CoutP, void* stream) {
-  const size_t n = (size_t)Cout * R * S * CinP + (wd ? (size_t)CinD * R * S * CoutP : 0);
+                         int CoutP, int CoutF, void* stream) {
+  if (CoutF < Cout || CinP < Cin) return (int)cudaErrorInvalidValue;
+  const size_t n = (size_t)CoutF * R * S * CinP + (wd ? (size_t)CinD * R * S * CoutP : 0);
   if (n == 0) return 0;
   pack_weights_kernel<<<stream_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)wf, (__nv_bfloat16*)wd,
-                                                                             Cout, Cin, R, S, CinP, CinD, CoutP);
+                                                                             Cout, Cin, R, S, CinP, CinD, CoutP, CoutF);
   HB_LAUNCH_CHECK();
   return 0;
 }

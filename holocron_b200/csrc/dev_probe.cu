@@ -1,0 +1,70 @@
+// Hardware probe (development aid, not on the product path): does tcgen05.mma accept a 128B-swizzled K-major A operand
+// whose start address is offset by an arbitrary number of 128-byte rows inside a TMA-written buffer?
+// Answers how the shifted-window (smem halo reuse) convolution can address its filter taps.
+//   out[128 x 64] = A[shift : shift+128, 0:64] * B[64 x 64]^T     A: [rows x 64] bf16 in gmem, B: [64 x 64] bf16
+// mode 0: base_offset field = 0;  mode 1: base_offset = (start_addr >> 7) & 7
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "tmap.cuh"
+
+namespace {
+using namespace tc;
+
+__global__ void __launch_bounds__(128, 1) shift_probe_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                             const __grid_constant__ CUtensorMap tmB, float* out, int shift,
+                                                             int mode, int rows) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sa = smem;                       // rows x 128 B
+  uint8_t* sb = smem + 64 * 1024;           // 64 x 128 B
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 80 * 1024);
+  uint64_t* done = bar + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(done, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(tmem_ptr, 64);
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(bar, rows * 128 + 64 * 128);
+    for (int r0 = 0; r0 < rows; r0 += 128) tma_load_2d(&tmA, bar, sa + r0 * 128, 0, r0);
+    tma_load_2d(&tmB, bar, sb, 0, 0);
+    mbar_wait(bar, 0);
+    tc_fence_after();
+    const uint32_t a_addr = smem_u32(sa) + shift * 128;
+    const uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
+    for (int k = 0; k < 4; ++k) {
+      uint64_t ad = make_smem_desc(a_addr + k * 32, 16, 1024, kLayoutSW128);
+      if (mode == 1) ad |= (uint64_t)((a_addr >> 7) & 7) << 49;
+      const uint64_t bd = make_smem_desc(smem_u32(sb) + k * 32, 16, 1024, kLayoutSW128);
+      umma_f16(tmem, ad, bd, idesc, k > 0);
+    }
+    umma_commit(done);
+  }
+  mbar_wait(done, 0);
+  tc_fence_after();
+  for (int c = 0; c < 64; c += 16) {
+    uint32_t v[16];
+    tmem_ld_x16(tmem + ((uint32_t)(warp * 32) << 16) + c, v);
+    tmem_ld_wait();
+    for (int j = 0; j < 16; ++j) out[(warp * 32 + lane) * 64 + c + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before(); __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 64); }
+}
+}  // namespace
+
+extern "C" int hb_dev_umma_shift_probe(const void* a, const void* b, float* out, int rows, int shift, int mode, void* stream) {
+  if (rows > 512 || rows % 128 != 0 || shift + 128 > rows) return (int)cudaErrorInvalidValue;
+  CUtensorMap tmA, tmB;
+  uint64_t dimsA[2] = {64, (uint64_t)rows}, dimsB[2] = {64, 64}, strides[1] = {128};
+  uint32_t boxA[2] = {64, 128}, boxB[2] = {64, 64};
+  int rc = tmap::encode_tiled_bf16(&tmA, a, 2, dimsA, strides, boxA, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  rc = tmap::encode_tiled_bf16(&tmB, b, 2, dimsB, strides, boxB, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  cudaFuncSetAttribute(shift_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  shift_probe_kernel<<<1, 128, 90 * 1024, (cudaStream_t)stream>>>(tmA, tmB, out, shift, mode, rows);
+  HB_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,111 @@
+"""Execution of reference-shaped module stacks on the fused kernels.
+
+The reference builds every backbone from ``conv_sequence`` lists ``[Conv2d, BatchNorm2d?, act?, DropBlock2d?]`` wrapped
+in ``nn.Sequential`` (holocron/models/utils.py:28-86). The model files of this package keep exactly those module trees
+(so ``state_dict`` keys and the init RNG order are unchanged) but use :class:`FusedSequential`, whose ``forward`` walks the
+stack and maps every ``conv -> BN -> act`` run onto
+  * the tcgen05 implicit-GEMM convolution (dense) or the depth-wise kernel (``groups == channels``), and
+  * ONE fused normalise/(residual)/activate pass (+ one statistics pass in training),
+instead of 3-4 separate library kernels. Anything it does not recognise is simply called.
+"""
+from typing import List, Optional, Sequence
+
+import torch
+from torch import Tensor, nn
+
+from ..nn import _fused as K
+
+_ACTS = (nn.ReLU, nn.ReLU6, nn.SiLU, nn.LeakyReLU, nn.Mish, nn.Identity)
+
+
+def _is_act(m: nn.Module) -> bool:
+    return isinstance(m, _ACTS) or type(m).__name__ == "HardMish"
+
+
+def _dense_ok(conv: nn.Conv2d) -> bool:
+    return (conv.groups == 1 and conv.padding_mode == "zeros" and conv.kernel_size[0] == conv.kernel_size[1]
+            and conv.stride[0] == conv.stride[1] and conv.padding[0] == conv.padding[1]
+            and conv.dilation[0] == conv.dilation[1] == 1 and isinstance(conv.padding[0], int))
+
+
+def _depthwise_ok(conv: nn.Conv2d) -> bool:
+    return (conv.groups == conv.in_channels == conv.out_channels and conv.padding_mode == "zeros"
+            and conv.kernel_size[0] == conv.kernel_size[1] and conv.stride[0] == conv.stride[1]
+            and conv.padding[0] == conv.padding[1] and conv.dilation[0] == conv.dilation[1] == 1
+            and conv.in_channels % 8 == 0)
+
+
+def conv_bn_act(x: Tensor, conv: nn.Conv2d, bn: Optional[nn.BatchNorm2d], act: Optional[nn.Module],
+                residual: Optional[Tensor] = None, res_after_act: bool = False, keep_padded: bool = False) -> Tensor:
+    """One ``conv -> BN -> act`` unit (+ optional shortcut) on the fused kernels."""
+    if _dense_ok(conv):
+        if bn is None and residual is None:
+            code, slope = K.act_code(act)
+            return K.conv2d_bias_act(x, conv.weight, conv.bias, conv.stride[0], conv.padding[0], code, slope)
+        y = K.conv2d(x, conv.weight, conv.bias, conv.stride[0], conv.padding[0], keep_padded=keep_padded or bn is not None)
+    elif _depthwise_ok(conv):
+        from ..nn._dwconv import dwconv2d
+        y = dwconv2d(x, conv.weight, conv.bias, conv.stride[0], conv.padding[0])
+    else:
+        y = conv(x)  # grouped / asymmetric convolutions are outside the hot path: library call
+    code, slope = K.act_code(act)
+    if bn is not None:
+        out = K.bn_act([y], [bn], code, slope, residual=residual, res_after_act=res_after_act)
+        if out.shape[1] != conv.out_channels and not keep_padded:
+            out = out[:, :conv.out_channels]
+        return out
+    if residual is not None:
+        cfg = ([], code, slope, False, True, res_after_act)
+        raise NotImplementedError("shortcut without normalisation layer")
+    return y if code == K.ACT_NONE else K.act_only(y, code, slope)
+
+
+def run_fused(mods: Sequence[nn.Module], x: Tensor, residual: Optional[Tensor] = None,
+              res_after_act: bool = False) -> Tensor:
+    """Runs ``mods`` sequentially, fusing conv/BN/act runs. ``residual`` is fused into the LAST conv unit."""
+    mods = list(mods)
+    # index of the last convolution (the unit the shortcut is attached to)
+    last_conv = max((i for i, m in enumerate(mods) if isinstance(m, nn.Conv2d)), default=-1)
+    i = 0
+    while i < len(mods):
+        m = mods[i]
+        if isinstance(m, nn.Conv2d):
+            j = i + 1
+            bn = act = None
+            if j < len(mods) and isinstance(mods[j], nn.BatchNorm2d):
+                bn = mods[j]; j += 1
+            if j < len(mods) and _is_act(mods[j]):
+                act = mods[j]; j += 1
+            res = residual if i == last_conv else None
+            x = conv_bn_act(x, m, bn, act, res, res_after_act)
+            if res is not None:
+                residual = None
+            i = j
+        elif isinstance(m, FusedSequential):
+            x = m(x)
+            i += 1
+        elif isinstance(m, nn.BatchNorm2d):
+            act = None
+            j = i + 1
+            if j < len(mods) and _is_act(mods[j]):
+                act = mods[j]; j += 1
+            code, slope = K.act_code(act)
+            x = K.bn_act([x], [m], code, slope)
+            i = j
+        elif _is_act(m) and x.is_cuda and x.ndim == 4 and x.shape[1] % 8 == 0 and not isinstance(m, nn.Identity):
+            code, slope = K.act_code(m)
+            x = K.act_only(x, code, slope)
+            i += 1
+        else:
+            x = m(x)
+            i += 1
+    if residual is not None:
+        x = x + residual
+    return x
+
+
+class FusedSequential(nn.Sequential):
+    """Drop-in ``nn.Sequential`` (same children, same ``state_dict``) executed by :func:`run_fused`."""
+
+    def forward(self, x: Tensor) -> Tensor:  # type: ignore[override]
+        return run_fused(list(self), x)

@@ -1,1 +1,2 @@
 from .repvgg import *  # noqa: F401,F403
+from .darknet import *  # noqa: F401,F403

@@ -89,19 +89,23 @@ def _empty_cl(n: int, c: int, h: int, w: int, device, dtype=torch.bfloat16) -> T
 # ------------------------------------------------------------------------------------------------------
 # filter packing cache: fp32 master (any layout) -> bf16 KRSC for fprop, flipped+transposed bf16 for dgrad
 class PackedFilter:
-    __slots__ = ("wf", "wd", "key", "cin_p", "cout", "cin", "r", "s")
+    __slots__ = ("wf", "wd", "key", "cin_p", "cout_p", "cin_d", "cout", "cin", "r", "s")
 
 
 _pack_cache = {}
 
 
-def pack_filter(weight: Tensor, need_dgrad: bool) -> PackedFilter:
+def pack_filter(weight: Tensor, need_dgrad: bool, cin_p: Optional[int] = None) -> PackedFilter:
+    """bf16 KRSC copy of an fp32 (Cout, Cin, kh, kw) filter, rows zero-padded to Cout % 16 == 0 and channels to
+    ``cin_p`` (the channel count of the activation it will meet, >= Cin, % 8 == 0); plus, for the data-gradient pass,
+    the flipped/transposed filter [cin_d][R][S][cout_p] with cin_d % 16 == 0."""
     cout, cin, r, s = weight.shape
-    key = (weight.data_ptr(), weight._version, need_dgrad, tuple(weight.stride()))
+    if cin_p is None:
+        cin_p = round_up(cin, 8)
+    key = (weight.data_ptr(), weight._version, need_dgrad, tuple(weight.stride()), cin_p)
     ent = _pack_cache.get(id(weight))
     if ent is not None and ent.key == key:
         return ent
-    cin_p = round_up(cin, 8)
     w = weight.detach()
     if w.dtype != torch.float32:
         w = w.float()
@@ -111,14 +115,25 @@ def pack_filter(weight: Tensor, need_dgrad: bool) -> PackedFilter:
         w_krsc = w_krsc.contiguous()
     ent = PackedFilter()
     ent.key, ent.cin_p, ent.cout, ent.cin, ent.r, ent.s = key, cin_p, cout, cin, r, s
-    ent.wf = torch.empty((cout, r, s, cin_p), device=w.device, dtype=torch.bfloat16)
-    cout_p = round_up(cout, 8)
-    cin_d = round_up(cin, 16)
-    ent.wd = torch.empty((cin_d, r, s, cout_p), device=w.device, dtype=torch.bfloat16) if need_dgrad else None
-    check(lib().hb_pack_conv_weights(ptr(w_krsc), ptr(ent.wf), ptr(ent.wd), cout, cin, r, s, cin_p, cin_d, cout_p,
-                                     stream_ptr()), "hb_pack_conv_weights")
+    ent.cout_p = round_up(cout, 16)
+    ent.cin_d = round_up(cin_p, 16)
+    ent.wf = torch.empty((ent.cout_p, r, s, cin_p), device=w.device, dtype=torch.bfloat16)
+    ent.wd = torch.empty((ent.cin_d, r, s, ent.cout_p), device=w.device, dtype=torch.bfloat16) if need_dgrad else None
+    check(lib().hb_pack_conv_weights(ptr(w_krsc), ptr(ent.wf), ptr(ent.wd), cout, cin, r, s, cin_p, ent.cin_d, ent.cout_p,
+                                     ent.cout_p, stream_ptr()), "hb_pack_conv_weights")
     _pack_cache[id(weight)] = ent
     return ent
+
+
+def _pad_vec(v: Optional[Tensor], n: int) -> Optional[Tensor]:
+    if v is None:
+        return None
+    v = v.detach().float().contiguous()
+    if v.numel() == n:
+        return v
+    out = torch.zeros(n, device=v.device, dtype=torch.float32)
+    out[:v.numel()] = v
+    return out
 
 
 def conv_out_size(h: int, k: int, stride: int, pad: int, dil: int) -> int:
@@ -139,68 +154,70 @@ def conv2d_forward_raw(x: Tensor, wf: Tensor, cout: int, r: int, s: int, stride:
 
 
 class _Conv2dFn(torch.autograd.Function):
-    """y = conv2d(x, weight) (+ bias) on the tcgen05 implicit-GEMM kernels; backward = dgrad + wgrad kernels."""
+    """y = conv2d(x, weight) (+ bias) on the tcgen05 implicit-GEMM kernels; backward = dgrad + wgrad kernels.
+
+    Channel counts that do not fit the kernels' granularity are zero-padded internally: the input to a multiple of 8
+    (or whatever padded width the incoming activation already has), the output to a multiple of 16. With
+    ``keep_padded`` the padded output is returned as is (its extra channels are exactly zero), otherwise it is sliced
+    back to ``out_channels``."""
 
     @staticmethod
-    def forward(ctx, x: Tensor, weight: Tensor, bias: Optional[Tensor], stride: int, pad: int, dil: int) -> Tensor:
+    def forward(ctx, x: Tensor, weight: Tensor, bias: Optional[Tensor], stride: int, pad: int, dil: int,
+                keep_padded: bool) -> Tensor:
         cout, cin, r, s = weight.shape
-        if cout % 16 != 0:
-            raise NotImplementedError("tensor-core conv needs out_channels % 16 == 0 (pad the layer)")
+        if x.shape[1] < cin:
+            raise RuntimeError(f"expected an input with at least {cin} channels, got {x.shape[1]}")
         need_dx = ctx.needs_input_grad[0]
-        pk = pack_filter(weight, need_dx)
+        pk = pack_filter(weight, need_dx, round_up(x.shape[1], 8))
         xb = to_channels_last_bf16(x, pk.cin_p)
-        bias_f = None if bias is None else bias.detach().float().contiguous()
-        y = conv2d_forward_raw(xb, pk.wf, cout, r, s, stride, pad, dil, bias_f)
+        y = conv2d_forward_raw(xb, pk.wf, pk.cout_p, r, s, stride, pad, dil, _pad_vec(bias, pk.cout_p))
         ctx.save_for_backward(xb, weight)
-        ctx.cfg = (stride, pad, dil, pk.wd, bias is not None, x.shape[1])
-        return y
+        ctx.cfg = (stride, pad, dil, pk.wd, bias is not None, x.shape[1], pk.cout_p, pk.cin_d)
+        return y if (keep_padded or pk.cout_p == cout) else y[:, :cout]
 
     @staticmethod
     def backward(ctx, dy: Tensor):
         xb, weight = ctx.saved_tensors
-        stride, pad, dil, wd, has_bias, cin_logical = ctx.cfg
+        stride, pad, dil, wd, has_bias, cin_x, cout_p, cin_d = ctx.cfg
         cout, cin, r, s = weight.shape
         n, cin_p, h, w = xb.shape
-        dyb = to_channels_last_bf16(dy)
+        dyb = to_channels_last_bf16(dy, cout_p)
         ho, wo = dyb.shape[2], dyb.shape[3]
         L = lib()
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             if dil != 1:
                 raise NotImplementedError("dgrad with dilation > 1")
-            cin_d, cout_p = wd.shape[0], wd.shape[3]
-            if cout_p != cout:
-                raise NotImplementedError("dgrad needs out_channels % 8 == 0")
             src = dyb
             if stride > 1:
-                src = _empty_cl(n, cout, h, w, dyb.device)
-                check(L.hb_zero_insert_bf16(ptr(dyb), ptr(src), n, ho, wo, h, w, cout, stride, stream_ptr()),
+                src = _empty_cl(n, cout_p, h, w, dyb.device)
+                check(L.hb_zero_insert_bf16(ptr(dyb), ptr(src), n, ho, wo, h, w, cout_p, stride, stream_ptr()),
                       "hb_zero_insert_bf16")
             dxp = _empty_cl(n, cin_d, h, w, dyb.device)
-            info = dict(N=n, H=h, W=w, Cin=cout, Cout=cin_d, R=r, S=s, stride=1, Ho=h, Wo=w, dgrad_of_stride=stride)
+            info = dict(N=n, H=h, W=w, Cin=cout_p, Cout=cin_d, R=r, S=s, stride=1, Ho=h, Wo=w, dgrad_of_stride=stride)
             _timed("dgrad", info, lambda: check(
-                L.hb_conv2d_fprop_bf16(ptr(src), ptr(wd), ptr(dxp), ptr(None), ptr(None), n, h, w, cout, cin_d, r, s, 1,
+                L.hb_conv2d_fprop_bf16(ptr(src), ptr(wd), ptr(dxp), ptr(None), ptr(None), n, h, w, cout_p, cin_d, r, s, 1,
                                        (r - 1) * dil - pad, 1, ACT_NONE, 0, stream_ptr()), "hb_conv2d_fprop_bf16[dgrad]"))
-            dx = dxp if cin_d == cin_logical else dxp[:, :cin_logical]
+            dx = dxp if cin_d == cin_x else dxp[:, :cin_x]
         if ctx.needs_input_grad[1]:
-            dwp = torch.empty((cout, r, s, cin_p), device=dyb.device, dtype=torch.float32)
-            info = dict(N=n, H=h, W=w, Cin=cin_p, Cout=cout, R=r, S=s, stride=stride, Ho=ho, Wo=wo)
+            dwp = torch.empty((cout_p, r, s, cin_p), device=dyb.device, dtype=torch.float32)
+            info = dict(N=n, H=h, W=w, Cin=cin_p, Cout=cout_p, R=r, S=s, stride=stride, Ho=ho, Wo=wo)
             _timed("wgrad", info, lambda: check(
-                L.hb_conv2d_wgrad_bf16(ptr(xb), ptr(dyb), ptr(dwp), n, h, w, cin_p, cout, r, s, stride, pad, dil, 0,
+                L.hb_conv2d_wgrad_bf16(ptr(xb), ptr(dyb), ptr(dwp), n, h, w, cin_p, cout_p, r, s, stride, pad, dil, 0,
                                        stream_ptr()), "hb_conv2d_wgrad_bf16"))
             dw = dwp.permute(0, 3, 1, 2)
-            if cin_p != cin:
-                dw = dw[:, :cin].contiguous(memory_format=torch.channels_last)
+            if cin_p != cin or cout_p != cout:
+                dw = dw[:cout, :cin].contiguous(memory_format=torch.channels_last)
         if has_bias and ctx.needs_input_grad[2]:
-            db = dyb.float().sum((0, 2, 3))
-        return dx, dw, db, None, None, None
+            db = dyb[:, :cout].float().sum((0, 2, 3))
+        return dx, dw, db, None, None, None, None
 
 
 def conv2d(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, stride: int = 1, padding: int = 0,
-           dilation: int = 1) -> Tensor:
+           dilation: int = 1, keep_padded: bool = False) -> Tensor:
     """Dense (groups=1) 2-D convolution on the sm_100a tensor cores; returns bf16 channels_last."""
     require_cuda(x, weight)
-    return _Conv2dFn.apply(x, weight, bias, int(stride), int(padding), int(dilation))
+    return _Conv2dFn.apply(x, weight, bias, int(stride), int(padding), int(dilation), bool(keep_padded))
 
 
 def conv2d_bias_act(x: Tensor, weight: Tensor, bias: Optional[Tensor], stride: int, padding: int, act: int = ACT_NONE,
@@ -212,13 +229,11 @@ def conv2d_bias_act(x: Tensor, weight: Tensor, bias: Optional[Tensor], stride: i
                                               (bias is not None and bias.requires_grad))
     if not needs_grad and act in (ACT_NONE, ACT_RELU):
         cout, cin, r, s = weight.shape
-        if cout % 16 != 0:
-            raise NotImplementedError("tensor-core conv needs out_channels % 16 == 0 (pad the layer)")
-        pk = pack_filter(weight, False)
+        pk = pack_filter(weight, False, round_up(x.shape[1], 8))
         xb = to_channels_last_bf16(x, pk.cin_p)
-        bias_f = None if bias is None else bias.detach().float().contiguous()
-        return conv2d_forward_raw(xb, pk.wf, cout, r, s, stride, padding, 1, bias_f, None, act)
-    y = _Conv2dFn.apply(x, weight, bias, int(stride), int(padding), 1)
+        y = conv2d_forward_raw(xb, pk.wf, pk.cout_p, r, s, stride, padding, 1, _pad_vec(bias, pk.cout_p), None, act)
+        return y if pk.cout_p == cout else y[:, :cout]
+    y = _Conv2dFn.apply(x, weight, bias, int(stride), int(padding), 1, False)
     if act == ACT_NONE:
         return y
     return act_only(y, act, slope)
@@ -247,7 +262,7 @@ class _BNActFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, cfg, *tensors: Tensor) -> Tensor:
-        branches, act, slope, training, has_res = cfg
+        branches, act, slope, training, has_res, res_after = cfg
         nb = len(branches)
         us = [to_channels_last_bf16(t) for t in tensors[:nb]]
         gammas = tensors[nb:2 * nb]
@@ -263,6 +278,7 @@ class _BNActFn(torch.autograd.Function):
         mean, rstd, scale, shift = stats[0], stats[1], stats[2], stats[3]
         g32 = [g.detach().float() for g in gammas]
         b32 = [b.detach().float() for b in betas]
+        c_log = g32[0].numel() if nb else c   # parameters may be narrower than a zero-padded activation
         up = [ptr(us[i]) if i < nb else ptr(None) for i in range(3)]
         if nb == 0:
             pass
@@ -280,23 +296,23 @@ class _BNActFn(torch.autograd.Function):
                                    _arr3([b.running_mean for b in branches]) if track else None,
                                    _arr3([b.running_var for b in branches]) if track else None,
                                    _arr3([b.num_batches_tracked for b in branches]) if track else None,
-                                   ptr(mean), ptr(rstd), ptr(scale), ptr(shift), nb, c, m, _c_float(eps), _c_float(mom),
-                                   stream_ptr()), "hb_bn_finalize")
+                                   ptr(mean), ptr(rstd), ptr(scale), ptr(shift), nb, c, c_log, m, _c_float(eps),
+                                   _c_float(mom), stream_ptr()), "hb_bn_finalize")
         else:
             for i, b in enumerate(branches):
                 check(L.hb_bn_eval_affine(ptr(g32[i]), ptr(b32[i]), ptr(b.running_mean), ptr(b.running_var),
-                                          _c_float(b.eps), c, ptr(scale[i]), ptr(shift[i]), ptr(mean[i]), ptr(rstd[i]),
-                                          stream_ptr()), "hb_bn_eval_affine")
+                                          _c_float(b.eps), c, c_log, ptr(scale[i]), ptr(shift[i]), ptr(mean[i]),
+                                          ptr(rstd[i]), stream_ptr()), "hb_bn_eval_affine")
         out = _empty_cl(n, c, h, w, dev)
         check(L.hb_bn_act_fwd_bf16(up[0], up[1], up[2], nb, ptr(scale), ptr(shift), ptr(res), ptr(out), m, c, act,
-                                   _c_float(slope), stream_ptr()), "hb_bn_act_fwd_bf16")
+                                   _c_float(slope), int(res_after), stream_ptr()), "hb_bn_act_fwd_bf16")
         ctx.save_for_backward(stats, *us, *([res] if has_res else []))
-        ctx.cfg = (nb, act, slope, training, has_res)
+        ctx.cfg = (nb, act, slope, training, has_res, c_log, int(res_after))
         return out
 
     @staticmethod
     def backward(ctx, dout: Tensor):
-        nb, act, slope, training, has_res = ctx.cfg
+        nb, act, slope, training, has_res, c_log, res_after = ctx.cfg
         saved = ctx.saved_tensors
         stats, us = saved[0], saved[1:1 + nb]
         res = saved[1 + nb] if has_res else None
@@ -318,26 +334,29 @@ class _BNActFn(torch.autograd.Function):
         check(L.hb_bn_act_bwd_bf16(ptr(dob), up[0], up[1], up[2], nb, ptr(scale), ptr(shift), ptr(mean), ptr(rstd),
                                    ptr(res), ptr(sums), dup[0], dup[1], dup[2], ptr(dres),
                                    ptr(dgb[0]) if need_gb else ptr(None), ptr(dgb[1]) if need_gb else ptr(None), m, c,
-                                   act, _c_float(slope), 1 if training else 0, stream_ptr()), "hb_bn_act_bwd_bf16")
+                                   act, _c_float(slope), 1 if training else 0, res_after, stream_ptr()),
+              "hb_bn_act_bwd_bf16")
         grads: List[Optional[Tensor]] = [None]
         grads += dus
-        grads += [dgb[0][i] if need_gb else None for i in range(nb)]
-        grads += [dgb[1][i] if need_gb else None for i in range(nb)]
+        grads += [dgb[0][i][:c_log] if need_gb else None for i in range(nb)]
+        grads += [dgb[1][i][:c_log] if need_gb else None for i in range(nb)]
         if has_res:
             grads.append(dres)
         return tuple(grads)
 
 
 def bn_act(us: Sequence[Tensor], bns: Sequence[nn.BatchNorm2d], act: int = ACT_NONE, slope: float = 0.0,
-           residual: Optional[Tensor] = None, training: Optional[bool] = None) -> Tensor:
-    """act(sum_b BatchNorm_b(u_b) + residual) as one fused pass (plus one statistics pass in training)."""
+           residual: Optional[Tensor] = None, training: Optional[bool] = None, res_after_act: bool = False) -> Tensor:
+    """act(sum_b BatchNorm_b(u_b) + residual) as one fused pass (plus one statistics pass in training);
+    ``res_after_act`` moves the residual outside the activation: act(sum_b ...) + residual."""
     if not 1 <= len(us) <= 3 or len(us) != len(bns):
         raise ValueError("between 1 and 3 (input, BatchNorm2d) pairs are supported")
     require_cuda(*us)
     if training is None:
         training = bns[0].training
     use_batch_stats = training or bns[0].running_mean is None
-    cfg = ([BNBranch(b) for b in bns], int(act), float(slope), bool(use_batch_stats), residual is not None)
+    cfg = ([BNBranch(b) for b in bns], int(act), float(slope), bool(use_batch_stats), residual is not None,
+           bool(res_after_act))
     args = list(us) + [b.weight for b in bns] + [b.bias for b in bns]
     if residual is not None:
         args.append(residual)
@@ -346,7 +365,7 @@ def bn_act(us: Sequence[Tensor], bns: Sequence[nn.BatchNorm2d], act: int = ACT_N
 
 def act_only(x: Tensor, act: int, slope: float = 0.0) -> Tensor:
     """Stand-alone activation through the fused pass (zero BN branches, x as the residual input)."""
-    cfg = ([], int(act), float(slope), False, True)
+    cfg = ([], int(act), float(slope), False, True, False)
     return _BNActFn.apply(cfg, x)
 
 

@@ -41,10 +41,10 @@ int hb_conv2d_fprop_bf16(const void* x, const void* w, void* y, const float* bia
 /* dw[Cout,R,S,Cin] (fp32, overwritten) = sum over pixels of dy[N,Ho,Wo,Cout] x im2col(x[N,H,W,Cin]) */
 int hb_conv2d_wgrad_bf16(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int R, int S,
                          int stride, int pad, int dil, int num_ctas, void* stream);
-/* fp32 KRSC master filter -> bf16 KRSC (Cin zero-padded to CinP) and, if wd != NULL, the flipped + transposed
- * bf16 filter [CinD][R][S][CoutP] used by the data-gradient pass */
+/* fp32 KRSC master filter -> bf16 KRSC [CoutF][R][S][CinP] (zero-padded rows / channels) and, if wd != NULL, the
+ * flipped + transposed bf16 filter [CinD][R][S][CoutP] used by the data-gradient pass */
 int hb_pack_conv_weights(const float* w, void* wf, void* wd, int Cout, int Cin, int R, int S, int CinP, int CinD,
-                         int CoutP, void* stream);
+                         int CoutP, int CoutF, void* stream);
 /* y[N,Ho,Wo,C] = zeros, y[n, sp*p, sp*q, :] = x[n,p,q,:]  (input of a stride-sp transposed convolution) */
 int hb_zero_insert_bf16(const void* x, void* y, int N, int Hi, int Wi, int Ho, int Wo, int C, int sp, void* stream);
 /* NCHW image (dtype code) -> NHWC bf16 with channels zero-padded to CP (CP % 8 == 0) */
@@ -59,18 +59,23 @@ int hb_bn_stats_bf16(const void* u0, const void* u1, const void* u2, int B, int 
  * num_batches_tracked counters, like nn.BatchNorm2d in training mode. */
 int hb_bn_finalize(const double* sums, const float* const* gamma, const float* const* beta, float* const* running_mean,
                    float* const* running_var, long long* const* num_batches_tracked, float* mean, float* rstd,
-                   float* scale, float* shift, int B, int C, int M, float eps, float momentum, void* stream);
+                   float* scale, float* shift, int B, int C, int C_logical, int M, float eps, float momentum,
+                   void* stream);
+/* channels in [C_logical, C) are zero padding (the parameter arrays hold C_logical entries): scale = shift = 0 */
 int hb_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
-                      float eps, int C, float* scale, float* shift, float* mean, float* rstd, void* stream);
-/* out = act(sum_b (scale_b * u_b + shift_b) + residual); act: 0 none 1 relu 2 relu6 3 silu 4 leaky(slope) 5 mish
+                      float eps, int C, int C_logical, float* scale, float* shift, float* mean, float* rstd,
+                      void* stream);
+/* out = act(sum_b (scale_b * u_b + shift_b) + residual)  [res_after = 1: act(sum_b ...) + residual, the shortcut of
+ * holocron/models/classification/resnet.py:75-87 (_ResBlock.forward) used by the Darknet ResBlocks]; act: 0 none 1 relu 2 relu6 3 silu 4 leaky(slope) 5 mish
  * 6 hard_mish, 7 funnel: out = max(sum_b(...), residual) (FReLU, holocron/nn/modules/activation.py:58-82) */
 int hb_bn_act_fwd_bf16(const void* u0, const void* u1, const void* u2, int B, const float* scale, const float* shift,
-                       const void* residual, void* out, int M, int C, int act, float slope, void* stream);
+                       const void* residual, void* out, int M, int C, int act, float slope, int res_after,
+                       void* stream);
 /* backward of the above; sums: double [1+B][C] pre-zeroed scratch; du_b/dres/dgamma/dbeta may be NULL */
 int hb_bn_act_bwd_bf16(const void* dout, const void* u0, const void* u1, const void* u2, int B, const float* scale,
                        const float* shift, const float* mean, const float* rstd, const void* residual, double* sums,
                        void* du0, void* du1, void* du2, void* dres, float* dgamma, float* dbeta, int M, int C, int act,
-                       float slope, int train, void* stream);
+                       float slope, int train, int res_after, void* stream);
 
 /* ---- depth-wise k x k convolution (NHWC bf16; weights fp32 [C,K,K]): FReLU's conv (activation.py:71-73) and the
  *      ReXNet depth-wise stage (holocron/models/classification/rexnet.py:112-125) ------------------------- */

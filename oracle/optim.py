@@ -17,15 +17,15 @@ def adabelief_step(p: Tensor, g: Tensor, m: Tensor, s: Tensor, step: int, lr: fl
     """reference optim/adabelief.py:121-167. No +eps inside the belief EMA (unlike the paper)."""
     if weight_decay != 0:
         g = g + weight_decay * p
-    m.copy_(beta1 * m + (1 - beta1) * g)
+    m.mul_(beta1).add_(g, alpha=1 - beta1)          # in-place: the CPU baseline times this function
     r = g - m
-    s.copy_(beta2 * s + (1 - beta2) * r * r)
+    s.mul_(beta2).addcmul_(r, r, value=1 - beta2)
     second = s
     if amsgrad:
-        s_max.copy_(torch.maximum(s_max, s))
+        torch.maximum(s_max, s, out=s_max)
         second = s_max
-    denom = second.sqrt() / math.sqrt(1 - beta2**step) + eps
-    p.sub_((lr / (1 - beta1**step)) * m / denom)
+    denom = second.sqrt().div_(math.sqrt(1 - beta2**step)).add_(eps)
+    p.addcdiv_(m, denom, value=-(lr / (1 - beta1**step)))
 
 
 @torch.no_grad()

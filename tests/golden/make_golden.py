@@ -258,7 +258,7 @@ def gen_models():
     torch.save(d, OUT / "models.pt")
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--zoo" not in sys.argv:
     gen_activations()
     gen_losses()
     gen_boxes()
@@ -267,3 +267,64 @@ if __name__ == "__main__":
     gen_models()
     for f in sorted(OUT.glob("*.pt")):
         print(f.name, f.stat().st_size)
+
+
+def gen_zoo():
+    """Model-zoo fixtures (rows a11-a14, a21 of SURVEY §8): seeded init (identical in both implementations, checked by
+    the state_dict tests), small inputs, training-mode forward + loss + a few gradients from the reference."""
+    models = holocron.models
+    d = {}
+
+    def grads_of(model, names):
+        ps = dict(model.named_parameters())
+        return {n: ps[n].grad.clone() for n in names}
+
+    for name in ("darknet53", "cspdarknet53"):
+        torch.manual_seed(0)
+        m = getattr(models, name)(num_classes=10).train()
+        torch.manual_seed(1)
+        x = torch.rand(2, 3, 64, 64)
+        t = torch.tensor([3, 7])
+        out = m(x)
+        loss = torch.nn.functional.cross_entropy(out, t)
+        loss.backward()
+        first = next(n for n, _ in m.named_parameters())
+        d[name] = dict(x=x, t=t, logits=out.detach(), loss=loss.detach(),
+                       grads=grads_of(m, [first, "classifier.weight"]), first=first)
+    # UNet3+ with DiceLoss (BASELINE config 5, at 64x64)
+    torch.manual_seed(0)
+    m = models.segmentation.unet3p(num_classes=21).train()
+    torch.manual_seed(2)
+    x = torch.rand(1, 3, 64, 64)
+    mask = torch.randint(0, 21, (1, 64, 64))
+    onehot = torch.nn.functional.one_hot(mask, 21).movedim(-1, 1).float()
+    out = m(x)
+    loss = F.dice_loss(torch.softmax(out, 1), onehot)
+    loss.backward()
+    d["unet3p"] = dict(x=x, mask=mask, out=out.detach(), loss=loss.detach(),
+                       grads=grads_of(m, ["encoder.0.0.weight", "classifier.weight"]))
+    # YOLOv4 (BASELINE config 4, at 128x128), DropBlock disabled (its RNG stream is device specific)
+    from holocron.nn import DropBlock2d
+    torch.manual_seed(0)
+    m = models.detection.yolov4(pretrained_backbone=False, num_classes=80).train()
+    for mod in m.modules():
+        if isinstance(mod, DropBlock2d):
+            mod.p = 0.0
+    torch.manual_seed(3)
+    x = torch.rand(2, 3, 128, 128)
+    target = []
+    for _ in range(2):
+        xy = torch.rand(3, 2) * 0.7
+        wh = torch.rand(3, 2) * 0.2 + 0.05
+        target.append({"boxes": torch.cat([xy, (xy + wh).clamp(max=1.0)], 1), "labels": torch.randint(0, 80, (3,))})
+    losses = m(x, target)
+    total = sum(losses.values())
+    total.backward()
+    d["yolov4"] = dict(x=x, target=target, losses={k: v.detach() for k, v in losses.items()},
+                       grads=grads_of(m, ["head.head3.24.weight", "head.head1.3.bias", "neck.pan2.convs.0.weight"]))
+    torch.save(d, OUT / "zoo.pt")
+
+
+if __name__ == "__main__" and "--zoo" in sys.argv:
+    gen_zoo()
+    print("zoo.pt", (OUT / "zoo.pt").stat().st_size)

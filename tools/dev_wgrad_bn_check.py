@@ -49,7 +49,7 @@ def run_dgrad(N, H, W, Cin, Cout, k, stride, pad):
     w_krsc = w.permute(0, 2, 3, 1).contiguous()  # fp32 KRSC master
     wf = torch.empty(Cout, k, k, Cin, device="cuda", dtype=torch.bfloat16)
     wd = torch.empty(Cin, k, k, Cout, device="cuda", dtype=torch.bfloat16)
-    rc = L.hb_pack_conv_weights(ptr(w_krsc), ptr(wf), ptr(wd), Cout, Cin, k, k, Cin, Cin, Cout, stream_ptr())
+    rc = L.hb_pack_conv_weights(ptr(w_krsc), ptr(wf), ptr(wd), Cout, Cin, k, k, Cin, Cin, Cout, Cout, stream_ptr())
     dy_nhwc = dy.permute(0, 2, 3, 1).contiguous()
     if stride > 1:
         dyu = torch.empty(N, H, W, Cout, device="cuda", dtype=torch.bfloat16)
@@ -86,10 +86,10 @@ def run_bn(M, C, B, act, residual):
     VP = ctypes.c_void_p * 3
     arr = lambda ts: VP(*[t.data_ptr() if t is not None else 0 for t in (list(ts) + [None] * 3)[:3]])
     rc |= L.hb_bn_finalize(ptr(sums), arr(gam), arr(bet), arr(rm), arr(rv), None, ptr(mean), ptr(rstd), ptr(scale), ptr(shift),
-                           B, C, M, ctypes.c_float(1e-5), ctypes.c_float(0.1), stream_ptr())
+                           B, C, C, M, ctypes.c_float(1e-5), ctypes.c_float(0.1), stream_ptr())
     out = torch.full((M, C), float("nan"), device=dev, dtype=torch.bfloat16)
     rc |= L.hb_bn_act_fwd_bf16(up[0], up[1], up[2], B, ptr(scale), ptr(shift), ptr(res), ptr(out), M, C, act,
-                               ctypes.c_float(0.1), stream_ptr())
+                               ctypes.c_float(0.1), 0, stream_ptr())
     bsums = torch.zeros(1 + B, C, device=dev, dtype=torch.float64)
     dus = [torch.full((M, C), float("nan"), device=dev, dtype=torch.bfloat16) for _ in range(B)]
     dres = torch.full((M, C), float("nan"), device=dev, dtype=torch.bfloat16) if residual else None
@@ -98,7 +98,7 @@ def run_bn(M, C, B, act, residual):
     dup = [ptr(dus[b]) if b < B else ptr(None) for b in range(3)]
     rc |= L.hb_bn_act_bwd_bf16(ptr(dout), up[0], up[1], up[2], B, ptr(scale), ptr(shift), ptr(mean), ptr(rstd), ptr(res),
                                ptr(bsums), dup[0], dup[1], dup[2], ptr(dres), ptr(dg), ptr(db), M, C, act,
-                               ctypes.c_float(0.1), 1, stream_ptr())
+                               ctypes.c_float(0.1), 1, 0, stream_ptr())
     torch.cuda.synchronize()
     # torch reference (fp32 math on the same bf16 inputs)
     uf = [u.float().requires_grad_(True) for u in us]
@@ -183,7 +183,7 @@ def main():
     sums = torch.zeros(3, 2, C, device="cuda", dtype=torch.float64)
     scale = torch.ones(3, C, device="cuda"); shift = torch.zeros(3, C, device="cuda")
     for name, fn in [("stats3", lambda: L.hb_bn_stats_bf16(ptr(u[0]), ptr(u[1]), ptr(u[2]), 3, M, C, ptr(sums), stream_ptr())),
-                     ("fwd3", lambda: L.hb_bn_act_fwd_bf16(ptr(u[0]), ptr(u[1]), ptr(u[2]), 3, ptr(scale), ptr(shift), ptr(None), ptr(out), M, C, 1, ctypes.c_float(0.0), stream_ptr()))]:
+                     ("fwd3", lambda: L.hb_bn_act_fwd_bf16(ptr(u[0]), ptr(u[1]), ptr(u[2]), 3, ptr(scale), ptr(shift), ptr(None), ptr(out), M, C, 1, ctypes.c_float(0.0), 0, stream_ptr()))]:
         for _ in range(2):
             fn()
         torch.cuda.synchronize()
