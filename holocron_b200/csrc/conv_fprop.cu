@@ -14,7 +14,11 @@
 //   warp 1      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=BN, K=16) x4 per stage,
 //               tcgen05.commit releases the smem stage / publishes the accumulator.
 //   warps 2-5   epilogue: tcgen05.ld the accumulator (double-buffered in TMEM, so the epilogue of tile i
-//               overlaps the MMAs of tile i+1), fuse bias / residual / activation, store bf16 NHWC.
+//               overlaps the MMAs of tile i+1), fuse bias / activation, stage the bf16 tile in shared memory
+//               (bank-conflict-free padded rows) and write it out with fully coalesced 128-bit stores
+//               (+ residual add in that pass). The first version stored one 96-byte row per thread straight
+//               from registers: 32 L1TEX wavefronts per store instruction made L1TEX the busiest unit
+//               (profiles/r01_conv_fprop_ncu_full.md).
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "tmap.cuh"
@@ -41,6 +45,7 @@ struct FpropParams {
   int cblocks;      // ceil(Cin / 64)
   int stages;
   int b_stage_bytes;  // BN*128 rounded up to 1024
+  int out_pitch;      // bytes per row of the smem output staging tile (BN*2 + 16)
   int a_mode;         // 0: plain 2-D [M, C] matrix (1x1 s1 p0), 1: im2col
   int act;            // 0 none, 1 relu
   __nv_bfloat16* y;
@@ -54,7 +59,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // carve: [stages][A | B] then barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stage_bytes = kABytes + p.b_stage_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint8_t* sout = smem + (size_t)p.stages * stage_bytes;   // [128][out_pitch] output staging tile
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sout + (size_t)kBM * p.out_pitch);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full = empty_bar + p.stages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;         // [2]
@@ -139,6 +145,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else {
     // ================= epilogue (warps 2..5) =================
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int et = threadIdx.x - 64;   // 0..127 among the epilogue threads
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_tile = tile / p.num_n_tiles, n_tile = tile % p.num_n_tiles;
@@ -146,48 +153,73 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int row = m_tile * kBM + quarter * 32 + lane;
-      const bool row_ok = row < p.m_total;
+      const int row_in_tile = quarter * 32 + lane;
       const int col_base = n_tile * p.BN;
       const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(quarter * 32) << 16);
-      for (int c = 0; c < p.BN; c += 16) {
-        uint32_t v[16];
+      // staging tile free? (all threads finished copying the previous tile out)
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      uint8_t* srow = sout + (size_t)row_in_tile * p.out_pitch;
+      for (int c = 0; c < p.BN; c += 32) {
+        uint32_t v[32];
+        const bool two = (c + 16) < p.BN;
         tmem_ld_x16(taddr + c, v);
+        if (two) tmem_ld_x16(taddr + c + 16, v + 16);
         tmem_ld_wait();
-        const int col = col_base + c;
-        if (row_ok && col < p.Cout) {
-          float f[16];
+        const int nchunk = two ? 2 : 1;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-          if (p.bias) {
+        for (int h = 0; h < 2; ++h) {
+          if (h < nchunk) {
+            float f[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] += __ldg(p.bias + col + j);
+            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[h * 16 + j]);
+            const int col = col_base + c + h * 16;
+            if (p.bias && col < p.Cout) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] += __ldg(p.bias + col + j);
+            }
+            if (p.act == 1 && !p.residual) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.0f);
+            }
+            uint4 o[2];
+            __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(o);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ob[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+            uint4* sp = reinterpret_cast<uint4*>(srow + (c + h * 16) * 2);
+            sp[0] = o[0];
+            sp[1] = o[1];
           }
-          const size_t off = (size_t)row * p.Cout + col;
-          if (p.residual) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
-            uint4 r0 = rp[0], r1 = rp[1];
-            const __nv_bfloat16* rb0 = reinterpret_cast<const __nv_bfloat16*>(&r0);
-            const __nv_bfloat16* rb1 = reinterpret_cast<const __nv_bfloat16*>(&r1);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { f[j] += __bfloat162float(rb0[j]); f[8 + j] += __bfloat162float(rb1[j]); }
-          }
-          if (p.act == 1) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.0f);
-          }
-          uint4 o[2];
-          __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(o);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) ob[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-          uint4* yp = reinterpret_cast<uint4*>(p.y + off);
-          yp[0] = o[0];
-          yp[1] = o[1];
         }
       }
+      // accumulator drained: hand it back to the MMA warp, then publish the staged tile to the other warps
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      // cooperative, fully coalesced copy-out: consecutive threads write consecutive 16-byte chunks of a row
+      const int chunks_per_row = p.BN / 8;
+      const int rows_valid = min(kBM, p.m_total - m_tile * kBM);
+      const int ncols_valid = min(p.BN, p.Cout - col_base);          // multiple of 16
+      const int total_chunks = rows_valid * chunks_per_row;
+      for (int ch = et; ch < total_chunks; ch += 128) {
+        const int r = ch / chunks_per_row, c8 = ch % chunks_per_row;
+        if (c8 * 8 >= ncols_valid) continue;
+        uint4 val = *reinterpret_cast<const uint4*>(sout + (size_t)r * p.out_pitch + c8 * 16);
+        const size_t off = (size_t)(m_tile * kBM + r) * p.Cout + col_base + c8 * 8;
+        if (p.residual) {
+          const uint4 rv = *reinterpret_cast<const uint4*>(p.residual + off);
+          __nv_bfloat162* a = reinterpret_cast<__nv_bfloat162*>(&val);
+          const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float2 fa = __bfloat1622float2(a[j]), fb = __bfloat1622float2(b[j]);
+            fa.x += fb.x; fa.y += fb.y;
+            if (p.act == 1) { fa.x = fmaxf(fa.x, 0.f); fa.y = fmaxf(fa.y, 0.f); }
+            a[j] = __floats2bfloat162_rn(fa.x, fa.y);
+          }
+        }
+        *reinterpret_cast<uint4*>(p.y + off) = val;
+      }
     }
   }
 
@@ -231,8 +263,10 @@ int hb_conv2d_fprop_bf16(const void* x, const void* w, void* y, const float* bia
   p.num_n_tiles = (Cout + BN - 1) / BN;
   p.cblocks = (Cin + kBK - 1) / kBK;
   p.b_stage_bytes = ((BN * 128) + 1023) & ~1023;
+  p.out_pitch = BN * 2 + 16;
+  const int out_bytes = ((kBM * p.out_pitch) + 1023) & ~1023;
   const int stage_bytes = kABytes + p.b_stage_bytes;
-  int stages = (200 * 1024) / stage_bytes;
+  int stages = (204 * 1024 - out_bytes) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) return (int)cudaErrorInvalidValue;
   p.stages = stages;
@@ -262,7 +296,7 @@ int hb_conv2d_fprop_bf16(const void* x, const void* w, void* y, const float* bia
     if (rc) return rc;
   }
 
-  const size_t smem_bytes = (size_t)stages * stage_bytes + (2 * stages + 4) * sizeof(uint64_t) + 16 + 1024;
+  const size_t smem_bytes = (size_t)stages * stage_bytes + out_bytes + (2 * stages + 4) * sizeof(uint64_t) + 16 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

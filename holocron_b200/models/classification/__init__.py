@@ -1,2 +1,3 @@
 from .repvgg import *  # noqa: F401,F403
 from .darknet import *  # noqa: F401,F403
+from .rexnet import *  # noqa: F401,F403

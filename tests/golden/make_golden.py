@@ -279,9 +279,11 @@ def gen_zoo():
         ps = dict(model.named_parameters())
         return {n: ps[n].grad.clone() for n in names}
 
-    for name in ("darknet53", "cspdarknet53"):
+    for name in ("darknet53", "cspdarknet53", "rexnet1_0x"):
         torch.manual_seed(0)
         m = getattr(models, name)(num_classes=10).train()
+        if name == "rexnet1_0x":
+            m.head[0].p = 0.0   # dropout off: device-specific RNG
         torch.manual_seed(1)
         x = torch.rand(2, 3, 64, 64)
         t = torch.tensor([3, 7])
@@ -289,8 +291,9 @@ def gen_zoo():
         loss = torch.nn.functional.cross_entropy(out, t)
         loss.backward()
         first = next(n for n, _ in m.named_parameters())
-        d[name] = dict(x=x, t=t, logits=out.detach(), loss=loss.detach(),
-                       grads=grads_of(m, [first, "classifier.weight"]), first=first)
+        last = "head.1.weight" if name == "rexnet1_0x" else "classifier.weight"
+        d[name] = dict(x=x, t=t, logits=out.detach(), loss=loss.detach(), grads=grads_of(m, [first, last]), first=first,
+                       last=last)
     # UNet3+ with DiceLoss (BASELINE config 5, at 64x64)
     torch.manual_seed(0)
     m = models.segmentation.unet3p(num_classes=21).train()
