@@ -19,6 +19,7 @@
 //               (+ residual add in that pass). The first version stored one 96-byte row per thread straight
 //               from registers: 32 L1TEX wavefronts per store instruction made L1TEX the busiest unit
 //               (profiles/r01_conv_fprop_ncu_full.md).
+#include <stdlib.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "tmap.cuh"
@@ -117,6 +118,9 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ================= MMA issuer =================
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(kBM, p.BN, 0, 0);
+      const uint32_t dhi = desc_hi(1024, kLayoutSW128);
+      const uint32_t a_lo0 = desc_lo(smem_u32(smem), 16);
+      const uint32_t stage_lo = (uint32_t)stage_bytes >> 4;
       int stage = 0; uint32_t phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -128,14 +132,11 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint32_t sb = sa + kABytes;
+          const uint32_t a_lo = a_lo0 + (uint32_t)stage * stage_lo;
+          const uint32_t b_lo = a_lo + (kABytes >> 4);
 #pragma unroll
-          for (int k = 0; k < kBK / kUmmaK; ++k) {
-            const uint64_t adesc = make_smem_desc(sa + k * kUmmaK * 2, 16, 1024, kLayoutSW128);
-            const uint64_t bdesc = make_smem_desc(sb + k * kUmmaK * 2, 16, 1024, kLayoutSW128);
-            umma_f16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
-          }
+          for (int k = 0; k < kBK / kUmmaK; ++k)
+            umma_f16_lh(d_tmem, a_lo + 2 * k, dhi, b_lo + 2 * k, dhi, idesc, (uint32_t)(kb | k));
           umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs have read it
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
@@ -230,6 +231,10 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
 }  // namespace
 
+// conv_rows.cu: shared-memory-reuse kernel for stride-1 3x3 layers whose filter fits in shared memory
+int hb_conv_rows_try(const void* x, const void* w, void* y, const float* bias, const void* residual, int N, int H, int W,
+                     int Cin, int Cout, int act, int num_ctas, cudaStream_t stream);
+
 extern "C" {
 
 // Forward convolution, NHWC bf16.  x: [N,H,W,Cin]  w: [Cout,R,S,Cin]  y: [N,Ho,Wo,Cout]
@@ -245,6 +250,15 @@ int hb_conv2d_fprop_bf16(const void* x, const void* w, void* y, const float* bia
   if (Ho <= 0 || Wo <= 0) return (int)cudaErrorInvalidValue;
   const long long m_total_ll = (long long)N * Ho * Wo;
   if (m_total_ll <= 0 || m_total_ll > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
+
+  if (R == 3 && S == 3 && stride == 1 && pad == 1 && dil == 1) {
+    static const bool rows_enabled = getenv("HB_DISABLE_CONV_ROWS") == nullptr;
+    if (rows_enabled) {
+      const int rc = hb_conv_rows_try(x, w, y, bias, residual, N, H, W, Cin, Cout, act, num_ctas, (cudaStream_t)stream);
+      if (rc == 0) return 0;
+      if (rc == -2) return (int)cudaErrorLaunchFailure;
+    }
+  }
 
   FpropParams p{};
   p.m_total = (int)m_total_ll;

@@ -1,0 +1,300 @@
+// "Row-window" 3x3 convolution (stride 1, pad 1) for the HBM/L2-bound layers (Cin <= 128, all filter taps resident
+// in shared memory): the input rows needed by a band of output rows are brought in ONCE per tile by a single tiled TMA
+// load (with a one-pixel zero halo supplied by TMA's out-of-bounds fill) and all nine filter taps are issued as
+// *shifted windows of that one buffer* - a tcgen05 shared-memory descriptor may start at any 128-byte row of a
+// 128B-swizzled TMA buffer because the swizzle is a function of the absolute shared-memory address
+// (probe: profiles/r01_umma_shifted_descriptor_probe.log).
+//
+// Why: the first implicit-GEMM kernel (conv_fprop.cu) issues one im2col TMA load per tap, i.e. it reads every input
+// element 9x from L2; ncu showed the 48-channel 112^2 layer moving 8 TB/s out of L2 while DRAM sat at 11%
+// (profiles/r01_conv_fprop_ncu_full.md). Here a tile of TRO output rows loads TRO+2 input rows: 1.3-2x instead of 9x.
+//
+// Geometry. Shared-memory row pitch Wp = W + 2 pixels (128 B each = one 64-channel block). A "sub-tile" is one
+// M = 128 MMA covering SR = floor(128 / Wp) output rows laid out with the SAME pitch Wp (so 2 junk columns per row);
+// for tap (r, s) its A operand is the buffer window starting at pixel row (sub*SR + r) * Wp + s. Junk accumulator rows
+// (q >= W, rows past the image) are skipped by the epilogue. The filter (all 9 taps x channel blocks) is loaded once
+// per CTA and stays resident.
+//
+// Same warp roles / double-buffered TMEM accumulators / smem-staged coalesced epilogue as conv_fprop.cu.
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "tmap.cuh"
+
+namespace {
+
+using namespace tc;
+
+constexpr int kThreads = 192;
+constexpr int kTmemCols = 512;
+
+struct RowsParams {
+  int N, H, W, Cin, Cout;
+  int Wp;        // smem row pitch in pixels (W + 2)
+  int SR;        // output rows per sub-tile (one M=128 MMA)
+  int NSUB;      // sub-tiles per tile
+  int TRO;       // output rows per tile = SR * NSUB
+  int CB;        // 64-channel blocks
+  int ksteps_last;  // UMMA k-steps (of 16 channels) in the last channel block
+  int BN;        // = Cout (multiple of 16, <= 256 / NSUB)
+  int tiles_per_img, num_tiles;
+  int stage_bytes;   // CB * (TRO+2) * Wp * 128, rounded to 1024
+  int cb_bytes;      // (TRO+2) * Wp * 128 rounded to 1024
+  int w_tap_bytes;   // BN * 128 rounded to 1024
+  int out_pitch;
+  int act;
+  __nv_bfloat16* y;
+  const float* bias;
+  const __nv_bfloat16* residual;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_rows_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const RowsParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* wsm = smem;                                          // [9][CB][BN x 128 B]
+  uint8_t* stage0 = wsm + (size_t)9 * p.CB * p.w_tap_bytes;     // 2 stages
+  uint8_t* sout = stage0 + (size_t)2 * p.stage_bytes;           // [128][out_pitch]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sout + (((size_t)128 * p.out_pitch + 15) & ~size_t(15)));
+  uint64_t* full_bar = bars;        // [2]
+  uint64_t* empty_bar = bars + 2;   // [2]
+  uint64_t* tmem_full = bars + 4;   // [2]
+  uint64_t* tmem_empty = bars + 6;  // [2]
+  uint64_t* w_bar = bars + 8;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmX);
+    prefetch_tmap(&tmW);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1);
+      mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4);
+    }
+    mbar_init(w_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      // resident filter: 9 taps x CB channel blocks
+      mbar_arrive_expect_tx(w_bar, (uint32_t)(9 * p.CB * p.BN * 128));
+      for (int tap = 0; tap < 9; ++tap)
+        for (int cb = 0; cb < p.CB; ++cb)
+          tma_load_3d(&tmW, w_bar, wsm + (size_t)(tap * p.CB + cb) * p.w_tap_bytes, cb * 64, tap, 0);
+      const uint32_t tx = (uint32_t)(p.CB * (p.TRO + 2) * p.Wp * 128);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int st = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        const int n = tile / p.tiles_per_img, p0 = (tile % p.tiles_per_img) * p.TRO;
+        mbar_wait(&empty_bar[st], ph ^ 1);
+        mbar_arrive_expect_tx(&full_bar[st], tx);
+        for (int cb = 0; cb < p.CB; ++cb) {
+          // box (64 ch, Wp, TRO+2 rows, 1 image) at (c, w = -1, h = p0 - 1, n): halo and image borders = OOB zero fill
+          asm volatile(
+              "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+              ::"r"(smem_u32(stage0 + (size_t)st * p.stage_bytes + (size_t)cb * p.cb_bytes)),
+                "l"(reinterpret_cast<uint64_t>(&tmX)), "r"(smem_u32(&full_bar[st])), "r"(cb * 64), "r"(-1), "r"(p0 - 1), "r"(n)
+              : "memory");
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, p.BN, 0, 0);
+      const uint32_t dhi = desc_hi(1024, kLayoutSW128);
+      const uint32_t w_lo0 = desc_lo(smem_u32(wsm), 16);
+      const uint32_t w_tap_lo = (uint32_t)p.w_tap_bytes >> 4;
+      const uint32_t cb_lo = (uint32_t)p.cb_bytes >> 4;
+      mbar_wait(w_bar, 0);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int st = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[st], ph ^ 1);   // accumulator set `st` drained by the epilogue
+        mbar_wait(&full_bar[st], ph);         // input rows landed
+        tc_fence_after();
+        const uint32_t s_lo = desc_lo(smem_u32(stage0 + (size_t)st * p.stage_bytes), 16);
+        for (int sub = 0; sub < p.NSUB; ++sub) {
+          const uint32_t d_tmem = tmem_base + st * 256 + sub * p.BN;
+          uint32_t accum = 0;
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const int r = tap / 3, s = tap % 3;
+            // 128-byte pixel rows: (row index) * 128 B >> 4 = row index * 8
+            uint32_t a_lo = s_lo + (uint32_t)(((sub * p.SR + r) * p.Wp + s) * 8);
+            uint32_t b_lo = w_lo0 + (uint32_t)(tap * p.CB) * w_tap_lo;
+            for (int cb = 0; cb < p.CB; ++cb) {
+              const int ks = (cb == p.CB - 1) ? p.ksteps_last : 4;
+              for (int k = 0; k < ks; ++k) {
+                umma_f16_lh(d_tmem, a_lo + 2 * k, dhi, b_lo + 2 * k, dhi, idesc, accum);
+                accum = 1;
+              }
+              a_lo += cb_lo;
+              b_lo += w_tap_lo;
+            }
+          }
+        }
+        umma_commit(&empty_bar[st]);   // input stage may be refilled
+        umma_commit(&tmem_full[st]);   // accumulators of this tile complete
+      }
+    }
+  } else {
+    // ================= epilogue (warps 2..5) =================
+    const int quarter = warp & 3;
+    const int et = threadIdx.x - 64;
+    const int chunks_per_row = p.BN / 8;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int st = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      const int n = tile / p.tiles_per_img, p0 = (tile % p.tiles_per_img) * p.TRO;
+      mbar_wait(&tmem_full[st], ph);
+      tc_fence_after();
+      for (int sub = 0; sub < p.NSUB; ++sub) {
+        const uint32_t taddr = tmem_base + st * 256 + sub * p.BN + ((uint32_t)(quarter * 32) << 16);
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // staging tile free
+        uint8_t* srow = sout + (size_t)(quarter * 32 + lane) * p.out_pitch;
+        for (int c = 0; c < p.BN; c += 32) {
+          uint32_t v[32];
+          const bool two = (c + 16) < p.BN;
+          tmem_ld_x16(taddr + c, v);
+          if (two) tmem_ld_x16(taddr + c + 16, v + 16);
+          tmem_ld_wait();
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (h == 0 || two) {
+              float f[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[h * 16 + j]);
+              const int col = c + h * 16;
+              if (p.bias) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] += __ldg(p.bias + col + j);
+              }
+              if (p.act == 1 && !p.residual) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.0f);
+              }
+              uint4 o[2];
+              __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(o);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) ob[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+              uint4* sp = reinterpret_cast<uint4*>(srow + col * 2);
+              sp[0] = o[0];
+              sp[1] = o[1];
+            }
+          }
+        }
+        if (sub == p.NSUB - 1) {   // last TMEM read of this accumulator set
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[st]);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // staged tile visible
+        // copy-out: iterate over the VALID output pixels of this sub-tile (row-major), 16-byte chunks
+        const int row0 = p0 + sub * p.SR;
+        const int rows_valid = max(0, min(p.SR, min(p.H, p0 + p.TRO) - row0));
+        const int total = rows_valid * p.W * chunks_per_row;
+        for (int ch = et; ch < total; ch += 128) {
+          const int c8 = ch % chunks_per_row;
+          const int pix = ch / chunks_per_row;
+          const int i = pix / p.W, q = pix % p.W;
+          uint4 val = *reinterpret_cast<const uint4*>(sout + (size_t)(i * p.Wp + q) * p.out_pitch + c8 * 16);
+          const size_t off = ((size_t)(n * p.H + row0 + i) * p.W + q) * p.Cout + c8 * 8;
+          if (p.residual) {
+            const uint4 rv = *reinterpret_cast<const uint4*>(p.residual + off);
+            __nv_bfloat162* a = reinterpret_cast<__nv_bfloat162*>(&val);
+            const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float2 fa = __bfloat1622float2(a[j]), fb = __bfloat1622float2(b[j]);
+              fa.x += fb.x; fa.y += fb.y;
+              if (p.act == 1) { fa.x = fmaxf(fa.x, 0.f); fa.y = fmaxf(fa.y, 0.f); }
+              a[j] = __floats2bfloat162_rn(fa.x, fa.y);
+            }
+          }
+          *reinterpret_cast<uint4*>(p.y + off) = val;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
+}
+
+}  // namespace
+
+// Returns 0 and launches when the shape is eligible; returns -1 (nothing launched) when the caller should use the
+// generic implicit-GEMM kernel instead. Not part of the public C ABI (called from hb_conv2d_fprop_bf16).
+int hb_conv_rows_try(const void* x, const void* w, void* y, const float* bias, const void* residual, int N, int H, int W,
+                     int Cin, int Cout, int act, int num_ctas, cudaStream_t stream) {
+  if (Cout % 16 != 0 || Cout > 128 || Cin % 8 != 0 || Cin > 128) return -1;
+  const int Wp = W + 2;
+  if (Wp > 128 || W < 8) return -1;
+  RowsParams p{};
+  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.Wp = Wp; p.BN = Cout;
+  p.SR = 128 / Wp;
+  p.CB = (Cin + 63) / 64;
+  const int last = Cin - (p.CB - 1) * 64;
+  p.ksteps_last = (last + 15) / 16;
+  p.w_tap_bytes = ((Cout * 128) + 1023) & ~1023;
+  p.out_pitch = Cout * 2 + 16;
+  const int w_bytes = 9 * p.CB * p.w_tap_bytes;
+  const int out_bytes = ((128 * p.out_pitch) + 1023) & ~1023;
+  const int budget = 222 * 1024 - w_bytes - out_bytes - 256;
+  // largest NSUB whose two stages fit in shared memory and whose accumulators fit half of TMEM
+  int nsub = 256 / Cout;
+  if (nsub > 8) nsub = 8;
+  const int max_rows_needed = (H + p.SR - 1) / p.SR;
+  if (nsub > max_rows_needed) nsub = max_rows_needed;
+  for (; nsub >= 1; --nsub) {
+    const int cb_bytes = (((nsub * p.SR + 2) * Wp * 128) + 1023) & ~1023;
+    // the last sub-tile's windows read up to 127 + 2*Wp + 2 pixel rows past its first row: keep them inside the stage
+    const int reach = (((nsub - 1) * p.SR + 2) * Wp + 2 + 128) * 128;
+    const int need = cb_bytes > reach ? cb_bytes : ((reach + 1023) & ~1023);
+    if (2 * p.CB * need <= budget) { p.cb_bytes = need; break; }
+  }
+  if (nsub < 1) return -1;
+  p.NSUB = nsub;
+  p.TRO = nsub * p.SR;
+  p.stage_bytes = p.CB * p.cb_bytes;
+  p.tiles_per_img = (H + p.TRO - 1) / p.TRO;
+  p.num_tiles = N * p.tiles_per_img;
+  p.act = act;
+  p.y = (__nv_bfloat16*)y; p.bias = bias; p.residual = (const __nv_bfloat16*)residual;
+
+  CUtensorMap tmX, tmW;
+  {
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+    uint32_t box[4] = {64, (uint32_t)Wp, (uint32_t)(p.TRO + 2), 1};
+    if (tmap::encode_tiled_bf16(&tmX, x, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
+    uint64_t wdims[3] = {(uint64_t)Cin, 9, (uint64_t)Cout};
+    uint64_t wstrides[2] = {(uint64_t)Cin * 2, (uint64_t)9 * Cin * 2};
+    uint32_t wbox[3] = {64, 1, (uint32_t)Cout};
+    if (tmap::encode_tiled_bf16(&tmW, w, 3, wdims, wstrides, wbox, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
+  }
+  const size_t smem_bytes = (size_t)w_bytes + 2 * (size_t)p.stage_bytes + out_bytes + 256 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(conv_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return -1;
+    attr_set = true;
+  }
+  if (smem_bytes > 227 * 1024) return -1;
+  int grid = num_ctas > 0 ? num_ctas : HB_NUM_SMS;
+  if (grid > p.num_tiles) grid = p.num_tiles;
+  conv_rows_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmX, tmW, p);
+  g_hb_launches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}

@@ -115,6 +115,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     if (lane == 0) {
       const int n_mma = (p.ci_tile + 15) & ~15;
       const uint32_t idesc = make_idesc_bf16(128, n_mma, 1, 1);
+      const uint32_t dhi = desc_hi(1024, kLayoutSW128);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
@@ -128,16 +129,16 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
+          // 16 pixels = two 8-row swizzle atoms (SBO 1024 B); 64-channel chunks are LBO = 8 KiB apart
+          const uint32_t a_lo = desc_lo(smem_u32(smem + (size_t)stage * p.stage_bytes), kChunkBytes);
+          uint32_t b_lo = a_lo + (kABytes >> 4);
+          const uint32_t acc0 = kb > kb0 ? 1u : 0u;
           for (int t = 0; t < ntaps; ++t) {
-            const uint32_t sb = sa + kABytes + t * b_tap_bytes;
 #pragma unroll
-            for (int k = 0; k < kBKpix / 16; ++k) {
-              // 16 pixels = two 8-row swizzle atoms (SBO 1024 B); 64-channel chunks are LBO = 8 KiB apart
-              const uint64_t adesc = make_smem_desc(sa + k * 2048, kChunkBytes, 1024, kLayoutSW128);
-              const uint64_t bdesc = make_smem_desc(sb + k * 2048, kChunkBytes, 1024, kLayoutSW128);
-              umma_f16(tmem_base + t * p.ci_cols, adesc, bdesc, idesc, (kb > kb0) || (k > 0));
-            }
+            for (int k = 0; k < kBKpix / 16; ++k)
+              umma_f16_lh(tmem_base + t * p.ci_cols, a_lo + k * (2048 >> 4), dhi, b_lo + k * (2048 >> 4), dhi, idesc,
+                          acc0 | (uint32_t)k);
+            b_lo += (uint32_t)b_tap_bytes >> 4;
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }

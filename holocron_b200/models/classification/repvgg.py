@@ -67,14 +67,17 @@ class RepBlock(nn.Module):
         conv1, bn1 = cast(nn.Sequential, self.branches[1])
         if not (isinstance(bn3, nn.BatchNorm2d) and isinstance(bn1, nn.BatchNorm2d)):
             raise NotImplementedError("the fused RepBlock needs nn.BatchNorm2d as norm_layer")
-        # one bf16 NHWC copy of the input (channels padded to a multiple of 8) shared by both convolutions
+        bns = [bn3, bn1] + ([cast(nn.BatchNorm2d, self.branches[2])] if len(self.branches) == 3 else [])
+        if conv3.out_channels % 16 == 0 and all(b.eps == bn3.eps and b.momentum == bn3.momentum for b in bns) \
+                and bn3.momentum is not None:
+            # whole block as one autograd node (input-gradient contributions chained through the conv epilogues)
+            out = K.repblock(x, conv3.weight, conv1.weight, bns, conv3.stride[0], code, slope, self.training)
+            return out if post is None else post(out)
+        # generic composition: one bf16 NHWC copy of the input shared by both convolutions
         xb = K.to_channels_last_bf16(x, K.round_up(x.shape[1], 8))
         y3 = K.conv2d(xb, conv3.weight, None, conv3.stride[0], 1)
         y1 = K.conv2d(xb, conv1.weight, None, conv1.stride[0], 0)
-        us, bns = [y3, y1], [bn3, bn1]
-        if len(self.branches) == 3:
-            us.append(xb)
-            bns.append(cast(nn.BatchNorm2d, self.branches[2]))
+        us = [y3, y1] + ([xb] if len(bns) == 3 else [])
         out = K.bn_act(us, bns, code, slope, training=self.training)
         return out if post is None else post(out)
 

@@ -370,6 +370,136 @@ def act_only(x: Tensor, act: int, slope: float = 0.0) -> Tensor:
 
 
 # ------------------------------------------------------------------------------------------------------
+class _RepBlockFn(torch.autograd.Function):
+    """Train-form RepVGG block as ONE autograd node:  out = act(BN3(conv3x3(x)) + BN1(conv1x1(x)) [+ BNid(x)]).
+
+    Forward = the same kernels as the unfused path (two tensor-core convolutions, one statistics pass, one fused
+    normalise/sum/activate pass). The point is the backward: instead of letting autograd sum the three input-gradient
+    contributions with two extra element-wise kernels, they are chained through the convolutions' residual inputs
+        dX = dgrad3x3(dY3) + [ dgrad1x1(dY1) + dXid ]
+    (for stride-2 blocks the 1x1 data gradient is computed at the low resolution and zero-inserted once).
+    """
+
+    @staticmethod
+    def forward(ctx, cfg, x: Tensor, w3: Tensor, w1: Tensor, *bn_params: Tensor) -> Tensor:
+        branches, act, slope, training, stride = cfg
+        nb = len(branches)
+        gammas, betas = bn_params[:nb], bn_params[nb:]
+        need_dx = ctx.needs_input_grad[1]
+        cout, cin = w3.shape[0], w3.shape[1]
+        pk3 = pack_filter(w3, need_dx, round_up(x.shape[1], 8))
+        pk1 = pack_filter(w1, need_dx, round_up(x.shape[1], 8))
+        if pk3.cout_p != cout:
+            raise NotImplementedError("fused RepBlock needs out_channels % 16 == 0")
+        xb = to_channels_last_bf16(x, pk3.cin_p)
+        y3 = conv2d_forward_raw(xb, pk3.wf, cout, 3, 3, stride, 1, 1)
+        y1 = conv2d_forward_raw(xb, pk1.wf, cout, 1, 1, stride, 0, 1)
+        us = [y3, y1] + ([xb] if nb == 3 else [])
+        n, c, h, w = y3.shape
+        m = n * h * w
+        dev = y3.device
+        L = lib()
+        stats = torch.empty((4, nb, c), device=dev, dtype=torch.float32)
+        mean, rstd, scale, shift = stats[0], stats[1], stats[2], stats[3]
+        g32 = [g.detach().float() for g in gammas]
+        b32 = [b.detach().float() for b in betas]
+        up = [ptr(us[i]) if i < nb else ptr(None) for i in range(3)]
+        if training:
+            sums = torch.zeros((nb, 2, c), device=dev, dtype=torch.float64)
+            check(L.hb_bn_stats_bf16(up[0], up[1], up[2], nb, m, c, ptr(sums), stream_ptr()), "hb_bn_stats_bf16")
+            track = branches[0].running_mean is not None
+            check(L.hb_bn_finalize(ptr(sums), _arr3(g32), _arr3(b32),
+                                   _arr3([b.running_mean for b in branches]) if track else None,
+                                   _arr3([b.running_var for b in branches]) if track else None,
+                                   _arr3([b.num_batches_tracked for b in branches]) if track else None,
+                                   ptr(mean), ptr(rstd), ptr(scale), ptr(shift), nb, c, c, m, _c_float(branches[0].eps),
+                                   _c_float(branches[0].momentum), stream_ptr()), "hb_bn_finalize")
+        else:
+            for i, b in enumerate(branches):
+                check(L.hb_bn_eval_affine(ptr(g32[i]), ptr(b32[i]), ptr(b.running_mean), ptr(b.running_var),
+                                          _c_float(b.eps), c, c, ptr(scale[i]), ptr(shift[i]), ptr(mean[i]), ptr(rstd[i]),
+                                          stream_ptr()), "hb_bn_eval_affine")
+        out = _empty_cl(n, c, h, w, dev)
+        check(L.hb_bn_act_fwd_bf16(up[0], up[1], up[2], nb, ptr(scale), ptr(shift), ptr(None), ptr(out), m, c, act,
+                                   _c_float(slope), 0, stream_ptr()), "hb_bn_act_fwd_bf16")
+        ctx.save_for_backward(stats, xb, y3, y1, w3, w1)
+        ctx.cfg = (nb, act, slope, training, stride, pk3.wd, pk1.wd, x.shape[1])
+        return out
+
+    @staticmethod
+    def backward(ctx, dout: Tensor):
+        nb, act, slope, training, stride, wd3, wd1, cin_x = ctx.cfg
+        stats, xb, y3, y1, w3, w1 = ctx.saved_tensors
+        mean, rstd, scale, shift = stats[0], stats[1], stats[2], stats[3]
+        n, c, ho, wo = y3.shape
+        _, cin_p, h, w = xb.shape
+        m = n * ho * wo
+        dev = dout.device
+        L = lib()
+        dob = to_channels_last_bf16(dout)
+        need_dx = ctx.needs_input_grad[1]
+        dy3, dy1 = _empty_cl(n, c, ho, wo, dev), _empty_cl(n, c, ho, wo, dev)
+        dxid = _empty_cl(n, c, ho, wo, dev) if (nb == 3 and need_dx) else None
+        sums = torch.zeros((1 + nb, c), device=dev, dtype=torch.float64)
+        dgb = torch.empty((2, nb, c), device=dev, dtype=torch.float32)
+        check(L.hb_bn_act_bwd_bf16(ptr(dob), ptr(y3), ptr(y1), ptr(xb) if nb == 3 else ptr(None), nb, ptr(scale), ptr(shift),
+                                   ptr(mean), ptr(rstd), ptr(None), ptr(sums), ptr(dy3), ptr(dy1), ptr(dxid), ptr(None),
+                                   ptr(dgb[0]), ptr(dgb[1]), m, c, act, _c_float(slope), 1 if training else 0, 0,
+                                   stream_ptr()), "hb_bn_act_bwd_bf16")
+        dx = None
+        if need_dx:
+            cin_d = wd3.shape[0]
+            if stride == 1:
+                # dXa = dgrad1x1(dY1) + dXid ; dX = dgrad3x3(dY3) + dXa   (cin_d == c for identity blocks)
+                dxa = _empty_cl(n, cin_d, h, w, dev)
+                res = dxid if (dxid is not None and cin_d == c) else None
+                _timed("dgrad", dict(N=n, H=h, W=w, Cin=c, Cout=cin_d, R=1, S=1, stride=1, Ho=h, Wo=w), lambda: check(
+                    L.hb_conv2d_fprop_bf16(ptr(dy1), ptr(wd1), ptr(dxa), ptr(None), ptr(res), n, h, w, c, cin_d, 1, 1, 1, 0, 1,
+                                           ACT_NONE, 0, stream_ptr()), "hb_conv2d_fprop_bf16[dgrad1x1]"))
+                if dxid is not None and res is None:
+                    dxa[:, :c] += dxid
+                src3 = dy3
+            else:
+                lo = _empty_cl(n, cin_d, ho, wo, dev)
+                _timed("dgrad", dict(N=n, H=ho, W=wo, Cin=c, Cout=cin_d, R=1, S=1, stride=1, Ho=ho, Wo=wo), lambda: check(
+                    L.hb_conv2d_fprop_bf16(ptr(dy1), ptr(wd1), ptr(lo), ptr(None), ptr(None), n, ho, wo, c, cin_d, 1, 1, 1, 0,
+                                           1, ACT_NONE, 0, stream_ptr()), "hb_conv2d_fprop_bf16[dgrad1x1]"))
+                dxa = _empty_cl(n, cin_d, h, w, dev)
+                check(L.hb_zero_insert_bf16(ptr(lo), ptr(dxa), n, ho, wo, h, w, cin_d, stride, stream_ptr()),
+                      "hb_zero_insert_bf16")
+                src3 = _empty_cl(n, c, h, w, dev)
+                check(L.hb_zero_insert_bf16(ptr(dy3), ptr(src3), n, ho, wo, h, w, c, stride, stream_ptr()),
+                      "hb_zero_insert_bf16")
+            dxp = _empty_cl(n, cin_d, h, w, dev)
+            _timed("dgrad", dict(N=n, H=h, W=w, Cin=c, Cout=cin_d, R=3, S=3, stride=1, Ho=h, Wo=w, dgrad_of_stride=stride),
+                   lambda: check(L.hb_conv2d_fprop_bf16(ptr(src3), ptr(wd3), ptr(dxp), ptr(None), ptr(dxa), n, h, w, c, cin_d,
+                                                        3, 3, 1, 1, 1, ACT_NONE, 0, stream_ptr()),
+                                 "hb_conv2d_fprop_bf16[dgrad3x3]"))
+            dx = dxp if cin_d == cin_x else dxp[:, :cin_x]
+        grads_w = []
+        for wt, dy, k, pad in ((w3, dy3, 3, 1), (w1, dy1, 1, 0)):
+            cin = wt.shape[1]
+            dwp = torch.empty((c, k, k, cin_p), device=dev, dtype=torch.float32)
+            _timed("wgrad", dict(N=n, H=h, W=w, Cin=cin_p, Cout=c, R=k, S=k, stride=stride, Ho=ho, Wo=wo), lambda: check(
+                L.hb_conv2d_wgrad_bf16(ptr(xb), ptr(dy), ptr(dwp), n, h, w, cin_p, c, k, k, stride, pad, 1, 0, stream_ptr()),
+                "hb_conv2d_wgrad_bf16"))
+            dw = dwp.permute(0, 3, 1, 2)
+            if cin_p != cin:
+                dw = dw[:, :cin].contiguous(memory_format=torch.channels_last)
+            grads_w.append(dw)
+        return (None, dx, grads_w[0], grads_w[1], *[dgb[0][i] for i in range(nb)], *[dgb[1][i] for i in range(nb)])
+
+
+def repblock(x: Tensor, w3: Tensor, w1: Tensor, bns: Sequence[nn.BatchNorm2d], stride: int, act: int, slope: float,
+             training: bool) -> Tensor:
+    """Fused train-form RepVGG block (see :class:`_RepBlockFn`). ``bns`` = [bn3, bn1] or [bn3, bn1, bn_identity]."""
+    require_cuda(x, w3, w1)
+    use_batch_stats = training or bns[0].running_mean is None
+    cfg = ([BNBranch(b) for b in bns], int(act), float(slope), bool(use_batch_stats), int(stride))
+    return _RepBlockFn.apply(cfg, x, w3, w1, *[b.weight for b in bns], *[b.bias for b in bns])
+
+
+# ------------------------------------------------------------------------------------------------------
 class _GapFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x: Tensor) -> Tensor:
