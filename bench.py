@@ -323,6 +323,14 @@ def main():
             kname = "conv_wgrad_kernel" if kind == "wgrad" else "conv_fprop_kernel"
             d = agg.setdefault(kname, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
             d["ms"] += a.elapsed_time(b); d["flops"] += fl; d["bytes"] += by; d["launches"] += 1
+        if os.environ.get("HB_BENCH_DETAIL"):
+            by_shape = {}
+            for kind, info, a, b in recs:
+                key = (kind, info["H"], info["Cin"], info["Cout"], info["R"], info["stride"], info.get("dgrad_of_stride", 0))
+                e = by_shape.setdefault(key, [0, 0.0])
+                e[0] += 1; e[1] += a.elapsed_time(b)
+            for key, (cnt, t) in sorted(by_shape.items(), key=lambda kv: -kv[1][1]):
+                print(f"DETAIL {key}: n={cnt} total {t:.3f} ms", file=sys.stderr)
         peaks = measured_peaks()
         dom = max(agg, key=lambda k: agg[k]["ms"])
         d = agg[dom]

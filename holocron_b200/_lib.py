@@ -33,10 +33,13 @@ SIGNATURES = {
     "hb_nl_relu_bwd": "pppzfip",
     "hb_nl_relu_bwd_from_out": "pppzfip",
     "hb_conv2d_fprop_bf16": "ppppp" + "i" * 12 + "p",
-    "hb_conv2d_wgrad_bf16": "ppp" + "i" * 11 + "p",
+    "hb_conv3x3_accum_bf16": "pppppp" + "i" + "p" + "i" * 6 + "p",
+    "hb_conv2d_wgrad_bf16": "ppppz" + "i" * 11 + "p",
+    "hb_conv2d_wgrad_workspace_bytes": "i" * 11,
     "hb_pack_conv_weights": "ppp" + "i" * 8 + "p",
     "hb_zero_insert_bf16": "pp" + "i" * 7 + "p",
     "hb_nchw_to_nhwc_pad_bf16": "pp" + "i" * 6 + "p",
+    "hb_im2col_smallc_bf16": "pp" + "i" * 10 + "p",
     "hb_bn_stats_bf16": "pppiiipp",
     "hb_bn_finalize": "pppppp" + "pppp" + "iiiiffp",
     "hb_bn_eval_affine": "ppppfiippppp",
@@ -84,7 +87,7 @@ def lib() -> ctypes.CDLL:
         for name, sig in SIGNATURES.items():
             fn = getattr(handle, name)  # AttributeError here = the library is stale: rebuild it
             fn.argtypes = [_CTYPE[c] for c in sig]
-            fn.restype = ctypes.c_int
+            fn.restype = ctypes.c_size_t if name.endswith("_bytes") else ctypes.c_int
         handle.hb_launch_count.argtypes = []
         handle.hb_launch_count.restype = ctypes.c_longlong
         handle.hb_launch_count_reset.argtypes = []

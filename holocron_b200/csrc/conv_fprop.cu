@@ -157,69 +157,76 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int row_in_tile = quarter * 32 + lane;
       const int col_base = n_tile * p.BN;
       const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(quarter * 32) << 16);
-      // staging tile free? (all threads finished copying the previous tile out)
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      uint8_t* srow = sout + (size_t)row_in_tile * p.out_pitch;
-      for (int c = 0; c < p.BN; c += 32) {
-        uint32_t v[32];
-        const bool two = (c + 16) < p.BN;
-        tmem_ld_x16(taddr + c, v);
-        if (two) tmem_ld_x16(taddr + c + 16, v + 16);
-        tmem_ld_wait();
-        const int nchunk = two ? 2 : 1;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          if (h < nchunk) {
-            float f[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[h * 16 + j]);
-            const int col = col_base + c + h * 16;
-            if (p.bias && col < p.Cout) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) f[j] += __ldg(p.bias + col + j);
-            }
-            if (p.act == 1 && !p.residual) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.0f);
-            }
-            uint4 o[2];
-            __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(o);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) ob[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-            uint4* sp = reinterpret_cast<uint4*>(srow + (c + h * 16) * 2);
-            sp[0] = o[0];
-            sp[1] = o[1];
-          }
-        }
-      }
-      // accumulator drained: hand it back to the MMA warp, then publish the staged tile to the other warps
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      // cooperative, fully coalesced copy-out: consecutive threads write consecutive 16-byte chunks of a row
-      const int chunks_per_row = p.BN / 8;
       const int rows_valid = min(kBM, p.m_total - m_tile * kBM);
       const int ncols_valid = min(p.BN, p.Cout - col_base);          // multiple of 16
-      const int total_chunks = rows_valid * chunks_per_row;
-      for (int ch = et; ch < total_chunks; ch += 128) {
-        const int r = ch / chunks_per_row, c8 = ch % chunks_per_row;
-        if (c8 * 8 >= ncols_valid) continue;
-        uint4 val = *reinterpret_cast<const uint4*>(sout + (size_t)r * p.out_pitch + c8 * 16);
-        const size_t off = (size_t)(m_tile * kBM + r) * p.Cout + col_base + c8 * 8;
-        if (p.residual) {
-          const uint4 rv = *reinterpret_cast<const uint4*>(p.residual + off);
-          __nv_bfloat162* a = reinterpret_cast<__nv_bfloat162*>(&val);
-          const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&rv);
+      uint8_t* srow = sout + (size_t)row_in_tile * p.out_pitch;
+      // column groups of <= 64 accumulator columns go through a small fixed-size staging tile (keeps the smem for
+      // pipeline stages whatever BN is); each group is written out as 128-byte row segments
+      for (int g0 = 0; g0 < p.BN; g0 += 64) {
+        const int gw = min(64, p.BN - g0);
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // staging tile free
+        for (int c = 0; c < gw; c += 32) {
+          uint32_t v[32];
+          const bool two = (c + 16) < gw;
+          tmem_ld_x16(taddr + g0 + c, v);
+          if (two) tmem_ld_x16(taddr + g0 + c + 16, v + 16);
+          tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float2 fa = __bfloat1622float2(a[j]), fb = __bfloat1622float2(b[j]);
-            fa.x += fb.x; fa.y += fb.y;
-            if (p.act == 1) { fa.x = fmaxf(fa.x, 0.f); fa.y = fmaxf(fa.y, 0.f); }
-            a[j] = __floats2bfloat162_rn(fa.x, fa.y);
+          for (int h = 0; h < 2; ++h) {
+            if (h == 0 || two) {
+              float f[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[h * 16 + j]);
+              const int col = col_base + g0 + c + h * 16;
+              if (p.bias && col < p.Cout) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] += __ldg(p.bias + col + j);
+              }
+              if (p.act == 1 && !p.residual) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.0f);
+              }
+              uint4 o[2];
+              __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(o);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) ob[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+              uint4* sp = reinterpret_cast<uint4*>(srow + (c + h * 16) * 2);
+              sp[0] = o[0];
+              sp[1] = o[1];
+            }
           }
         }
-        *reinterpret_cast<uint4*>(p.y + off) = val;
+        if (g0 + 64 >= p.BN) {   // last TMEM read of this accumulator: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // staged group visible to all epilogue warps
+        const int chunks_per_row = gw / 8;
+        const int total_chunks = rows_valid * chunks_per_row;
+        int r = et / chunks_per_row, c8 = et - r * chunks_per_row;
+        const int dr = 128 / chunks_per_row, dc = 128 - dr * chunks_per_row;
+        for (int ch = et; ch < total_chunks; ch += 128) {
+          if (g0 + c8 * 8 < ncols_valid) {
+            uint4 val = *reinterpret_cast<const uint4*>(sout + (size_t)r * p.out_pitch + c8 * 16);
+            const size_t off = (size_t)(m_tile * kBM + r) * p.Cout + col_base + g0 + c8 * 8;
+            if (p.residual) {
+              const uint4 rv = *reinterpret_cast<const uint4*>(p.residual + off);
+              __nv_bfloat162* a = reinterpret_cast<__nv_bfloat162*>(&val);
+              const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float2 fa = __bfloat1622float2(a[j]), fb = __bfloat1622float2(b[j]);
+                fa.x += fb.x; fa.y += fb.y;
+                if (p.act == 1) { fa.x = fmaxf(fa.x, 0.f); fa.y = fmaxf(fa.y, 0.f); }
+                a[j] = __floats2bfloat162_rn(fa.x, fa.y);
+              }
+            }
+            *reinterpret_cast<uint4*>(p.y + off) = val;
+          }
+          r += dr; c8 += dc;
+          if (c8 >= chunks_per_row) { c8 -= chunks_per_row; ++r; }
+        }
       }
     }
   }
@@ -233,7 +240,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
 // conv_rows.cu: shared-memory-reuse kernel for stride-1 3x3 layers whose filter fits in shared memory
 int hb_conv_rows_try(const void* x, const void* w, void* y, const float* bias, const void* residual, int N, int H, int W,
-                     int Cin, int Cout, int act, int num_ctas, cudaStream_t stream);
+                     int Cin, int Cout, int act, int num_ctas, cudaStream_t stream, int nextra = 0,
+                     const void* const* xe = nullptr, const void* const* we = nullptr);
 
 extern "C" {
 
@@ -277,7 +285,7 @@ int hb_conv2d_fprop_bf16(const void* x, const void* w, void* y, const float* bia
   p.num_n_tiles = (Cout + BN - 1) / BN;
   p.cblocks = (Cin + kBK - 1) / kBK;
   p.b_stage_bytes = ((BN * 128) + 1023) & ~1023;
-  p.out_pitch = BN * 2 + 16;
+  p.out_pitch = (BN < 64 ? BN : 64) * 2 + 16;
   const int out_bytes = ((kBM * p.out_pitch) + 1023) & ~1023;
   const int stage_bytes = kABytes + p.b_stage_bytes;
   int stages = (204 * 1024 - out_bytes) / stage_bytes;

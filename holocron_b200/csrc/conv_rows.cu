@@ -42,17 +42,20 @@ struct RowsParams {
   int w_tap_bytes;   // BN * 128 rounded to 1024
   int out_pitch;
   int act;
+  int nextra;        // 0..2 additional "centre tap only" sources accumulated into the same output (see below)
   __nv_bfloat16* y;
   const float* bias;
   const __nv_bfloat16* residual;
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
-conv_rows_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const RowsParams p) {
+conv_rows_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                 const __grid_constant__ CUtensorMap tmXe0, const __grid_constant__ CUtensorMap tmWe0,
+                 const __grid_constant__ CUtensorMap tmXe1, const __grid_constant__ CUtensorMap tmWe1, const RowsParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* wsm = smem;                                          // [9][CB][BN x 128 B]
-  uint8_t* stage0 = wsm + (size_t)9 * p.CB * p.w_tap_bytes;     // 2 stages
+  uint8_t* wsm = smem;                                          // [9 + nextra][CB][BN x 128 B]
+  uint8_t* stage0 = wsm + (size_t)(9 + p.nextra) * p.CB * p.w_tap_bytes;     // ring of 2 block buffers
   uint8_t* sout = stage0 + (size_t)2 * p.stage_bytes;           // [128][out_pitch]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sout + (((size_t)128 * p.out_pitch + 15) & ~size_t(15)));
   uint64_t* full_bar = bars;        // [2]
@@ -82,26 +85,35 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
-      // resident filter: 9 taps x CB channel blocks
-      mbar_arrive_expect_tx(w_bar, (uint32_t)(9 * p.CB * p.BN * 128));
+      prefetch_tmap(&tmXe0); prefetch_tmap(&tmWe0); prefetch_tmap(&tmXe1); prefetch_tmap(&tmWe1);
+      // resident filters: 9 taps x CB channel blocks (+ one 1x1 filter per extra source)
+      mbar_arrive_expect_tx(w_bar, (uint32_t)((9 + p.nextra) * p.CB * p.BN * 128));
       for (int tap = 0; tap < 9; ++tap)
         for (int cb = 0; cb < p.CB; ++cb)
           tma_load_3d(&tmW, w_bar, wsm + (size_t)(tap * p.CB + cb) * p.w_tap_bytes, cb * 64, tap, 0);
-      const uint32_t tx = (uint32_t)(p.CB * (p.TRO + 2) * p.Wp * 128);
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        const int st = it & 1;
-        const uint32_t ph = (it >> 1) & 1;
+      for (int e = 0; e < p.nextra; ++e)
+        for (int cb = 0; cb < p.CB; ++cb)
+          tma_load_3d(e == 0 ? &tmWe0 : &tmWe1, w_bar, wsm + (size_t)((9 + e) * p.CB + cb) * p.w_tap_bytes, cb * 64, 0, 0);
+      const uint32_t tx_main = (uint32_t)(p.CB * (p.TRO + 2) * p.Wp * 128);
+      const uint32_t tx_extra = (uint32_t)(p.CB * p.TRO * p.Wp * 128);
+      int blk = 0;   // running block counter: ring slot = blk & 1, phase = (blk >> 1) & 1
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int n = tile / p.tiles_per_img, p0 = (tile % p.tiles_per_img) * p.TRO;
-        mbar_wait(&empty_bar[st], ph ^ 1);
-        mbar_arrive_expect_tx(&full_bar[st], tx);
-        for (int cb = 0; cb < p.CB; ++cb) {
-          // box (64 ch, Wp, TRO+2 rows, 1 image) at (c, w = -1, h = p0 - 1, n): halo and image borders = OOB zero fill
-          asm volatile(
-              "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-              ::"r"(smem_u32(stage0 + (size_t)st * p.stage_bytes + (size_t)cb * p.cb_bytes)),
-                "l"(reinterpret_cast<uint64_t>(&tmX)), "r"(smem_u32(&full_bar[st])), "r"(cb * 64), "r"(-1), "r"(p0 - 1), "r"(n)
-              : "memory");
+        for (int b = 0; b <= p.nextra; ++b, ++blk) {
+          const int st = blk & 1;
+          const uint32_t ph = (blk >> 1) & 1;
+          mbar_wait(&empty_bar[st], ph ^ 1);
+          mbar_arrive_expect_tx(&full_bar[st], b == 0 ? tx_main : tx_extra);
+          const CUtensorMap* tm = b == 0 ? &tmX : (b == 1 ? &tmXe0 : &tmXe1);
+          const int h0 = b == 0 ? p0 - 1 : p0;   // the extra sources need no row halo (centre tap only)
+          for (int cb = 0; cb < p.CB; ++cb) {
+            // box (64 ch, Wp, rows, 1 image) at (c, w = -1, h0, n): halo and image borders = OOB zero fill
+            asm volatile(
+                "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                ::"r"(smem_u32(stage0 + (size_t)st * p.stage_bytes + (size_t)cb * p.cb_bytes)),
+                  "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(&full_bar[st])), "r"(cb * 64), "r"(-1), "r"(h0), "r"(n)
+                : "memory");
+          }
         }
       }
     }
@@ -114,36 +126,50 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       const uint32_t w_tap_lo = (uint32_t)p.w_tap_bytes >> 4;
       const uint32_t cb_lo = (uint32_t)p.cb_bytes >> 4;
       mbar_wait(w_bar, 0);
-      int it = 0;
+      int it = 0, blk = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        const int st = it & 1;
-        const uint32_t ph = (it >> 1) & 1;
-        mbar_wait(&tmem_empty[st], ph ^ 1);   // accumulator set `st` drained by the epilogue
-        mbar_wait(&full_bar[st], ph);         // input rows landed
-        tc_fence_after();
-        const uint32_t s_lo = desc_lo(smem_u32(stage0 + (size_t)st * p.stage_bytes), 16);
-        for (int sub = 0; sub < p.NSUB; ++sub) {
-          const uint32_t d_tmem = tmem_base + st * 256 + sub * p.BN;
-          uint32_t accum = 0;
+        const int acc = it & 1;
+        mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);   // accumulator set drained by the epilogue
+        for (int b = 0; b <= p.nextra; ++b, ++blk) {
+          const int st = blk & 1;
+          mbar_wait(&full_bar[st], (blk >> 1) & 1);         // block landed
+          tc_fence_after();
+          const uint32_t s_lo = desc_lo(smem_u32(stage0 + (size_t)st * p.stage_bytes), 16);
+          for (int sub = 0; sub < p.NSUB; ++sub) {
+            const uint32_t d_tmem = tmem_base + acc * 256 + sub * p.BN;
+            if (b == 0) {
+              uint32_t accum = 0;
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            const int r = tap / 3, s = tap % 3;
-            // 128-byte pixel rows: (row index) * 128 B >> 4 = row index * 8
-            uint32_t a_lo = s_lo + (uint32_t)(((sub * p.SR + r) * p.Wp + s) * 8);
-            uint32_t b_lo = w_lo0 + (uint32_t)(tap * p.CB) * w_tap_lo;
-            for (int cb = 0; cb < p.CB; ++cb) {
-              const int ks = (cb == p.CB - 1) ? p.ksteps_last : 4;
-              for (int k = 0; k < ks; ++k) {
-                umma_f16_lh(d_tmem, a_lo + 2 * k, dhi, b_lo + 2 * k, dhi, idesc, accum);
-                accum = 1;
+              for (int tap = 0; tap < 9; ++tap) {
+                const int r = tap / 3, s = tap % 3;
+                // 128-byte pixel rows: (row index) * 128 B >> 4 = row index * 8
+                uint32_t a_lo = s_lo + (uint32_t)(((sub * p.SR + r) * p.Wp + s) * 8);
+                uint32_t b_lo = w_lo0 + (uint32_t)(tap * p.CB) * w_tap_lo;
+                for (int cb = 0; cb < p.CB; ++cb) {
+                  const int ks = (cb == p.CB - 1) ? p.ksteps_last : 4;
+                  for (int k = 0; k < ks; ++k) {
+                    umma_f16_lh(d_tmem, a_lo + 2 * k, dhi, b_lo + 2 * k, dhi, idesc, accum);
+                    accum = 1;
+                  }
+                  a_lo += cb_lo;
+                  b_lo += w_tap_lo;
+                }
               }
-              a_lo += cb_lo;
-              b_lo += w_tap_lo;
+            } else {
+              // centre-tap source: buffer row 0 is output row p0, columns start at w = -1 -> window offset 1 pixel
+              uint32_t a_lo = s_lo + (uint32_t)((sub * p.SR * p.Wp + 1) * 8);
+              uint32_t b_lo = w_lo0 + (uint32_t)((9 + b - 1) * p.CB) * w_tap_lo;
+              for (int cb = 0; cb < p.CB; ++cb) {
+                const int ks = (cb == p.CB - 1) ? p.ksteps_last : 4;
+                for (int k = 0; k < ks; ++k) umma_f16_lh(d_tmem, a_lo + 2 * k, dhi, b_lo + 2 * k, dhi, idesc, 1u);
+                a_lo += cb_lo;
+                b_lo += w_tap_lo;
+              }
             }
           }
+          umma_commit(&empty_bar[st]);   // ring slot may be refilled
         }
-        umma_commit(&empty_bar[st]);   // input stage may be refilled
-        umma_commit(&tmem_full[st]);   // accumulators of this tile complete
+        umma_commit(&tmem_full[acc]);    // accumulators of this tile complete
       }
     }
   } else {
@@ -203,10 +229,13 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const int row0 = p0 + sub * p.SR;
         const int rows_valid = max(0, min(p.SR, min(p.H, p0 + p.TRO) - row0));
         const int total = rows_valid * p.W * chunks_per_row;
+        // division-free walk: thread `et` starts at chunk et of the valid pixels and advances by 128 chunks per trip
+        int pix0 = et / chunks_per_row;
+        int c8 = et - pix0 * chunks_per_row;
+        int i = pix0 / p.W, q = pix0 - i * p.W;
+        const int dpix = 128 / chunks_per_row, dc = 128 - dpix * chunks_per_row;
+        const int di = dpix / p.W, dq = dpix - di * p.W;
         for (int ch = et; ch < total; ch += 128) {
-          const int c8 = ch % chunks_per_row;
-          const int pix = ch / chunks_per_row;
-          const int i = pix / p.W, q = pix % p.W;
           uint4 val = *reinterpret_cast<const uint4*>(sout + (size_t)(i * p.Wp + q) * p.out_pitch + c8 * 16);
           const size_t off = ((size_t)(n * p.H + row0 + i) * p.W + q) * p.Cout + c8 * 8;
           if (p.residual) {
@@ -222,6 +251,9 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             }
           }
           *reinterpret_cast<uint4*>(p.y + off) = val;
+          c8 += dc; q += dq; i += di;
+          if (c8 >= chunks_per_row) { c8 -= chunks_per_row; ++q; }
+          if (q >= p.W) { q -= p.W; ++i; }
         }
       }
     }
@@ -235,31 +267,34 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 }  // namespace
 
 // Returns 0 and launches when the shape is eligible; returns -1 (nothing launched) when the caller should use the
-// generic implicit-GEMM kernel instead. Not part of the public C ABI (called from hb_conv2d_fprop_bf16).
+// generic implicit-GEMM kernel instead. Not part of the public C ABI (called from hb_conv2d_fprop_bf16 and
+// hb_conv3x3_accum_bf16). xe/we: up to two extra [N,H,W,Cin] sources with [Cout,1,1,Cin] filters accumulated into the
+// same output:  y = conv3x3(x, w) + sum_e conv1x1(xe[e], we[e]).
 int hb_conv_rows_try(const void* x, const void* w, void* y, const float* bias, const void* residual, int N, int H, int W,
-                     int Cin, int Cout, int act, int num_ctas, cudaStream_t stream) {
+                     int Cin, int Cout, int act, int num_ctas, cudaStream_t stream, int nextra = 0,
+                     const void* const* xe = nullptr, const void* const* we = nullptr) {
   if (Cout % 16 != 0 || Cout > 128 || Cin % 8 != 0 || Cin > 128) return -1;
   const int Wp = W + 2;
-  if (Wp > 128 || W < 8) return -1;
+  if (Wp > 128 || W < 8 || nextra < 0 || nextra > 2) return -1;
   RowsParams p{};
-  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.Wp = Wp; p.BN = Cout;
+  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.Wp = Wp; p.BN = Cout; p.nextra = nextra;
   p.SR = 128 / Wp;
   p.CB = (Cin + 63) / 64;
   const int last = Cin - (p.CB - 1) * 64;
   p.ksteps_last = (last + 15) / 16;
   p.w_tap_bytes = ((Cout * 128) + 1023) & ~1023;
   p.out_pitch = Cout * 2 + 16;
-  const int w_bytes = 9 * p.CB * p.w_tap_bytes;
+  const int w_bytes = (9 + nextra) * p.CB * p.w_tap_bytes;
   const int out_bytes = ((128 * p.out_pitch) + 1023) & ~1023;
   const int budget = 222 * 1024 - w_bytes - out_bytes - 256;
-  // largest NSUB whose two stages fit in shared memory and whose accumulators fit half of TMEM
+  // largest NSUB whose two ring buffers fit in shared memory and whose accumulators fit half of TMEM
   int nsub = 256 / Cout;
   if (nsub > 8) nsub = 8;
   const int max_rows_needed = (H + p.SR - 1) / p.SR;
   if (nsub > max_rows_needed) nsub = max_rows_needed;
   for (; nsub >= 1; --nsub) {
     const int cb_bytes = (((nsub * p.SR + 2) * Wp * 128) + 1023) & ~1023;
-    // the last sub-tile's windows read up to 127 + 2*Wp + 2 pixel rows past its first row: keep them inside the stage
+    // the last sub-tile's windows read up to 127 + 2*Wp + 2 pixel rows past its first row: keep them inside the buffer
     const int reach = (((nsub - 1) * p.SR + 2) * Wp + 2 + 128) * 128;
     const int need = cb_bytes > reach ? cb_bytes : ((reach + 1023) & ~1023);
     if (2 * p.CB * need <= budget) { p.cb_bytes = need; break; }
@@ -273,7 +308,7 @@ int hb_conv_rows_try(const void* x, const void* w, void* y, const float* bias, c
   p.act = act;
   p.y = (__nv_bfloat16*)y; p.bias = bias; p.residual = (const __nv_bfloat16*)residual;
 
-  CUtensorMap tmX, tmW;
+  CUtensorMap tmX, tmW, tmXe[2], tmWe[2];
   {
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
     uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
@@ -283,6 +318,17 @@ int hb_conv_rows_try(const void* x, const void* w, void* y, const float* bias, c
     uint64_t wstrides[2] = {(uint64_t)Cin * 2, (uint64_t)9 * Cin * 2};
     uint32_t wbox[3] = {64, 1, (uint32_t)Cout};
     if (tmap::encode_tiled_bf16(&tmW, w, 3, wdims, wstrides, wbox, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
+    uint32_t ebox[4] = {64, (uint32_t)Wp, (uint32_t)p.TRO, 1};
+    uint64_t ewdims[3] = {(uint64_t)Cin, 1, (uint64_t)Cout};
+    uint64_t ewstrides[2] = {(uint64_t)Cin * 2, (uint64_t)Cin * 2};
+    for (int e = 0; e < 2; ++e) {
+      // unused slots alias the main tensors (never dereferenced by the kernel)
+      const void* xs = e < nextra ? xe[e] : x;
+      const void* ws = e < nextra ? we[e] : w;
+      if (!hb::aligned16(xs) || !hb::aligned16(ws)) return -1;
+      if (tmap::encode_tiled_bf16(&tmXe[e], xs, 4, dims, strides, ebox, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
+      if (tmap::encode_tiled_bf16(&tmWe[e], ws, 3, ewdims, ewstrides, wbox, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
+    }
   }
   const size_t smem_bytes = (size_t)w_bytes + 2 * (size_t)p.stage_bytes + out_bytes + 256 + 1024;
   static bool attr_set = false;
@@ -294,7 +340,28 @@ int hb_conv_rows_try(const void* x, const void* w, void* y, const float* bias, c
   if (smem_bytes > 227 * 1024) return -1;
   int grid = num_ctas > 0 ? num_ctas : HB_NUM_SMS;
   if (grid > p.num_tiles) grid = p.num_tiles;
-  conv_rows_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmX, tmW, p);
+  conv_rows_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmX, tmW, tmXe[0], tmWe[0], tmXe[1], tmWe[1], p);
   g_hb_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
+
+extern "C" {
+
+// y[N,H,W,Cout] = conv3x3(x, w; stride 1, pad 1) + sum_{e < nextra} conv1x1(xe[e], we[e])    (all NHWC bf16, Cin channels)
+// One kernel, one accumulator: used for the input gradient of a RepVGG block,
+//   dX = dgrad3x3(dY3) + dgrad1x1(dY1) + I * dX_identity
+// (reference: the three autograd contributions of models/classification/repvgg.py:71-73 summed by two add kernels).
+// Returns cudaErrorNotSupported (801) without launching when the shape does not fit the shared-memory-resident scheme;
+// callers then fall back to separate convolutions.
+int hb_conv3x3_accum_bf16(const void* x, const void* w, const void* xe0, const void* we0, const void* xe1, const void* we1,
+                          int nextra, void* y, int N, int H, int W, int Cin, int Cout, int num_ctas, void* stream) {
+  const void* xe[2] = {xe0, xe1};
+  const void* we[2] = {we0, we1};
+  if (!hb::aligned16(x) || !hb::aligned16(w) || !hb::aligned16(y)) return (int)cudaErrorMisalignedAddress;
+  const int rc = hb_conv_rows_try(x, w, y, nullptr, nullptr, N, H, W, Cin, Cout, 0, num_ctas, (cudaStream_t)stream, nextra,
+                                  xe, we);
+  if (rc == 0) return 0;
+  return rc == -1 ? (int)cudaErrorNotSupported : (int)cudaErrorLaunchFailure;
+}
+
+}  // extern "C"

@@ -13,6 +13,7 @@
 // fp32 red.global.add (or stored directly when there is a single range).
 // This replaces cuDNN's wgrad behind autograd for nn.Conv2d in the reference
 // (holocron/models/utils.py:71, models/classification/repvgg.py:55-62).
+#include <cstdlib>
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "tmap.cuh"
@@ -36,8 +37,10 @@ struct WgradParams {
   int num_tap_groups, num_co_tiles, num_ci_tiles, k_splits;
   int kblocks_total;   // ceil(m_total / 64)
   int stages, stage_bytes;
-  int use_atomics;
-  float* dw;  // [Cout, R, S, Cin] fp32
+  int use_atomics;     // 0: single pixel range, store; 1: atomics; 2: per-range partials in `ws` (reduced by a 2nd kernel)
+  float* dw;           // [Cout, R, S, Cin] fp32
+  float* ws;           // [k_splits][Cout*R*S*Cin] fp32 partial sums (mode 2)
+  long long dw_elems;
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -160,6 +163,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
       const int co = co_t * 128 + quarter * 32 + lane;
       const bool co_ok = co < p.Cout;
       const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      if (kb1 <= kb0 && p.use_atomics == 2 && co_ok) {
+        // empty pixel range: this unit's slice of the partial buffer must still read as zero
+        for (int t = 0; t < ntaps; ++t)
+          for (int c = 0; c < p.ci_tile && ci_t * p.ci_tile + c < p.Cin; ++c)
+            p.ws[(size_t)ks * p.dw_elems + ((size_t)co * RS + tap0 + t) * p.Cin + ci_t * p.ci_tile + c] = 0.f;
+      }
       if (kb1 > kb0) {
         for (int t = 0; t < ntaps; ++t) {
           const int tap = tap0 + t;
@@ -169,9 +178,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
             tmem_ld_wait();
             const int ci = ci_t * p.ci_tile + c;
             if (co_ok && ci < p.Cin) {
-              float* dst = p.dw + ((size_t)co * RS + tap) * p.Cin + ci;
+              float* base = p.use_atomics == 2 ? p.ws + (size_t)ks * p.dw_elems : p.dw;
+              float* dst = base + ((size_t)co * RS + tap) * p.Cin + ci;
               const int nvalid = min(16, p.Cin - ci);
-              if (p.use_atomics) {
+              if (p.use_atomics == 1) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
                   if (j < nvalid) atomicAdd(dst + j, __uint_as_float(v[j]));
@@ -203,27 +213,43 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
 }
 
-}  // namespace
+// dw[i] = sum_k ws[k][i]  (fixed order: deterministic), 4 elements per thread
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, long long n, int k_splits) {
+  const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= n) return;
+  if (i4 + 3 < n) {
+    float4 acc = *reinterpret_cast<const float4*>(ws + i4);
+#pragma unroll 8
+    for (int k = 1; k < k_splits; ++k) {
+      const float4 v = *reinterpret_cast<const float4*>(ws + (size_t)k * n + i4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    *reinterpret_cast<float4*>(dw + i4) = acc;
+  } else {
+    for (long long i = i4; i < n; ++i) {
+      float acc = 0.f;
+      for (int k = 0; k < k_splits; ++k) acc += ws[(size_t)k * n + i];
+      dw[i] = acc;
+    }
+  }
+}
 
-extern "C" {
+struct WgradPlan {
+  WgradParams p;
+  size_t ws_bytes;
+};
 
-// dW (fp32, [Cout,R,S,Cin]) = wgrad(x [N,H,W,Cin] bf16, dy [N,Ho,Wo,Cout] bf16). Overwrites dW.
-// Requirements: Cin % 8 == 0, Cout % 8 == 0, 16-byte aligned pointers.
-int hb_conv2d_wgrad_bf16(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int R, int S,
-                         int stride, int pad, int dil, int num_ctas, void* stream) {
-  if (Cin % 8 != 0 || Cout % 8 != 0) return (int)cudaErrorInvalidValue;
-  if (!hb::aligned16(x) || !hb::aligned16(dy) || !hb::aligned16(dw)) return (int)cudaErrorMisalignedAddress;
+// shared planning of the decomposition (also used by the workspace-size query)
+int plan_wgrad(WgradPlan& plan, int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int dil,
+               int num_ctas) {
+  WgradParams& p = plan.p;
   const int Ho = (H + 2 * pad - dil * (R - 1) - 1) / stride + 1;
   const int Wo = (W + 2 * pad - dil * (S - 1) - 1) / stride + 1;
   const long long m_ll = (long long)N * Ho * Wo;
   if (Ho <= 0 || Wo <= 0 || m_ll > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
-  cudaStream_t st = (cudaStream_t)stream;
-
-  WgradParams p{};
   p.m_total = (int)m_ll; p.Ho = Ho; p.Wo = Wo; p.stride = stride; p.pad = pad; p.dil = dil;
   p.R = R; p.S = S; p.Cin = Cin; p.Cout = Cout;
   const int RS = R * S;
-  // Cin tile: whole Cin up to 256, otherwise the largest divisor that is a multiple of 64 (or 256 + masked tail)
   int ci_tile = Cin;
   if (Cin > 256) {
     ci_tile = 256;
@@ -231,10 +257,9 @@ int hb_conv2d_wgrad_bf16(const void* x, const void* dy, float* dw, int N, int H,
   }
   p.ci_tile = ci_tile;
   p.ci_chunks = (ci_tile + 63) / 64;
-  p.ci_cols = (ci_tile + 31) & ~31;
+  p.ci_cols = (ci_tile + 15) & ~15;
   p.taps_per_group = kTmemCols / p.ci_cols;
   if (p.taps_per_group > RS) p.taps_per_group = RS;
-  // smem: keep at least 2 stages
   auto stage_bytes_for = [&](int taps) { return kABytes + taps * p.ci_chunks * kChunkBytes; };
   while (p.taps_per_group > 1 && 2 * stage_bytes_for(p.taps_per_group) > 200 * 1024) --p.taps_per_group;
   p.stage_bytes = stage_bytes_for(p.taps_per_group);
@@ -253,9 +278,66 @@ int hb_conv2d_wgrad_bf16(const void* x, const void* dy, float* dw, int N, int H,
   if (k_splits > max_splits) k_splits = max_splits;
   if (k_splits < 1) k_splits = 1;
   p.k_splits = k_splits;
-  p.use_atomics = k_splits > 1 ? 1 : 0;
+  p.dw_elems = (long long)Cout * RS * Cin;
+  plan.ws_bytes = k_splits > 1 ? (size_t)k_splits * p.dw_elems * sizeof(float) : 0;
+  return 0;
+}
+
+}  // namespace
+
+// conv_wgrad_rows.cu: row-window variant for stride-1 3x3 layers with few channels
+size_t hb_wgrad_rows_workspace_bytes(int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int dil,
+                                     int num_ctas);
+int hb_wgrad_rows_try(const void* x, const void* dy, float* ws, size_t ws_bytes, int N, int H, int W, int Cin, int Cout,
+                      int num_ctas, cudaStream_t stream, int* grid_out);
+
+extern "C" {
+
+// Bytes of fp32 scratch hb_conv2d_wgrad_bf16 wants for this shape (0 when a single pixel range is used). With a
+// workspace the per-range partial sums are written with plain stores and reduced in a fixed order (deterministic);
+// without one they are accumulated with fp32 atomics.
+size_t hb_conv2d_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int dil,
+                                       int num_ctas) {
+  WgradPlan plan{};
+  if (plan_wgrad(plan, N, H, W, Cin, Cout, R, S, stride, pad, dil, num_ctas)) return 0;
+  const size_t rows = hb_wgrad_rows_workspace_bytes(N, H, W, Cin, Cout, R, S, stride, pad, dil, num_ctas);
+  return rows > plan.ws_bytes ? rows : plan.ws_bytes;
+}
+
+// dW (fp32, [Cout,R,S,Cin]) = wgrad(x [N,H,W,Cin] bf16, dy [N,Ho,Wo,Cout] bf16). Overwrites dW.
+// Requirements: Cin % 8 == 0, Cout % 8 == 0, 16-byte aligned pointers.
+int hb_conv2d_wgrad_bf16(const void* x, const void* dy, float* dw, float* workspace, size_t workspace_bytes, int N, int H,
+                         int W, int Cin, int Cout, int R, int S, int stride, int pad, int dil, int num_ctas, void* stream) {
+  if (Cin % 8 != 0 || Cout % 8 != 0) return (int)cudaErrorInvalidValue;
+  if (!hb::aligned16(x) || !hb::aligned16(dy) || !hb::aligned16(dw)) return (int)cudaErrorMisalignedAddress;
+  cudaStream_t st = (cudaStream_t)stream;
+  static const bool rows_enabled = getenv("HB_DISABLE_WGRAD_ROWS") == nullptr;
+  if (rows_enabled && R == 3 && S == 3 && stride == 1 && pad == 1 && dil == 1 && workspace && hb::aligned16(workspace)) {
+    int slices = 0;
+    const int rc = hb_wgrad_rows_try(x, dy, workspace, workspace_bytes, N, H, W, Cin, Cout, num_ctas, st, &slices);
+    if (rc == 0) {
+      const long long n = (long long)Cout * 9 * Cin;
+      wgrad_reduce_kernel<<<(unsigned)((n / 4 + 256) / 256), 256, 0, st>>>(workspace, dw, n, slices);
+      HB_LAUNCH_CHECK();
+      return 0;
+    }
+    if (rc == -2) return (int)cudaErrorLaunchFailure;
+  }
+  WgradPlan plan{};
+  if (int rc = plan_wgrad(plan, N, H, W, Cin, Cout, R, S, stride, pad, dil, num_ctas)) return rc;
+  WgradParams& p = plan.p;
+  const int RS = R * S;
+  const int k_splits = p.k_splits;
+  const int base_units = p.num_co_tiles * p.num_ci_tiles * p.num_tap_groups;
+  const int ctas = num_ctas > 0 ? num_ctas : HB_NUM_SMS;
   p.dw = dw;
-  if (p.use_atomics) {
+  p.ws = workspace;
+  if (k_splits == 1) {
+    p.use_atomics = 0;
+  } else if (workspace && workspace_bytes >= plan.ws_bytes && hb::aligned16(workspace)) {
+    p.use_atomics = 2;
+  } else {
+    p.use_atomics = 1;
     cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)Cout * RS * Cin * sizeof(float), st);
     if (e != cudaSuccess) return (int)e;
   }
@@ -282,6 +364,11 @@ int hb_conv2d_wgrad_bf16(const void* x, const void* dy, float* dw, int N, int H,
   int grid = ctas < num_units ? ctas : num_units;
   conv_wgrad_kernel<<<grid, kThreads, smem_bytes, st>>>(tmDY, tmX, p);
   HB_LAUNCH_CHECK();
+  if (p.use_atomics == 2) {
+    const long long n = p.dw_elems;
+    wgrad_reduce_kernel<<<(unsigned)((n / 4 + 256) / 256), 256, 0, st>>>(workspace, dw, n, k_splits);
+    HB_LAUNCH_CHECK();
+  }
   return 0;
 }
 

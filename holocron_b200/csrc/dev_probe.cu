@@ -68,3 +68,41 @@ extern "C" int hb_dev_umma_shift_probe(const void* a, const void* b, float* out,
   HB_LAUNCH_CHECK();
   return 0;
 }
+
+// ---- probe 2: tcgen05.mma issue/execute rate as a function of N (M = 128, K = 16, bf16) -----------------------------
+// Every CTA (one per SM) issues `count` back-to-back MMAs on the same (uninitialised) smem operands and waits for the
+// commit. Reports nothing itself; time it with events from the host.
+namespace {
+__global__ void __launch_bounds__(128, 1) mma_rate_probe_kernel(int N, int count, int distinct_acc) {
+  extern __shared__ __align__(1024) uint8_t smem_raw2[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw2) + 1023) & ~uintptr_t(1023));
+  uint64_t* done = reinterpret_cast<uint64_t*>(smem + 64 * 1024);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done + 1);
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { tc::mbar_init(done, 1); tc::fence_barrier_init(); }
+  if (warp == 0) tc::tmem_alloc(tmem_ptr, 512);
+  tc::tc_fence_before(); __syncthreads(); tc::tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = tc::make_idesc_bf16(128, N, 0, 0);
+    const uint32_t dhi = tc::desc_hi(1024, tc::kLayoutSW128);
+    const uint32_t a_lo = tc::desc_lo(tc::smem_u32(smem), 16);
+    const uint32_t b_lo = tc::desc_lo(tc::smem_u32(smem + 16 * 1024), 16);
+    for (int i = 0; i < count; ++i) {
+      const uint32_t d = tmem + (distinct_acc ? (uint32_t)((i & 1) * 256) : 0u);
+      tc::umma_f16_lh(d, a_lo + 2 * (i & 3), dhi, b_lo + 2 * (i & 3), dhi, idesc, 1u);
+    }
+    tc::umma_commit(done);
+    tc::mbar_wait(done, 0);
+  }
+  tc::tc_fence_before(); __syncthreads();
+  if (warp == 0) { tc::tc_fence_after(); tc::tmem_dealloc(tmem, 512); }
+}
+}  // namespace
+
+extern "C" int hb_dev_mma_rate_probe(int N, int count, int distinct_acc, int ctas, void* stream) {
+  cudaFuncSetAttribute(mma_rate_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+  mma_rate_probe_kernel<<<ctas, 128, 70 * 1024, (cudaStream_t)stream>>>(N, count, distinct_acc);
+  HB_LAUNCH_CHECK();
+  return 0;
+}

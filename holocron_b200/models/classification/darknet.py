@@ -15,8 +15,9 @@ from ...nn.init import init_module
 from .._blocks import FusedSequential, run_fused
 from ..utils import conv_sequence
 
-__all__ = ["CSPStage", "DarknetBodyV3", "DarknetBodyV4", "DarknetV3", "DarknetV4", "ResBlock", "cspdarknet53",
-           "cspdarknet53_mish", "darknet53"]
+__all__ = ["CSPStage", "DarknetBodyV1", "DarknetBodyV2", "DarknetBodyV3", "DarknetBodyV4", "DarknetV1", "DarknetV2",
+           "DarknetV3", "DarknetV4", "ResBlock", "cspdarknet53", "cspdarknet53_mish", "darknet19", "darknet24",
+           "darknet53"]
 
 
 class ResBlock(nn.Module):
@@ -188,9 +189,124 @@ class DarknetV4(_DarknetClassifier):
         init_module(self, "leaky_relu")
 
 
+class DarknetBodyV1(nn.Sequential):
+    """YOLOv1 backbone: 7x7 stride-2 stem, then max-pool + alternating 1x1 / 3x3 units; no normalisation layer by
+    default, so the convolutions carry a bias that is fused with the LeakyReLU in the conv epilogue pass
+    (reference holocron/models/classification/darknet.py:29-105)."""
+
+    def __init__(self, layout: List[List[int]], in_channels: int = 3, stem_channels: int = 64, act_layer=None,
+                 norm_layer=None, drop_layer=None, conv_layer=None) -> None:
+        if act_layer is None:
+            act_layer = nn.LeakyReLU(0.1, inplace=True)
+        in_chans = [stem_channels] + [_layout[-1] for _layout in layout[:-1]]
+        super().__init__(OrderedDict([
+            ("stem", FusedSequential(*conv_sequence(in_channels, stem_channels, act_layer, norm_layer, drop_layer, conv_layer,
+                                                     kernel_size=7, padding=3, stride=2, bias=(norm_layer is None)))),
+            ("layers", nn.Sequential(*[self._make_layer([_in, *planes], act_layer, norm_layer, drop_layer, conv_layer)
+                                       for _in, planes in zip(in_chans, layout)])),
+        ]))
+        init_module(self, "leaky_relu")
+
+    @staticmethod
+    def _make_layer(planes: List[int], act_layer=None, norm_layer=None, drop_layer=None, conv_layer=None):
+        layers: List[nn.Module] = [nn.MaxPool2d(2)]
+        for in_planes, out_planes in zip(planes[:-1], planes[1:]):
+            grow = out_planes > in_planes
+            layers.extend(conv_sequence(in_planes, out_planes, act_layer, norm_layer, drop_layer, conv_layer,
+                                        kernel_size=3 if grow else 1, padding=1 if grow else 0,
+                                        bias=(norm_layer is None)))
+        return FusedSequential(*layers)
+
+
+class DarknetV1(_DarknetClassifier):
+    """reference darknet.py:108-133."""
+
+    def __init__(self, layout: List[List[int]], num_classes: int = 10, in_channels: int = 3, stem_channels: int = 64,
+                 act_layer=None, norm_layer=None, drop_layer=None, conv_layer=None) -> None:
+        super().__init__(OrderedDict([
+            ("features", DarknetBodyV1(layout, in_channels, stem_channels, act_layer, norm_layer, drop_layer, conv_layer)),
+            ("pool", GlobalAvgPool2d(flatten=True)),
+            ("classifier", nn.Linear(layout[2][-1], num_classes)),
+        ]))
+        init_module(self, "leaky_relu")
+
+
+class DarknetBodyV2(nn.Sequential):
+    """YOLOv2 backbone (reference darknetv2.py:32-148): 3x3 stem, then per stage max-pool + 3x3 + n x (1x1, 3x3)."""
+
+    def __init__(self, layout: List[Tuple[int, int]], in_channels: int = 3, stem_channels: int = 32, passthrough: bool = False,
+                 act_layer=None, norm_layer=None, drop_layer=None, conv_layer=None) -> None:
+        if act_layer is None:
+            act_layer = nn.LeakyReLU(0.1, inplace=True)
+        if norm_layer is None:
+            norm_layer = nn.BatchNorm2d
+        in_chans = [stem_channels] + [_layout[0] for _layout in layout[:-1]]
+        super().__init__(OrderedDict([
+            ("stem", FusedSequential(*conv_sequence(in_channels, stem_channels, act_layer, norm_layer, drop_layer, conv_layer,
+                                                     kernel_size=3, padding=1, bias=(norm_layer is None)))),
+            ("layers", nn.Sequential(*[self._make_layer(nb, _in, out, act_layer, norm_layer, drop_layer, conv_layer)
+                                       for _in, (out, nb) in zip(in_chans, layout)])),
+        ]))
+        self.passthrough = passthrough
+
+    @staticmethod
+    def _make_layer(num_blocks: int, in_planes: int, out_planes: int, act_layer=None, norm_layer=None, drop_layer=None,
+                    conv_layer=None):
+        layers: List[nn.Module] = [nn.MaxPool2d(2)]
+        layers.extend(conv_sequence(in_planes, out_planes, act_layer, norm_layer, drop_layer, conv_layer, kernel_size=3,
+                                    padding=1, stride=1, bias=(norm_layer is None)))
+        for _ in range(num_blocks):
+            layers.extend(conv_sequence(out_planes, out_planes // 2, act_layer, norm_layer, drop_layer, conv_layer,
+                                        kernel_size=1, padding=0, stride=1, bias=(norm_layer is None)))
+            layers.extend(conv_sequence(out_planes // 2, out_planes, act_layer, norm_layer, drop_layer, conv_layer,
+                                        kernel_size=3, padding=1, stride=1, bias=(norm_layer is None)))
+        return FusedSequential(*layers)
+
+    def forward(self, x: Tensor):  # type: ignore[override]
+        x = self.stem(x)
+        aux = None
+        for idx, layer in enumerate(self.layers):
+            x = layer(x)
+            if self.passthrough and idx == len(self.layers) - 2:
+                aux = x.clone()
+        return (x, aux) if self.passthrough else x
+
+
+class DarknetV2(nn.Sequential):
+    """reference darknetv2.py:151-178 (1x1 convolution classifier followed by global average pooling)."""
+
+    def __init__(self, layout: List[Tuple[int, int]], num_classes: int = 10, in_channels: int = 3, stem_channels: int = 32,
+                 act_layer=None, norm_layer=None, drop_layer=None, conv_layer=None) -> None:
+        super().__init__(OrderedDict([
+            ("features", DarknetBodyV2(layout, in_channels, stem_channels, False, act_layer, norm_layer, drop_layer,
+                                       conv_layer)),
+            ("classifier", nn.Conv2d(layout[-1][0], num_classes, 1)),
+            ("pool", GlobalAvgPool2d(flatten=True)),
+        ]))
+        init_module(self, "leaky_relu")
+
+    def forward(self, x: Tensor) -> Tensor:  # type: ignore[override]
+        from .._blocks import conv_bn_act
+        feats = self.features(x)
+        logits = conv_bn_act(feats, self.classifier, None, None, keep_padded=False)
+        return logits.float().mean((2, 3))
+
+
 def _no_pretrained(pretrained: bool, checkpoint: Any) -> None:
     if pretrained or checkpoint is not None:
         raise NotImplementedError("pretrained checkpoints need network access; load a reference state_dict instead")
+
+
+def darknet24(pretrained: bool = False, progress: bool = True, **kwargs: Any) -> DarknetV1:
+    """Darknet-24 / YOLOv1 backbone (reference darknet.py:143-159)."""
+    _no_pretrained(pretrained, None)
+    return DarknetV1([[192], [128, 256, 256, 512], [*([256, 512] * 4), 512, 1024], [512, 1024] * 2], **kwargs)
+
+
+def darknet19(pretrained: bool = False, checkpoint: Any = None, progress: bool = True, **kwargs: Any) -> DarknetV2:
+    """Darknet-19 / YOLOv2 backbone (reference darknetv2.py:211-237)."""
+    _no_pretrained(pretrained, checkpoint)
+    return DarknetV2([(64, 0), (128, 1), (256, 1), (512, 2), (1024, 2)], **kwargs)
 
 
 def darknet53(pretrained: bool = False, checkpoint: Any = None, progress: bool = True, **kwargs: Any) -> DarknetV3:

@@ -14,7 +14,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 from torch import Tensor, nn
 
-from .._lib import check, lib, ptr, require_cuda, stream_ptr
+from .._lib import DTYPE_CODE, check, lib, ptr, require_cuda, stream_ptr
 
 ACT_NONE, ACT_RELU, ACT_RELU6, ACT_SILU, ACT_LEAKY, ACT_MISH, ACT_HARDMISH, ACT_FRELU = range(8)
 
@@ -200,11 +200,9 @@ class _Conv2dFn(torch.autograd.Function):
                                        (r - 1) * dil - pad, 1, ACT_NONE, 0, stream_ptr()), "hb_conv2d_fprop_bf16[dgrad]"))
             dx = dxp if cin_d == cin_x else dxp[:, :cin_x]
         if ctx.needs_input_grad[1]:
-            dwp = torch.empty((cout_p, r, s, cin_p), device=dyb.device, dtype=torch.float32)
-            info = dict(N=n, H=h, W=w, Cin=cin_p, Cout=cout_p, R=r, S=s, stride=stride, Ho=ho, Wo=wo)
-            _timed("wgrad", info, lambda: check(
-                L.hb_conv2d_wgrad_bf16(ptr(xb), ptr(dyb), ptr(dwp), n, h, w, cin_p, cout_p, r, s, stride, pad, dil, 0,
-                                       stream_ptr()), "hb_conv2d_wgrad_bf16"))
+            if r != s:
+                raise NotImplementedError("non-square filters")
+            dwp = wgrad_raw(xb, dyb, cout_p, r, stride, pad, dil)
             dw = dwp.permute(0, 3, 1, 2)
             if cin_p != cin or cout_p != cout:
                 dw = dw[:cout, :cin].contiguous(memory_format=torch.channels_last)
@@ -218,6 +216,20 @@ def conv2d(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, stride: int
     """Dense (groups=1) 2-D convolution on the sm_100a tensor cores; returns bf16 channels_last."""
     require_cuda(x, weight)
     return _Conv2dFn.apply(x, weight, bias, int(stride), int(padding), int(dilation), bool(keep_padded))
+
+
+def wgrad_raw(xb: Tensor, dyb: Tensor, cout: int, k: int, stride: int, pad: int, dil: int = 1) -> Tensor:
+    """fp32 [cout, k, k, cin_p] weight gradient of a conv with NHWC bf16 input ``xb`` and output gradient ``dyb``."""
+    n, cin_p, h, w = xb.shape
+    L = lib()
+    dwp = torch.empty((cout, k, k, cin_p), device=xb.device, dtype=torch.float32)
+    ws_bytes = L.hb_conv2d_wgrad_workspace_bytes(n, h, w, cin_p, cout, k, k, stride, pad, dil, 0)
+    ws = torch.empty(ws_bytes // 4, device=xb.device, dtype=torch.float32) if ws_bytes else None
+    info = dict(N=n, H=h, W=w, Cin=cin_p, Cout=cout, R=k, S=k, stride=stride, Ho=dyb.shape[2], Wo=dyb.shape[3])
+    _timed("wgrad", info, lambda: check(
+        L.hb_conv2d_wgrad_bf16(ptr(xb), ptr(dyb), ptr(dwp), ptr(ws), ws_bytes, n, h, w, cin_p, cout, k, k, stride, pad, dil,
+                               0, stream_ptr()), "hb_conv2d_wgrad_bf16"))
+    return dwp
 
 
 def conv2d_bias_act(x: Tensor, weight: Tensor, bias: Optional[Tensor], stride: int, padding: int, act: int = ACT_NONE,
@@ -387,13 +399,21 @@ class _RepBlockFn(torch.autograd.Function):
         gammas, betas = bn_params[:nb], bn_params[nb:]
         need_dx = ctx.needs_input_grad[1]
         cout, cin = w3.shape[0], w3.shape[1]
-        pk3 = pack_filter(w3, need_dx, round_up(x.shape[1], 8))
-        pk1 = pack_filter(w1, need_dx, round_up(x.shape[1], 8))
-        if pk3.cout_p != cout:
+        if cout % 16 != 0:
             raise NotImplementedError("fused RepBlock needs out_channels % 16 == 0")
-        xb = to_channels_last_bf16(x, pk3.cin_p)
-        y3 = conv2d_forward_raw(xb, pk3.wf, cout, 3, 3, stride, 1, 1)
-        y1 = conv2d_forward_raw(xb, pk1.wf, cout, 1, 1, stride, 0, 1)
+        stem = cin <= 4 and x.shape[1] == cin and not need_dx and x.is_contiguous() and x.dtype in DTYPE_CODE
+        if stem:
+            # network stem: explicit im2col once (27 -> 32 columns), both branches become dense GEMMs over it
+            xb, w3p, w1p = _stem_im2col(x, w3, w1, stride)
+            y3 = conv2d_forward_raw(xb, w3p, cout, 1, 1, 1, 0, 1)
+            y1 = conv2d_forward_raw(xb, w1p, cout, 1, 1, 1, 0, 1)
+            pk3 = pk1 = None
+        else:
+            pk3 = pack_filter(w3, need_dx, round_up(x.shape[1], 8))
+            pk1 = pack_filter(w1, need_dx, round_up(x.shape[1], 8))
+            xb = to_channels_last_bf16(x, pk3.cin_p)
+            y3 = conv2d_forward_raw(xb, pk3.wf, cout, 3, 3, stride, 1, 1)
+            y1 = conv2d_forward_raw(xb, pk1.wf, cout, 1, 1, stride, 0, 1)
         us = [y3, y1] + ([xb] if nb == 3 else [])
         n, c, h, w = y3.shape
         m = n * h * w
@@ -423,12 +443,12 @@ class _RepBlockFn(torch.autograd.Function):
         check(L.hb_bn_act_fwd_bf16(up[0], up[1], up[2], nb, ptr(scale), ptr(shift), ptr(None), ptr(out), m, c, act,
                                    _c_float(slope), 0, stream_ptr()), "hb_bn_act_fwd_bf16")
         ctx.save_for_backward(stats, xb, y3, y1, w3, w1)
-        ctx.cfg = (nb, act, slope, training, stride, pk3.wd, pk1.wd, x.shape[1])
+        ctx.cfg = (nb, act, slope, training, stride, None if stem else pk3.wd, None if stem else pk1.wd, x.shape[1], stem)
         return out
 
     @staticmethod
     def backward(ctx, dout: Tensor):
-        nb, act, slope, training, stride, wd3, wd1, cin_x = ctx.cfg
+        nb, act, slope, training, stride, wd3, wd1, cin_x, stem = ctx.cfg
         stats, xb, y3, y1, w3, w1 = ctx.saved_tensors
         mean, rstd, scale, shift = stats[0], stats[1], stats[2], stats[3]
         n, c, ho, wo = y3.shape
@@ -449,45 +469,89 @@ class _RepBlockFn(torch.autograd.Function):
         dx = None
         if need_dx:
             cin_d = wd3.shape[0]
-            if stride == 1:
-                # dXa = dgrad1x1(dY1) + dXid ; dX = dgrad3x3(dY3) + dXa   (cin_d == c for identity blocks)
-                dxa = _empty_cl(n, cin_d, h, w, dev)
-                res = dxid if (dxid is not None and cin_d == c) else None
-                _timed("dgrad", dict(N=n, H=h, W=w, Cin=c, Cout=cin_d, R=1, S=1, stride=1, Ho=h, Wo=w), lambda: check(
-                    L.hb_conv2d_fprop_bf16(ptr(dy1), ptr(wd1), ptr(dxa), ptr(None), ptr(res), n, h, w, c, cin_d, 1, 1, 1, 0, 1,
-                                           ACT_NONE, 0, stream_ptr()), "hb_conv2d_fprop_bf16[dgrad1x1]"))
-                if dxid is not None and res is None:
-                    dxa[:, :c] += dxid
-                src3 = dy3
-            else:
-                lo = _empty_cl(n, cin_d, ho, wo, dev)
-                _timed("dgrad", dict(N=n, H=ho, W=wo, Cin=c, Cout=cin_d, R=1, S=1, stride=1, Ho=ho, Wo=wo), lambda: check(
-                    L.hb_conv2d_fprop_bf16(ptr(dy1), ptr(wd1), ptr(lo), ptr(None), ptr(None), n, ho, wo, c, cin_d, 1, 1, 1, 0,
-                                           1, ACT_NONE, 0, stream_ptr()), "hb_conv2d_fprop_bf16[dgrad1x1]"))
-                dxa = _empty_cl(n, cin_d, h, w, dev)
-                check(L.hb_zero_insert_bf16(ptr(lo), ptr(dxa), n, ho, wo, h, w, cin_d, stride, stream_ptr()),
-                      "hb_zero_insert_bf16")
-                src3 = _empty_cl(n, c, h, w, dev)
-                check(L.hb_zero_insert_bf16(ptr(dy3), ptr(src3), n, ho, wo, h, w, c, stride, stream_ptr()),
-                      "hb_zero_insert_bf16")
             dxp = _empty_cl(n, cin_d, h, w, dev)
-            _timed("dgrad", dict(N=n, H=h, W=w, Cin=c, Cout=cin_d, R=3, S=3, stride=1, Ho=h, Wo=w, dgrad_of_stride=stride),
-                   lambda: check(L.hb_conv2d_fprop_bf16(ptr(src3), ptr(wd3), ptr(dxp), ptr(None), ptr(dxa), n, h, w, c, cin_d,
-                                                        3, 3, 1, 1, 1, ACT_NONE, 0, stream_ptr()),
-                                 "hb_conv2d_fprop_bf16[dgrad3x3]"))
+            fused = False
+            if stride == 1 and wd3.shape[3] == c and (dxid is None or cin_d == c):
+                # one kernel, one accumulator: dgrad3x3(dY3) + dgrad1x1(dY1) + I * dXid
+                eye = _identity_filter(cin_d, c, dev) if dxid is not None else None
+                info = dict(N=n, H=h, W=w, Cin=c, Cout=cin_d, R=3, S=3, stride=1, Ho=h, Wo=w, dgrad_of_stride=1, fused=1)
+                rc = []
+                _timed("dgrad", info, lambda: rc.append(
+                    L.hb_conv3x3_accum_bf16(ptr(dy3), ptr(wd3), ptr(dy1), ptr(wd1), ptr(dxid), ptr(eye),
+                                            2 if dxid is not None else 1, ptr(dxp), n, h, w, c, cin_d, 0, stream_ptr())))
+                if rc[0] == 0:
+                    fused = True
+                elif rc[0] != 801:   # 801 = cudaErrorNotSupported: shape not eligible, use the composition below
+                    check(rc[0], "hb_conv3x3_accum_bf16")
+            if not fused:
+                if stride == 1:
+                    src3 = dy3
+                    dxa = _empty_cl(n, cin_d, h, w, dev)
+                    _timed("dgrad", dict(N=n, H=h, W=w, Cin=c, Cout=cin_d, R=1, S=1, stride=1, Ho=h, Wo=w), lambda: check(
+                        L.hb_conv2d_fprop_bf16(ptr(dy1), ptr(wd1), ptr(dxa), ptr(None), ptr(None), n, h, w, c, cin_d, 1, 1, 1,
+                                               0, 1, ACT_NONE, 0, stream_ptr()), "hb_conv2d_fprop_bf16[dgrad1x1]"))
+                else:
+                    lo = _empty_cl(n, cin_d, ho, wo, dev)
+                    _timed("dgrad", dict(N=n, H=ho, W=wo, Cin=c, Cout=cin_d, R=1, S=1, stride=1, Ho=ho, Wo=wo), lambda: check(
+                        L.hb_conv2d_fprop_bf16(ptr(dy1), ptr(wd1), ptr(lo), ptr(None), ptr(None), n, ho, wo, c, cin_d, 1, 1, 1,
+                                               0, 1, ACT_NONE, 0, stream_ptr()), "hb_conv2d_fprop_bf16[dgrad1x1]"))
+                    dxa = _empty_cl(n, cin_d, h, w, dev)
+                    check(L.hb_zero_insert_bf16(ptr(lo), ptr(dxa), n, ho, wo, h, w, cin_d, stride, stream_ptr()),
+                          "hb_zero_insert_bf16")
+                    src3 = _empty_cl(n, c, h, w, dev)
+                    check(L.hb_zero_insert_bf16(ptr(dy3), ptr(src3), n, ho, wo, h, w, c, stride, stream_ptr()),
+                          "hb_zero_insert_bf16")
+                _timed("dgrad", dict(N=n, H=h, W=w, Cin=c, Cout=cin_d, R=3, S=3, stride=1, Ho=h, Wo=w,
+                                     dgrad_of_stride=stride), lambda: check(
+                    L.hb_conv2d_fprop_bf16(ptr(src3), ptr(wd3), ptr(dxp), ptr(None), ptr(None), n, h, w, c, cin_d, 3, 3, 1, 1,
+                                           1, ACT_NONE, 0, stream_ptr()), "hb_conv2d_fprop_bf16[dgrad3x3]"))
+                dxp.add_(dxa)
+                if dxid is not None:
+                    dxp[:, :c].add_(dxid)
             dx = dxp if cin_d == cin_x else dxp[:, :cin_x]
+        if stem:
+            cin = w3.shape[1]
+            g3 = wgrad_raw(xb, dy3, c, 1, 1, 0).view(c, -1)[:, :9 * cin].view(c, 3, 3, cin).permute(0, 3, 1, 2)
+            g1 = wgrad_raw(xb, dy1, c, 1, 1, 0).view(c, -1)[:, 4 * cin:5 * cin].reshape(c, cin, 1, 1)
+            return (None, None, g3, g1, *[dgb[0][i] for i in range(nb)], *[dgb[1][i] for i in range(nb)])
         grads_w = []
         for wt, dy, k, pad in ((w3, dy3, 3, 1), (w1, dy1, 1, 0)):
             cin = wt.shape[1]
-            dwp = torch.empty((c, k, k, cin_p), device=dev, dtype=torch.float32)
-            _timed("wgrad", dict(N=n, H=h, W=w, Cin=cin_p, Cout=c, R=k, S=k, stride=stride, Ho=ho, Wo=wo), lambda: check(
-                L.hb_conv2d_wgrad_bf16(ptr(xb), ptr(dy), ptr(dwp), n, h, w, cin_p, c, k, k, stride, pad, 1, 0, stream_ptr()),
-                "hb_conv2d_wgrad_bf16"))
+            dwp = wgrad_raw(xb, dy, c, k, stride, pad)
             dw = dwp.permute(0, 3, 1, 2)
             if cin_p != cin:
                 dw = dw[:, :cin].contiguous(memory_format=torch.channels_last)
             grads_w.append(dw)
         return (None, dx, grads_w[0], grads_w[1], *[dgb[0][i] for i in range(nb)], *[dgb[1][i] for i in range(nb)])
+
+
+_eye_cache = {}
+
+
+def _identity_filter(rows: int, cols: int, device) -> Tensor:
+    """[rows, 1, 1, cols] bf16 filter that is the identity on the first min(rows, cols) channels."""
+    key = (rows, cols, str(device))
+    if key not in _eye_cache:
+        _eye_cache[key] = torch.eye(rows, cols, device=device, dtype=torch.bfloat16).reshape(rows, 1, 1, cols).contiguous()
+    return _eye_cache[key]
+
+
+def _stem_im2col(x: Tensor, w3: Tensor, w1: Tensor, stride: int):
+    """x (N, C<=4, H, W) NCHW -> im2col matrix as a channels_last (N, 32, Ho, Wo) bf16 tensor, plus the two branch
+    filters re-expressed over its 32 columns (k = (r*3 + s)*C + c; the 1x1 branch only touches the centre tap)."""
+    from .._lib import dtype_code
+    n, cin, h, w = x.shape
+    cout = w3.shape[0]
+    kp = round_up(9 * cin, 32)
+    ho, wo = conv_out_size(h, 3, stride, 1, 1), conv_out_size(w, 3, stride, 1, 1)
+    col = _empty_cl(n, kp, ho, wo, x.device)
+    check(lib().hb_im2col_smallc_bf16(ptr(x), ptr(col), n, cin, h, w, 3, 3, stride, 1, kp, dtype_code(x), stream_ptr()),
+          "hb_im2col_smallc_bf16")
+    w3p = torch.zeros((cout, 1, 1, kp), device=x.device, dtype=torch.bfloat16)
+    w3p.view(cout, kp)[:, :9 * cin] = w3.detach().permute(0, 2, 3, 1).reshape(cout, 9 * cin)
+    w1p = torch.zeros((cout, 1, 1, kp), device=x.device, dtype=torch.bfloat16)
+    w1p.view(cout, kp)[:, 4 * cin:5 * cin] = w1.detach().reshape(cout, cin)
+    return col, w3p, w1p
 
 
 def repblock(x: Tensor, w3: Tensor, w1: Tensor, bns: Sequence[nn.BatchNorm2d], stride: int, act: int, slope: float,

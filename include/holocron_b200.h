@@ -38,9 +38,19 @@ int hb_nl_relu_bwd_from_out(const void* y, const void* dy, void* dx, size_t n, f
 int hb_conv2d_fprop_bf16(const void* x, const void* w, void* y, const float* bias, const void* residual, int N, int H,
                          int W, int Cin, int Cout, int R, int S, int stride, int pad, int dil, int act, int num_ctas,
                          void* stream);
-/* dw[Cout,R,S,Cin] (fp32, overwritten) = sum over pixels of dy[N,Ho,Wo,Cout] x im2col(x[N,H,W,Cin]) */
-int hb_conv2d_wgrad_bf16(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int R, int S,
-                         int stride, int pad, int dil, int num_ctas, void* stream);
+/* y = conv3x3(x, w; stride 1, pad 1) + sum_{e<nextra} conv1x1(xe_e, we_e), one accumulator (nextra <= 2; all inputs
+ * [N,H,W,Cin] bf16, w [Cout,3,3,Cin], we_e [Cout,1,1,Cin]). Input gradient of a RepVGG block in one kernel
+ * (holocron/models/classification/repvgg.py:71-73). Returns cudaErrorNotSupported (801) when the filter does not fit the
+ * shared-memory-resident scheme (Cin, Cout <= 64 typically) - fall back to separate convolutions then. */
+int hb_conv3x3_accum_bf16(const void* x, const void* w, const void* xe0, const void* we0, const void* xe1, const void* we1,
+                          int nextra, void* y, int N, int H, int W, int Cin, int Cout, int num_ctas, void* stream);
+/* dw[Cout,R,S,Cin] (fp32, overwritten) = sum over pixels of dy[N,Ho,Wo,Cout] x im2col(x[N,H,W,Cin]).
+ * workspace: optional fp32 scratch of hb_conv2d_wgrad_workspace_bytes(...) bytes: the per-pixel-range partial sums are
+ * then reduced in a fixed order (deterministic); with NULL they are accumulated with fp32 atomics. */
+size_t hb_conv2d_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int dil,
+                                       int num_ctas);
+int hb_conv2d_wgrad_bf16(const void* x, const void* dy, float* dw, float* workspace, size_t workspace_bytes, int N, int H,
+                         int W, int Cin, int Cout, int R, int S, int stride, int pad, int dil, int num_ctas, void* stream);
 /* fp32 KRSC master filter -> bf16 KRSC [CoutF][R][S][CinP] (zero-padded rows / channels) and, if wd != NULL, the
  * flipped + transposed bf16 filter [CinD][R][S][CoutP] used by the data-gradient pass */
 int hb_pack_conv_weights(const float* w, void* wf, void* wd, int Cout, int Cin, int R, int S, int CinP, int CinD,
@@ -49,6 +59,11 @@ int hb_pack_conv_weights(const float* w, void* wf, void* wd, int Cout, int Cin, 
 int hb_zero_insert_bf16(const void* x, void* y, int N, int Hi, int Wi, int Ho, int Wo, int C, int sp, void* stream);
 /* NCHW image (dtype code) -> NHWC bf16 with channels zero-padded to CP (CP % 8 == 0) */
 int hb_nchw_to_nhwc_pad_bf16(const void* x, void* y, int N, int C, int H, int W, int CP, int dtype, void* stream);
+
+/* explicit im2col for stems (Cin <= 4): x NCHW (dtype code) -> col [N*Ho*Wo, Kp] bf16 with k = (r*S + s)*C + c, zero
+ * padded to Kp (multiple of 8); the stem then runs as a 1x1 convolution over Kp channels */
+int hb_im2col_smallc_bf16(const void* x, void* col, int N, int C, int H, int W, int R, int S, int stride, int pad, int Kp,
+                          int dtype, void* stream);
 
 /* ---- BatchNorm2d + branch sum + activation, fused: BatchNorm2d/act emitted by conv_sequence
  *      (holocron/models/utils.py:73-78) and the branch sum of RepBlock.forward (repvgg.py:71-73) ------------- */

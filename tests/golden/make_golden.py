@@ -279,7 +279,7 @@ def gen_zoo():
         ps = dict(model.named_parameters())
         return {n: ps[n].grad.clone() for n in names}
 
-    for name in ("darknet53", "cspdarknet53", "rexnet1_0x"):
+    for name in ("darknet53", "cspdarknet53", "rexnet1_0x", "darknet24", "darknet19"):
         torch.manual_seed(0)
         m = getattr(models, name)(num_classes=10).train()
         if name == "rexnet1_0x":

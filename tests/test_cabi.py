@@ -13,7 +13,7 @@ def _header_decls():
     hdr = (ROOT / "include" / "holocron_b200.h").read_text()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
     out = {}
-    for name, args in re.findall(r"int (hb_\w+)\((.*?)\);", hdr, flags=re.S):
+    for name, args in re.findall(r"(?:int|size_t) (hb_\w+)\((.*?)\);", hdr, flags=re.S):
         args = [a.strip() for a in args.replace("\n", " ").split(",")]
         if args == ["void"]:
             args = []

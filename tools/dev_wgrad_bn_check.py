@@ -29,7 +29,9 @@ def run_wgrad(N, H, W, Cin, Cout, k, stride, pad, ctas=0):
     x_nhwc = x.permute(0, 2, 3, 1).contiguous()
     dy_nhwc = dy.permute(0, 2, 3, 1).contiguous()
     dw = torch.full((Cout, k, k, Cin), float("nan"), device="cuda", dtype=torch.float32)
-    rc = L.hb_conv2d_wgrad_bf16(ptr(x_nhwc), ptr(dy_nhwc), ptr(dw), N, H, W, Cin, Cout, k, k, stride, pad, 1, ctas,
+    wsb = L.hb_conv2d_wgrad_workspace_bytes(N, H, W, Cin, Cout, k, k, stride, pad, 1, ctas)
+    ws = torch.empty(max(wsb // 4, 1), device='cuda')
+    rc = L.hb_conv2d_wgrad_bf16(ptr(x_nhwc), ptr(dy_nhwc), ptr(dw), ptr(ws), wsb, N, H, W, Cin, Cout, k, k, stride, pad, 1, ctas,
                                 stream_ptr())
     torch.cuda.synchronize()
     w = torch.zeros(Cout, Cin, k, k, device="cuda", requires_grad=True)
@@ -137,7 +139,11 @@ def main():
     for cfg in [(2, 16, 16, 64, 64, 1, 1, 0), (2, 16, 16, 64, 64, 3, 1, 1), (2, 14, 14, 48, 48, 3, 1, 1),
                 (4, 28, 28, 96, 96, 3, 1, 1), (3, 14, 14, 192, 192, 3, 1, 1), (2, 28, 28, 48, 96, 3, 2, 1),
                 (2, 28, 28, 48, 96, 1, 2, 0), (2, 7, 7, 192, 1280, 3, 1, 1), (8, 7, 7, 1280, 1280, 3, 1, 1),
-                (2, 56, 56, 8, 48, 3, 2, 1), (16, 56, 56, 48, 48, 3, 1, 1), (16, 56, 56, 48, 48, 1, 1, 0)]:
+                (2, 56, 56, 8, 48, 3, 2, 1), (16, 56, 56, 48, 48, 3, 1, 1), (16, 56, 56, 48, 48, 1, 1, 0),
+                (3, 112, 112, 48, 48, 3, 1, 1), (2, 30, 20, 32, 48, 3, 1, 1), (2, 9, 11, 16, 16, 3, 1, 1),
+                (5, 28, 28, 64, 96, 3, 1, 1), (2, 17, 33, 8, 32, 3, 1, 1), (300, 14, 14, 48, 48, 3, 1, 1),
+                (2, 126, 126, 24, 40, 3, 1, 1), (1, 8, 8, 64, 64, 3, 1, 1), (2, 16, 16, 72, 200, 3, 1, 1),
+                (2, 20, 12, 256, 256, 3, 1, 1), (40, 14, 14, 192, 192, 3, 1, 1)]:
         try:
             ok &= run_wgrad(*cfg)
         except Exception as e:  # noqa: BLE001
@@ -163,7 +169,9 @@ def main():
         x = torch.randn(N, H, W, Ci, device="cuda").to(torch.bfloat16)
         dy = torch.randn(N, H, W, Co, device="cuda").to(torch.bfloat16)
         dw = torch.empty(Co, 3, 3, Ci, device="cuda")
-        args = (ptr(x), ptr(dy), ptr(dw), N, H, W, Ci, Co, 3, 3, 1, 1, 1, 0, stream_ptr())
+        wsb = L.hb_conv2d_wgrad_workspace_bytes(N, H, W, Ci, Co, 3, 3, 1, 1, 1, 0)
+        ws = torch.empty(max(wsb // 4, 1), device='cuda')
+        args = (ptr(x), ptr(dy), ptr(dw), ptr(ws), wsb, N, H, W, Ci, Co, 3, 3, 1, 1, 1, 0, stream_ptr())
         for _ in range(3):
             L.hb_conv2d_wgrad_bf16(*args)
         torch.cuda.synchronize()
