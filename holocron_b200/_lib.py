@@ -36,8 +36,12 @@ SIGNATURES = {
     "hb_conv3x3_accum_bf16": "pppppp" + "i" + "p" + "i" * 6 + "p",
     "hb_conv2d_wgrad_bf16": "ppppz" + "i" * 11 + "p",
     "hb_conv2d_wgrad_workspace_bytes": "i" * 11,
+    "hb_repvgg_wgrad_workspace_bytes": "i" * 6,
+    "hb_repvgg_wgrad_bf16": "pppppz" + "i" * 6 + "p",
     "hb_pack_conv_weights": "ppp" + "i" * 8 + "p",
     "hb_zero_insert_bf16": "pp" + "i" * 7 + "p",
+    "hb_conv2d_dgrad_s2_bf16": "ppppp" + "i" * 8 + "p",
+    "hb_pack_dgrad_s2_weights": "pp" + "i" * 4 + "p",
     "hb_nchw_to_nhwc_pad_bf16": "pp" + "i" * 6 + "p",
     "hb_im2col_smallc_bf16": "pp" + "i" * 10 + "p",
     "hb_bn_stats_bf16": "pppiiipp",

@@ -13,6 +13,7 @@
 //   bwd apply  : one pass: du_b = scale_b * (dz - mean(dz) - xhat_b * mean(dz*xhat_b)), dresidual = dz
 // Every thread owns 8 consecutive channels (one 128-bit bf16 vector) of a row; rows are walked with a stride
 // that keeps the thread's channel group fixed, so per-channel parameters live in registers.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
@@ -221,56 +222,131 @@ struct FwdParams {
   float slope;
   int res_after;  // 1: out = act(z) + residual (ResNet-style shortcut after the activation); 0: act(z + residual)
 };
+using RawVec = Vec16<__nv_bfloat16>;
+
+__device__ __forceinline__ void unpack8(const RawVec& v, float* f) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = __bfloat162float(v.v[j]);
+}
+
+// ---- per-thread cp.async ring ---------------------------------------------------------------------
+// Every thread streams ITS OWN 16-byte vectors (one per input tensor and row) global -> shared with cp.async, kDepth rows
+// ahead of the row it is computing on; nothing else reads those slots, so the ring needs no barrier at all. This puts
+// kDepth * (#inputs) * 16 B per thread in flight without holding them in registers: the register-staged version of these
+// kernels had ~36 KB per SM in flight and sat at 2.2 - 3.4 TB/s with long-scoreboard stalls (profiles/r01_bn_ncu.md);
+// HBM needs ~60 KB per SM (44 GB/s per SM x ~1.3 us loaded latency).
+constexpr int kDepth = 3;            // rows in flight per thread
+constexpr int kSlots = kDepth + 1;   // the slot refilled at step k is the one consumed at step k-1
+
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ RawVec lds16(uint32_t saddr) {
+  RawVec r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.raw.x), "=r"(r.raw.y), "=r"(r.raw.z), "=r"(r.raw.w) : "r"(saddr));
+  return r;
+}
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Walks the rows m = m0, m0 + stride, ... < M of one thread. NT input tensors; `src(t)` gives tensor t's base pointer.
+template <int NT>
+struct RowRing {
+  uint32_t base;       // shared address of this thread's slot 0 / tensor 0
+  size_t m0, stride, M;
+  size_t col_off;      // element offset of the thread's 8 channels inside a row
+  int C;
+  const __nv_bfloat16* src[NT > 0 ? NT : 1];
+  // slot s, tensor t of this thread
+  __device__ __forceinline__ uint32_t addr(int s, int t) const { return base + (uint32_t)((s * NT + t) * kThreads * 16); }
+  __device__ __forceinline__ bool valid(size_t k) const { return m0 + k * stride < M; }
+  __device__ __forceinline__ size_t off(size_t k) const { return (m0 + k * stride) * C + col_off; }
+  __device__ __forceinline__ void issue(size_t k) const {
+    if (valid(k)) {
+      const int s = (int)(k % kSlots);
+      const size_t o = off(k);
+#pragma unroll
+      for (int t = 0; t < NT; ++t)
+        if (src[t]) cp_async16(addr(s, t), src[t] + o);
+    }
+    cp_async_commit();   // always: keeps the group count uniform
+  }
+  __device__ __forceinline__ void prologue() const {
+#pragma unroll
+    for (int k = 0; k < kDepth; ++k) issue(k);
+  }
+  // row k has landed
+  __device__ __forceinline__ void wait() const { cp_async_wait<kDepth - 1>(); }
+};
+
+// forward: out = act(sum_b scale_b*u_b + shift_b (+ residual))
+template <int NB>
 __global__ void __launch_bounds__(kThreads) bn_act_fwd_kernel(FwdParams p, Geo g) {
+  extern __shared__ __align__(16) uint8_t ring_smem[];
   const int tx = threadIdx.x % g.cg_t, ty = threadIdx.x / g.cg_t;
   const int cg = blockIdx.y * g.cg_t + tx;
   if (ty >= g.rows_t || cg >= g.cg_total) return;
-  float sc[kMaxBranches][8], sh[8];
+  float sc[NB > 0 ? NB : 1][8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) sh[j] = 0.f;
 #pragma unroll
-  for (int b = 0; b < kMaxBranches; ++b) {
-    if (b < p.br.n) {
+  for (int b = 0; b < NB; ++b) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        sc[b][j] = p.scale[(size_t)b * p.C + cg * 8 + j];
-        sh[j] += p.shift[(size_t)b * p.C + cg * 8 + j];
-      }
+    for (int j = 0; j < 8; ++j) {
+      sc[b][j] = p.scale[(size_t)b * p.C + cg * 8 + j];
+      sh[j] += p.shift[(size_t)b * p.C + cg * 8 + j];
     }
   }
-  const size_t row_stride = (size_t)gridDim.x * g.rows_t;
-  for (size_t m = (size_t)blockIdx.x * g.rows_t + ty; m < (size_t)p.M; m += row_stride) {
-    const size_t off = m * p.C + cg * 8;
+  const bool has_res = p.residual != nullptr;
+  RowRing<NB + 1> ring;
+  ring.base = smem_addr(ring_smem) + threadIdx.x * 16;
+  ring.m0 = (size_t)blockIdx.x * g.rows_t + ty;
+  ring.stride = (size_t)gridDim.x * g.rows_t;
+  ring.M = (size_t)p.M;
+  ring.col_off = (size_t)cg * 8;
+  ring.C = p.C;
+#pragma unroll
+  for (int b = 0; b < NB; ++b) ring.src[b] = p.br.u[b];
+  ring.src[NB] = p.residual;
+  ring.prologue();
+  for (size_t k = 0; ring.valid(k); ++k) {
+    ring.wait();
+    const int s = (int)(k % kSlots);
+    RawVec u[NB > 0 ? NB : 1], r;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) u[b] = lds16(ring.addr(s, b));
+    if (has_res) r = lds16(ring.addr(s, NB));
+    ring.issue(k + kDepth);
     float z[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) z[j] = sh[j];
 #pragma unroll
-    for (int b = 0; b < kMaxBranches; ++b) {
-      if (b < p.br.n) {
-        float u[8];
-        load8(p.br.u[b] + off, u);
+    for (int b = 0; b < NB; ++b) {
+      float f[8];
+      unpack8(u[b], f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) z[j] = fmaf(sc[b][j], u[j], z[j]);
-      }
+      for (int j = 0; j < 8; ++j) z[j] = fmaf(sc[b][j], f[j], z[j]);
     }
-    float r[8];
-    if (p.residual) load8(p.residual + off, r);
-    if (p.residual && !p.res_after) {
+    float rr[8];
+    if (has_res) unpack8(r, rr);
+    if (has_res && !p.res_after) {
       if (p.act == ACT_FRELU) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) z[j] = fmaxf(z[j], r[j]);
+        for (int j = 0; j < 8; ++j) z[j] = fmaxf(z[j], rr[j]);
       } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) z[j] += r[j];
+        for (int j = 0; j < 8; ++j) z[j] += rr[j];
       }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) z[j] = act_fwd(p.act, z[j], p.slope);
-    if (p.residual && p.res_after) {
+    if (has_res && p.res_after) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) z[j] += r[j];
+      for (int j = 0; j < 8; ++j) z[j] += rr[j];
     }
-    store8(p.out + off, z);
+    store8(p.out + ring.off(k), z);
   }
 }
 
@@ -284,7 +360,7 @@ struct BwdParams {
   const float* shift;
   const float* mean;
   const float* rstd;
-  double* sums;        // [1 + B][C]: sum dz, sum dz*xhat_b
+  double* sums;        // [1 + B][C]: sum dz, sum dz*u_b
   __nv_bfloat16* du[kMaxBranches];
   __nv_bfloat16* dres;  // may be null
   int M, C, act;
@@ -293,55 +369,71 @@ struct BwdParams {
   int res_after;
 };
 
-// Per-channel constants of the block's channel slab live in shared memory (keeps the kernels at
-// <= 128 registers so two 256-thread CTAs fit per SM).
+// Per-channel constants of the block's channel slab in shared memory, read as float4 pairs (8 channels per thread).
+//   z    = sum_b scale_b * u_b + shift
+//   du_b = scale_b * (dz - mean(dz) - xhat_b * mean(dz * xhat_b))  =  scale_b * dz + cu_b * u_b + c0_b
+// with cu_b = -scale_b * rstd_b * mdzx_b, c0_b = -scale_b * mdz - cu_b * mean_b and
+// mdzx_b = mean(dz * xhat_b) = rstd_b * (sum(dz * u_b) / M - mean_b * mdz) from the first pass' sums.
 struct SlabConsts {
   float scale[kMaxBranches][256];
-  float mean[kMaxBranches][256];
-  float rstd[kMaxBranches][256];
+  float cu[kMaxBranches][256];
+  float c0[kMaxBranches][256];
   float shift[256];   // sum over branches
-  float mdz[256];     // mean(dz)            (apply pass)
-  float mdzx[kMaxBranches][256];  // mean(dz * xhat_b) (apply pass)
 };
 
 template <int NB>
 __device__ __forceinline__ void load_slab_consts(SlabConsts& k, const BwdParams& p, const Geo& g, bool with_means) {
   const int nch = g.cg_t * 8;
-  const float invM = 1.f / (float)p.M;
+  const double invM = 1.0 / (double)p.M;
   for (int ch = threadIdx.x; ch < nch; ch += kThreads) {
     const int c = blockIdx.y * nch + ch;
+    const bool ok = c < p.C;
     float sh = 0.f;
+    const double mdz = (with_means && p.train && ok) ? p.sums[c] * invM : 0.0;
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
-      const bool ok = c < p.C;
       const size_t o = (size_t)b * p.C + c;
-      k.scale[b][ch] = ok ? p.scale[o] : 0.f;
-      k.mean[b][ch] = ok ? p.mean[o] : 0.f;
-      k.rstd[b][ch] = ok ? p.rstd[o] : 0.f;
+      const float sc = ok ? p.scale[o] : 0.f;
+      k.scale[b][ch] = sc;
       sh += ok ? p.shift[o] : 0.f;
-      k.mdzx[b][ch] = (with_means && p.train && ok) ? (float)(p.sums[(size_t)(1 + b) * p.C + c] * (double)invM) : 0.f;
+      float cu = 0.f, c0 = 0.f;
+      if (with_means && p.train && ok) {
+        const double mean = (double)p.mean[o], rstd = (double)p.rstd[o];
+        const double mdzx = rstd * (p.sums[(size_t)(1 + b) * p.C + c] * invM - mean * mdz);
+        const double cud = -(double)sc * rstd * mdzx;
+        cu = (float)cud;
+        c0 = (float)(-(double)sc * mdz - cud * mean);
+      }
+      k.cu[b][ch] = cu;
+      k.c0[b][ch] = c0;
     }
     k.shift[ch] = sh;
-    k.mdz[ch] = (with_means && p.train && c < p.C) ? (float)(p.sums[c] * (double)invM) : 0.f;
   }
   __syncthreads();
 }
 
+__device__ __forceinline__ void lds8(const float* p, float* f) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
 // dz = d out / d z (z = normalised branch sum [+ residual]); dr = gradient reaching the residual input
 template <int NB>
-__device__ __forceinline__ void recompute_dz(const BwdParams& p, const SlabConsts& k, int ch0, size_t off,
-                                             float (*u)[8], float* dz, float* dr) {
+__device__ __forceinline__ void recompute_dz(const BwdParams& p, const SlabConsts& k, int ch0, const RawVec* uv,
+                                             const RawVec& rv, const RawVec& dv, float (*u)[8], float* dz, float* dr) {
   float z[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) z[j] = k.shift[ch0 + j];
+  lds8(&k.shift[ch0], z);
 #pragma unroll
   for (int b = 0; b < NB; ++b) {
-    load8(p.br.u[b] + off, u[b]);
+    float sc[8];
+    lds8(&k.scale[b][ch0], sc);
+    unpack8(uv[b], u[b]);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) z[j] = fmaf(k.scale[b][ch0 + j], u[b][j], z[j]);
+    for (int j = 0; j < 8; ++j) z[j] = fmaf(sc[j], u[b][j], z[j]);
   }
   float d[8];
-  load8(p.dout + off, d);
+  unpack8(dv, d);
   if (p.residual && p.res_after) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) { dz[j] = d[j] * act_grad(p.act, z[j], p.slope); dr[j] = d[j]; }
@@ -349,7 +441,7 @@ __device__ __forceinline__ void recompute_dz(const BwdParams& p, const SlabConst
   }
   if (p.residual) {
     float r[8];
-    load8(p.residual + off, r);
+    unpack8(rv, r);
     if (p.act == ACT_FRELU) {
       // binary max: the gradient goes to the larger argument, ties are split evenly (PyTorch semantics)
 #pragma unroll
@@ -368,9 +460,27 @@ __device__ __forceinline__ void recompute_dz(const BwdParams& p, const SlabConst
 }
 
 template <int NB>
+__device__ __forceinline__ void init_bwd_ring(RowRing<NB + 2>& ring, const BwdParams& p, const Geo& g, uint8_t* ring_smem,
+                                              int ty, int cg) {
+  ring.base = smem_addr(ring_smem) + threadIdx.x * 16;
+  ring.m0 = (size_t)blockIdx.x * g.rows_t + ty;
+  ring.stride = (size_t)gridDim.x * g.rows_t;
+  ring.M = (size_t)p.M;
+  ring.col_off = (size_t)cg * 8;
+  ring.C = p.C;
+#pragma unroll
+  for (int b = 0; b < NB; ++b) ring.src[b] = p.br.u[b];
+  ring.src[NB] = (p.residual && !p.res_after) ? p.residual : nullptr;   // its value only matters inside act()
+  ring.src[NB + 1] = p.dout;
+}
+
+// pass 1: sums[0][c] += sum_m dz, sums[1+b][c] += sum_m dz * u_b
+template <int NB>
 __global__ void __launch_bounds__(kThreads, 2) bn_act_bwd_reduce_kernel(BwdParams p, Geo g) {
-  __shared__ SlabConsts k;
-  __shared__ float red[kThreads * 8];
+  extern __shared__ __align__(16) uint8_t dyn_smem[];
+  SlabConsts& k = *reinterpret_cast<SlabConsts*>(dyn_smem);
+  float* red = reinterpret_cast<float*>(dyn_smem + sizeof(SlabConsts));   // [kThreads * 8]
+  uint8_t* ring_smem = dyn_smem + sizeof(SlabConsts) + kThreads * 8 * sizeof(float);
   load_slab_consts<NB>(k, p, g, false);
   const int tx = threadIdx.x % g.cg_t, ty = threadIdx.x / g.cg_t;
   const int cg = blockIdx.y * g.cg_t + tx;
@@ -381,17 +491,26 @@ __global__ void __launch_bounds__(kThreads, 2) bn_act_bwd_reduce_kernel(BwdParam
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
   if (active) {
-    const size_t row_stride = (size_t)gridDim.x * g.rows_t;
-    for (size_t m = (size_t)blockIdx.x * g.rows_t + ty; m < (size_t)p.M; m += row_stride) {
+    RowRing<NB + 2> ring;
+    init_bwd_ring<NB>(ring, p, g, ring_smem, ty, cg);
+    ring.prologue();
+    for (size_t kk = 0; ring.valid(kk); ++kk) {
+      ring.wait();
+      const int s = (int)(kk % kSlots);
+      RawVec uv[NB > 0 ? NB : 1], rv, dv;
+#pragma unroll
+      for (int b = 0; b < NB; ++b) uv[b] = lds16(ring.addr(s, b));
+      if (ring.src[NB]) rv = lds16(ring.addr(s, NB));
+      dv = lds16(ring.addr(s, NB + 1));
+      ring.issue(kk + kDepth);
       float u[NB > 0 ? NB : 1][8], dz[8], dr[8];
-      recompute_dz<NB>(p, k, tx * 8, m * p.C + cg * 8, u, dz, dr);
+      recompute_dz<NB>(p, k, tx * 8, uv, rv, dv, u, dz, dr);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[0][j] += dz[j];
 #pragma unroll
       for (int b = 0; b < NB; ++b) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          acc[1 + b][j] += dz[j] * ((u[b][j] - k.mean[b][tx * 8 + j]) * k.rstd[b][tx * 8 + j]);
+        for (int j = 0; j < 8; ++j) acc[1 + b][j] = fmaf(dz[j], u[b][j], acc[1 + b][j]);
       }
     }
   }
@@ -413,29 +532,41 @@ __global__ void __launch_bounds__(kThreads, 2) bn_act_bwd_reduce_kernel(BwdParam
   }
 }
 
+// pass 2: du_b = scale_b * dz + cu_b * u_b + c0_b, dres = dr
 template <int NB>
 __global__ void __launch_bounds__(kThreads, 2) bn_act_bwd_apply_kernel(BwdParams p, Geo g) {
-  __shared__ SlabConsts k;
+  extern __shared__ __align__(16) uint8_t dyn_smem[];
+  SlabConsts& k = *reinterpret_cast<SlabConsts*>(dyn_smem);
+  uint8_t* ring_smem = dyn_smem + sizeof(SlabConsts);
   load_slab_consts<NB>(k, p, g, true);
   const int tx = threadIdx.x % g.cg_t, ty = threadIdx.x / g.cg_t;
   const int cg = blockIdx.y * g.cg_t + tx;
   if (ty >= g.rows_t || cg >= g.cg_total) return;
-  const size_t row_stride = (size_t)gridDim.x * g.rows_t;
-  for (size_t m = (size_t)blockIdx.x * g.rows_t + ty; m < (size_t)p.M; m += row_stride) {
-    const size_t off = m * p.C + cg * 8;
+  RowRing<NB + 2> ring;
+  init_bwd_ring<NB>(ring, p, g, ring_smem, ty, cg);
+  ring.prologue();
+  for (size_t kk = 0; ring.valid(kk); ++kk) {
+    ring.wait();
+    const int s = (int)(kk % kSlots);
+    RawVec uv[NB > 0 ? NB : 1], rv, dv;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) uv[b] = lds16(ring.addr(s, b));
+    if (ring.src[NB]) rv = lds16(ring.addr(s, NB));
+    dv = lds16(ring.addr(s, NB + 1));
+    ring.issue(kk + kDepth);
+    const size_t off = ring.off(kk);
     float u[NB > 0 ? NB : 1][8], dz[8], dr[8];
-    recompute_dz<NB>(p, k, tx * 8, off, u, dz, dr);
+    recompute_dz<NB>(p, k, tx * 8, uv, rv, dv, u, dz, dr);
     if (p.dres) store8(p.dres + off, dr);
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
       if (p.du[b]) {
-        float d[8];
+        float sc[8], cu[8], c0[8], d[8];
+        lds8(&k.scale[b][tx * 8], sc);
+        lds8(&k.cu[b][tx * 8], cu);
+        lds8(&k.c0[b][tx * 8], c0);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int ch = tx * 8 + j;
-          const float xh = (u[b][j] - k.mean[b][ch]) * k.rstd[b][ch];
-          d[j] = k.scale[b][ch] * (dz[j] - k.mdz[ch] - xh * k.mdzx[b][ch]);
-        }
+        for (int j = 0; j < 8; ++j) d[j] = fmaf(sc[j], dz[j], fmaf(cu[j], u[b][j], c0[j]));
         store8(p.du[b] + off, d);
       }
     }
@@ -443,25 +574,57 @@ __global__ void __launch_bounds__(kThreads, 2) bn_act_bwd_apply_kernel(BwdParams
 }
 
 // dgamma_b = sum dz*xhat_b, dbeta_b = sum dz  (fp32 outputs from the fp64 sums)
-__global__ void bn_param_grads_kernel(const double* sums, int B, int C, float* dgamma, float* dbeta) {
+// (sum dz * xhat_b = rstd_b * (sum dz * u_b - mean_b * sum dz), evaluated in fp64)
+__global__ void bn_param_grads_kernel(const double* sums, const float* mean, const float* rstd, int B, int C, float* dgamma,
+                                      float* dbeta) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (c >= C) return;
-  dgamma[(size_t)b * C + c] = (float)sums[(size_t)(1 + b) * C + c];
-  dbeta[(size_t)b * C + c] = (float)sums[c];
+  const size_t o = (size_t)b * C + c;
+  dgamma[o] = (float)((double)rstd[o] * (sums[(size_t)(1 + b) * C + c] - (double)mean[o] * sums[c]));
+  dbeta[o] = (float)sums[c];
 }
 
-inline dim3 make_grid(const Geo& g, int M, int z) {
+// persistent grid: `per_sm` blocks per SM, grid-stride over rows
+inline dim3 make_grid(const Geo& g, int M, int z, int per_sm = 4) {
   const int slabs = (g.cg_total + g.cg_t - 1) / g.cg_t;
   long long row_blocks = ((long long)M + g.rows_t - 1) / g.rows_t;
-  long long cap = (HB_NUM_SMS * 4) / slabs;
+  long long cap = (HB_NUM_SMS * per_sm) / slabs;
   if (cap < 1) cap = 1;
-  // give every block at least ~8 rows per lane when there is enough work
-  long long want = (row_blocks + 7) / 8;
+  long long want = (row_blocks + 3) / 4;   // at least ~4 rows per lane when there is enough work
   if (want < 1) want = 1;
   if (want > cap) want = cap;
   return dim3((unsigned)want, (unsigned)slabs, (unsigned)z);
 }
+
+inline int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+template <typename K>
+inline cudaError_t allow_smem(K kernel, size_t bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+#define HB_BN_LAUNCH(KERNEL, NB, GRID, SMEM, ST, ...)                                        \
+  {                                                                                          \
+    static bool ready = false;                                                               \
+    if (!ready) {                                                                            \
+      if (allow_smem(KERNEL<NB>, 200 * 1024) != cudaSuccess) return (int)cudaErrorInvalidValue; \
+      ready = true;                                                                          \
+    }                                                                                        \
+    KERNEL<NB><<<GRID, kThreads, SMEM, ST>>>(__VA_ARGS__);                                   \
+  }
+#define HB_BN_DISPATCH(KERNEL, B, GRID, SMEM, ST, ...)                                       \
+  switch (B) {                                                                               \
+    case 0: HB_BN_LAUNCH(KERNEL, 0, GRID, SMEM, ST, __VA_ARGS__) break;                      \
+    case 1: HB_BN_LAUNCH(KERNEL, 1, GRID, SMEM, ST, __VA_ARGS__) break;                      \
+    case 2: HB_BN_LAUNCH(KERNEL, 2, GRID, SMEM, ST, __VA_ARGS__) break;                      \
+    default: HB_BN_LAUNCH(KERNEL, 3, GRID, SMEM, ST, __VA_ARGS__) break;                     \
+  }
+
+inline size_t ring_bytes(int tensors) { return (size_t)kSlots * tensors * kThreads * 16; }
 
 }  // namespace
 
@@ -516,7 +679,11 @@ int hb_bn_act_fwd_bf16(const void* u0, const void* u1, const void* u2, int B, co
   p.scale = scale; p.shift = shift; p.residual = (const __nv_bfloat16*)residual; p.out = (__nv_bfloat16*)out;
   p.M = M; p.C = C; p.act = act; p.slope = slope; p.res_after = res_after;
   Geo g = Geo::make(C);
-  bn_act_fwd_kernel<<<make_grid(g, M, 1), kThreads, 0, (cudaStream_t)stream>>>(p, g);
+  static const int per_sm = env_int("HB_BN_CAP_FWD", 3);
+  const dim3 grid = make_grid(g, M, 1, per_sm);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = ring_bytes(B + 1);
+  HB_BN_DISPATCH(bn_act_fwd_kernel, B, grid, smem, st, p, g)
   HB_LAUNCH_CHECK();
   return 0;
 }
@@ -537,27 +704,23 @@ int hb_bn_act_bwd_bf16(const void* dout, const void* u0, const void* u1, const v
   p.M = M; p.C = C; p.act = act; p.slope = slope; p.train = train; p.res_after = res_after;
   Geo g = Geo::make(C);
   cudaStream_t st = (cudaStream_t)stream;
-  const dim3 grid = make_grid(g, M, 1);
+  static const int cap_red = env_int("HB_BN_CAP_RED", 2), cap_app = env_int("HB_BN_CAP_APPLY", 2);
   if (train || (dgamma && dbeta)) {
-    switch (B) {
-      case 0: bn_act_bwd_reduce_kernel<0><<<grid, kThreads, 0, st>>>(p, g); break;
-      case 1: bn_act_bwd_reduce_kernel<1><<<grid, kThreads, 0, st>>>(p, g); break;
-      case 2: bn_act_bwd_reduce_kernel<2><<<grid, kThreads, 0, st>>>(p, g); break;
-      default: bn_act_bwd_reduce_kernel<3><<<grid, kThreads, 0, st>>>(p, g); break;
-    }
+    const dim3 grid = make_grid(g, M, 1, cap_red);
+    const size_t smem = sizeof(SlabConsts) + kThreads * 8 * sizeof(float) + ring_bytes(B + 2);
+    HB_BN_DISPATCH(bn_act_bwd_reduce_kernel, B, grid, smem, st, p, g)
     HB_LAUNCH_CHECK();
     if (dgamma && dbeta && B > 0) {
-      bn_param_grads_kernel<<<dim3((C + 127) / 128, B), 128, 0, st>>>(sums, B, C, dgamma, dbeta);
+      bn_param_grads_kernel<<<dim3((C + 127) / 128, B), 128, 0, st>>>(sums, mean, rstd, B, C, dgamma, dbeta);
       HB_LAUNCH_CHECK();
     }
   }
-  switch (B) {
-    case 0: bn_act_bwd_apply_kernel<0><<<grid, kThreads, 0, st>>>(p, g); break;
-    case 1: bn_act_bwd_apply_kernel<1><<<grid, kThreads, 0, st>>>(p, g); break;
-    case 2: bn_act_bwd_apply_kernel<2><<<grid, kThreads, 0, st>>>(p, g); break;
-    default: bn_act_bwd_apply_kernel<3><<<grid, kThreads, 0, st>>>(p, g); break;
+  {
+    const dim3 grid = make_grid(g, M, 1, cap_app);
+    const size_t smem = sizeof(SlabConsts) + ring_bytes(B + 2);
+    HB_BN_DISPATCH(bn_act_bwd_apply_kernel, B, grid, smem, st, p, g)
+    HB_LAUNCH_CHECK();
   }
-  HB_LAUNCH_CHECK();
   return 0;
 }
 

@@ -40,6 +40,34 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
   }
 }
 
+// Class filters of the stride-2 3x3 pad-1 data gradient (hb_conv2d_dgrad_s2_bf16). Output parity class (a, b) is a
+// correlation over dy with (1+a) x (1+b) taps: out_ab[ci][t][u][co] = w[co][r(a,t)][s(b,u)][ci] with
+// r(0,0) = 1, r(1,0) = 2, r(1,1) = 0 (dy row i+t feeds dx row 2i+a through filter row r = 2i+a+1-2(i+t)).
+// Classes are stored back to back in the order (0,0), (0,1), (1,0), (1,1); rows ci >= Cin / columns co >= Cout are zero.
+__global__ void pack_dgrad_s2_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int Cin,
+                                     int CinD, int CoutP) {
+  const size_t unit = (size_t)CinD * CoutP;
+  const size_t total = 9 * unit;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int a, b; size_t k;
+    if (i < unit) { a = 0; b = 0; k = i; }
+    else if (i < 3 * unit) { a = 0; b = 1; k = i - unit; }
+    else if (i < 5 * unit) { a = 1; b = 0; k = i - 3 * unit; }
+    else { a = 1; b = 1; k = i - 5 * unit; }
+    const int S = 1 + b, R = 1 + a;
+    const int co = k % CoutP;
+    size_t t = k / CoutP;
+    const int u = t % S; t /= S;
+    const int tt = t % R;
+    const int ci = t / R;
+    const int r = a == 0 ? 1 : (tt == 0 ? 2 : 0);
+    const int sx = b == 0 ? 1 : (u == 0 ? 2 : 0);
+    const float v = (co < Cout && ci < Cin) ? w[(((size_t)co * 3 + r) * 3 + sx) * Cin + ci] : 0.f;
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
 // y[n, sp*p, sp*q, :] = x[n, p, q, :]; everything else zero. One thread per 16-byte channel vector of y.
 __global__ void zero_insert_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int Hi,
                                    int Wi, int Ho, int Wo, int C, int sp) {
@@ -166,6 +194,15 @@ int hb_pack_conv_weights(const float* w, void* wf, void* wd, int Cout, int Cin, 
   if (n == 0) return 0;
   pack_weights_kernel<<<stream_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)wf, (__nv_bfloat16*)wd,
                                                                              Cout, Cin, R, S, CinP, CinD, CoutP, CoutF);
+  HB_LAUNCH_CHECK();
+  return 0;
+}
+
+int hb_pack_dgrad_s2_weights(const float* w, void* out, int Cout, int Cin, int CinD, int CoutP, void* stream) {
+  if (CinD < Cin || CoutP < Cout) return (int)cudaErrorInvalidValue;
+  const size_t n = (size_t)9 * CinD * CoutP;
+  if (n == 0) return 0;
+  pack_dgrad_s2_kernel<<<stream_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)out, Cout, Cin, CinD, CoutP);
   HB_LAUNCH_CHECK();
   return 0;
 }

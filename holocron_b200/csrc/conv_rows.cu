@@ -15,7 +15,10 @@
 // (q >= W, rows past the image) are skipped by the epilogue. The filter (all 9 taps x channel blocks) is loaded once
 // per CTA and stays resident.
 //
-// Same warp roles / double-buffered TMEM accumulators / smem-staged coalesced epilogue as conv_fprop.cu.
+// Same warp roles / double-buffered TMEM accumulators / smem-staged coalesced epilogue as conv_fprop.cu, with TWO
+// epilogue warpgroups (warps 2-5 and 6-9) that take alternate sub-tiles: one sub-tile's epilogue is a chain of
+// latencies (tcgen05.ld -> convert -> st.shared -> barrier -> ld.shared -> st.global, ~1.5 us) that four warps cannot
+// overlap with themselves, and on the 48..96-channel layers it - not the MMAs (0.7 us) - set the kernel time.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "tmap.cuh"
@@ -24,7 +27,7 @@ namespace {
 
 using namespace tc;
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;      // TMA warp, MMA warp, 2 x 4 epilogue warps
 constexpr int kTmemCols = 512;
 
 struct RowsParams {
@@ -56,8 +59,9 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* wsm = smem;                                          // [9 + nextra][CB][BN x 128 B]
   uint8_t* stage0 = wsm + (size_t)(9 + p.nextra) * p.CB * p.w_tap_bytes;     // ring of 2 block buffers
-  uint8_t* sout = stage0 + (size_t)2 * p.stage_bytes;           // [128][out_pitch]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sout + (((size_t)128 * p.out_pitch + 15) & ~size_t(15)));
+  uint8_t* sout0 = stage0 + (size_t)2 * p.stage_bytes;          // [2 groups][128][out_pitch]
+  const size_t sout_bytes = ((size_t)128 * p.out_pitch + 15) & ~size_t(15);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sout0 + 2 * sout_bytes);
   uint64_t* full_bar = bars;        // [2]
   uint64_t* empty_bar = bars + 2;   // [2]
   uint64_t* tmem_full = bars + 4;   // [2]
@@ -71,7 +75,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     prefetch_tmap(&tmW);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1);
-      mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8);
     }
     mbar_init(w_bar, 1);
     fence_barrier_init();
@@ -173,20 +177,33 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       }
     }
   } else {
-    // ================= epilogue (warps 2..5) =================
-    const int quarter = warp & 3;
-    const int et = threadIdx.x - 64;
+    // ================= epilogue (warps 2..5 = group 0, warps 6..9 = group 1) =================
+    const int quarter = warp & 3;             // TMEM lane quarter this warp may access
+    const int group = (warp - 2) >> 2;
+    const int et = (threadIdx.x - 64) & 127;  // thread index inside the group
+    uint8_t* sout = sout0 + (size_t)group * sout_bytes;
     const int chunks_per_row = p.BN / 8;
     int it = 0;
+    long long subctr = 0;   // running sub-tile counter: sub-tile j belongs to group j & 1
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int st = it & 1;
       const uint32_t ph = (it >> 1) & 1;
       const int n = tile / p.tiles_per_img, p0 = (tile % p.tiles_per_img) * p.TRO;
       mbar_wait(&tmem_full[st], ph);
       tc_fence_after();
+      // last sub-tile of this tile that is mine (-1: none) -> after it this warp releases the accumulator set
+      int last_mine = -1;
+      for (int sub = 0; sub < p.NSUB; ++sub) if (((subctr + sub) & 1) == group) last_mine = sub;
+      if (last_mine < 0) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[st]);
+      }
       for (int sub = 0; sub < p.NSUB; ++sub) {
+        if (((subctr + sub) & 1) != group) continue;
         const uint32_t taddr = tmem_base + st * 256 + sub * p.BN + ((uint32_t)(quarter * 32) << 16);
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // staging tile free
+        if (group == 0) asm volatile("bar.sync 1, 128;" ::: "memory");   // staging tile free
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
         uint8_t* srow = sout + (size_t)(quarter * 32 + lane) * p.out_pitch;
         for (int c = 0; c < p.BN; c += 32) {
           uint32_t v[32];
@@ -219,12 +236,13 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             }
           }
         }
-        if (sub == p.NSUB - 1) {   // last TMEM read of this accumulator set
+        if (sub == last_mine) {   // this warp's last TMEM read of the accumulator set
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty[st]);
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // staged tile visible
+        if (group == 0) asm volatile("bar.sync 1, 128;" ::: "memory");   // staged tile visible
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
         // copy-out: iterate over the VALID output pixels of this sub-tile (row-major), 16-byte chunks
         const int row0 = p0 + sub * p.SR;
         const int rows_valid = max(0, min(p.SR, min(p.H, p0 + p.TRO) - row0));
@@ -256,6 +274,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           if (q >= p.W) { q -= p.W; ++i; }
         }
       }
+      subctr += p.NSUB;
     }
   }
 
@@ -285,7 +304,7 @@ int hb_conv_rows_try(const void* x, const void* w, void* y, const float* bias, c
   p.w_tap_bytes = ((Cout * 128) + 1023) & ~1023;
   p.out_pitch = Cout * 2 + 16;
   const int w_bytes = (9 + nextra) * p.CB * p.w_tap_bytes;
-  const int out_bytes = ((128 * p.out_pitch) + 1023) & ~1023;
+  const int out_bytes = ((2 * ((128 * p.out_pitch + 15) & ~15)) + 1023) & ~1023;   // one staging tile per epilogue group
   const int budget = 222 * 1024 - w_bytes - out_bytes - 256;
   // largest NSUB whose two ring buffers fit in shared memory and whose accumulators fit half of TMEM
   int nsub = 256 / Cout;

@@ -287,9 +287,9 @@ int plan_wgrad(WgradPlan& plan, int N, int H, int W, int Cin, int Cout, int R, i
 
 // conv_wgrad_rows.cu: row-window variant for stride-1 3x3 layers with few channels
 size_t hb_wgrad_rows_workspace_bytes(int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int dil,
-                                     int num_ctas);
-int hb_wgrad_rows_try(const void* x, const void* dy, float* ws, size_t ws_bytes, int N, int H, int W, int Cin, int Cout,
-                      int num_ctas, cudaStream_t stream, int* grid_out);
+                                     int num_ctas, int has_b1);
+int hb_wgrad_rows_try(const void* x, const void* dy, const void* dy1, float* ws, size_t ws_bytes, int N, int H, int W, int Cin,
+                      int Cout, int num_ctas, cudaStream_t stream, int* slices_out);
 
 extern "C" {
 
@@ -300,7 +300,7 @@ size_t hb_conv2d_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout, i
                                        int num_ctas) {
   WgradPlan plan{};
   if (plan_wgrad(plan, N, H, W, Cin, Cout, R, S, stride, pad, dil, num_ctas)) return 0;
-  const size_t rows = hb_wgrad_rows_workspace_bytes(N, H, W, Cin, Cout, R, S, stride, pad, dil, num_ctas);
+  const size_t rows = hb_wgrad_rows_workspace_bytes(N, H, W, Cin, Cout, R, S, stride, pad, dil, num_ctas, 0);
   return rows > plan.ws_bytes ? rows : plan.ws_bytes;
 }
 
@@ -314,7 +314,7 @@ int hb_conv2d_wgrad_bf16(const void* x, const void* dy, float* dw, float* worksp
   static const bool rows_enabled = getenv("HB_DISABLE_WGRAD_ROWS") == nullptr;
   if (rows_enabled && R == 3 && S == 3 && stride == 1 && pad == 1 && dil == 1 && workspace && hb::aligned16(workspace)) {
     int slices = 0;
-    const int rc = hb_wgrad_rows_try(x, dy, workspace, workspace_bytes, N, H, W, Cin, Cout, num_ctas, st, &slices);
+    const int rc = hb_wgrad_rows_try(x, dy, nullptr, workspace, workspace_bytes, N, H, W, Cin, Cout, num_ctas, st, &slices);
     if (rc == 0) {
       const long long n = (long long)Cout * 9 * Cin;
       wgrad_reduce_kernel<<<(unsigned)((n / 4 + 256) / 256), 256, 0, st>>>(workspace, dw, n, slices);
@@ -369,6 +369,30 @@ int hb_conv2d_wgrad_bf16(const void* x, const void* dy, float* dw, float* worksp
     wgrad_reduce_kernel<<<(unsigned)((n / 4 + 256) / 256), 256, 0, st>>>(workspace, dw, n, k_splits);
     HB_LAUNCH_CHECK();
   }
+  return 0;
+}
+
+// Both weight gradients of a stride-1 RepVGG block (3x3 pad-1 branch and 1x1 branch over the same input,
+// models/classification/repvgg.py:55-73) in one pass over x: dw = [dW3 (Cout,3,3,Cin) | dW1 (Cout,Cin)] fp32, overwritten.
+// workspace: hb_repvgg_wgrad_workspace_bytes(...) bytes; a size of 0 means the shape does not fit the row-window scheme
+// (call hb_conv2d_wgrad_bf16 twice then); hb_repvgg_wgrad_bf16 returns cudaErrorNotSupported in that case.
+size_t hb_repvgg_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout, int num_ctas) {
+  return hb_wgrad_rows_workspace_bytes(N, H, W, Cin, Cout, 3, 3, 1, 1, 1, num_ctas, 1);
+}
+
+int hb_repvgg_wgrad_bf16(const void* x, const void* dy3, const void* dy1, float* dw, float* workspace, size_t workspace_bytes,
+                         int N, int H, int W, int Cin, int Cout, int num_ctas, void* stream) {
+  if (Cin % 8 != 0 || Cout % 8 != 0) return (int)cudaErrorInvalidValue;
+  if (!hb::aligned16(x) || !hb::aligned16(dy3) || !hb::aligned16(dy1) || !hb::aligned16(dw) || !hb::aligned16(workspace))
+    return (int)cudaErrorMisalignedAddress;
+  cudaStream_t st = (cudaStream_t)stream;
+  int slices = 0;
+  const int rc = hb_wgrad_rows_try(x, dy3, dy1, workspace, workspace_bytes, N, H, W, Cin, Cout, num_ctas, st, &slices);
+  if (rc == -1) return (int)cudaErrorNotSupported;
+  if (rc != 0) return (int)cudaErrorLaunchFailure;
+  const long long n = (long long)Cout * 10 * Cin;
+  wgrad_reduce_kernel<<<(unsigned)((n / 4 + 256) / 256), 256, 0, st>>>(workspace, dw, n, slices);
+  HB_LAUNCH_CHECK();
   return 0;
 }
 

@@ -13,6 +13,8 @@
 // writes a partial dW, reduced afterwards in a fixed order (deterministic).
 // More channels than one CTA's TMEM can accumulate (Cin > 64 or Cout > 96) are split into (64-input-channel,
 // <=96-output-channel) groups; the CTAs of a group share the tiles between them, each group owns a disjoint part of dW.
+// RepVGG blocks: the 1x1 branch's weight gradient dW1[co, ci] = sum dY1[n,p,q,co] * X[n,p,q,ci] reads the same X rows
+// through the centre-tap window, so it rides along as a sixth accumulator slot fed by a second dY buffer (has_b1).
 // The generic kernel (conv_wgrad.cu) re-reads X nine times from L2 (one im2col load per tap): 0.94 ms for the 48-channel
 // 112^2 layer of RepVGG-A0 at batch 256 against an HBM time of 0.1 ms.
 #include "common.cuh"
@@ -35,12 +37,15 @@ struct WRowsParams {
   int ncols;             // TMEM columns per tap slot (= co_group)
   int tiles_per_img, num_tiles;
   int xbuf_bytes, ybuf_chunk_bytes, stage_bytes;
-  float* ws;             // [gridDim.x][Cout*9*Cin] partial sums
-  long long dw_elems;
+  int has_b1;            // 1: also accumulate the 1x1 branch (slot 5, second dY source)
+  float* ws;             // [members][dw_elems (+ Cout*Cin)] partial sums
+  long long dw_elems;    // Cout*9*Cin
+  long long slice_elems; // dw_elems + (has_b1 ? Cout*Cin : 0)
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
-conv_wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY, const WRowsParams p) {
+conv_wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                       const __grid_constant__ CUtensorMap tmDY1, const WRowsParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)2 * p.stage_bytes);
@@ -72,7 +77,8 @@ conv_wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
 
   if (warp == 0) {
     if (lane == 0) {
-      const uint32_t tx = (uint32_t)((p.TRO + 2) * p.Wp * 128 + p.co_chunks * p.TRO * p.Wp * 128);
+      const uint32_t tx = (uint32_t)((p.TRO + 2) * p.Wp * 128 + (1 + p.has_b1) * p.co_chunks * p.TRO * p.Wp * 128);
+      if (p.has_b1) prefetch_tmap(&tmDY1);
       int it = 0;
       for (int tile = member; tile < p.num_tiles; tile += members, ++it) {
         const int st = it & 1;
@@ -89,6 +95,13 @@ conv_wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
               "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
               ::"r"(smem_u32(sx + p.xbuf_bytes + c * p.ybuf_chunk_bytes)), "l"(reinterpret_cast<uint64_t>(&tmDY)),
                 "r"(smem_u32(&full_bar[st])), "r"(co0 + c * 64), "r"(0), "r"(p0), "r"(n) : "memory");
+        if (p.has_b1)
+          for (int c = 0; c < p.co_chunks; ++c)
+            asm volatile(
+                "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                ::"r"(smem_u32(sx + p.xbuf_bytes + (p.co_chunks + c) * p.ybuf_chunk_bytes)),
+                  "l"(reinterpret_cast<uint64_t>(&tmDY1)), "r"(smem_u32(&full_bar[st])), "r"(co0 + c * 64), "r"(0), "r"(p0), "r"(n)
+                : "memory");
       }
     }
   } else if (warp == 1) {
@@ -114,6 +127,14 @@ conv_wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
           for (int k = 0; k < p.KS; ++k)
             umma_f16_lh(d_tmem, a_lo0 + k * (2048 >> 4), dhi, b_lo0 + k * (2048 >> 4), dhi, idesc, (any || k > 0) ? 1u : 0u);
         }
+        if (p.has_b1) {
+          // 1x1 branch: centre-tap window of X (second M chunk = don't care) against the dY1 buffer
+          const uint32_t a_lo0 = desc_lo(sx + (p.Wp + 1) * 128, 0);
+          const uint32_t b1_lo0 = desc_lo(sy + p.co_chunks * p.ybuf_chunk_bytes, lbo_b);
+          const uint32_t d_tmem = tmem_base + 5 * p.ncols;
+          for (int k = 0; k < p.KS; ++k)
+            umma_f16_lh(d_tmem, a_lo0 + k * (2048 >> 4), dhi, b1_lo0 + k * (2048 >> 4), dhi, idesc, (any || k > 0) ? 1u : 0u);
+        }
         any = true;
         umma_commit(&empty_bar[st]);
       }
@@ -125,7 +146,7 @@ conv_wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     mbar_wait(done_bar, 0);
     tc_fence_after();
     const bool has_work = member < p.num_tiles;
-    float* out = p.ws + (size_t)member * p.dw_elems;
+    float* out = p.ws + (size_t)member * p.slice_elems;
     const int ci = ci0 + (quarter & 1) * 32 + lane;     // lanes 0-63: first tap of the slot, 64-127: second tap
     const int which = quarter >> 1;
     for (int slot = 0; slot < 5; ++slot) {
@@ -144,6 +165,21 @@ conv_wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         }
       }
     }
+    if (p.has_b1) {
+      float* out1 = out + p.dw_elems;   // [Cout][Cin]
+      for (int c = 0; c < p.ncols; c += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(tmem_base + 5 * p.ncols + c + ((uint32_t)(quarter * 32) << 16), v);
+        tmem_ld_wait();
+        if (which == 0 && ci < p.Cin) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int co = co0 + c + j;
+            if (c + j < p.co_group && co < p.Cout) out1[(size_t)co * p.Cin + ci] = has_work ? __uint_as_float(v[j]) : 0.f;
+          }
+        }
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -152,18 +188,21 @@ conv_wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
 
 struct WRowsPlan { WRowsParams p; int grid, members; size_t smem; };
 
-bool plan_wrows(WRowsPlan& pl, int N, int H, int W, int Cin, int Cout, int num_ctas) {
+bool plan_wrows(WRowsPlan& pl, int N, int H, int W, int Cin, int Cout, int num_ctas, int has_b1 = 0) {
   if (Cin % 8 != 0 || Cout % 8 != 0 || W < 8 || W + 2 > 128) return false;
   WRowsParams& p = pl.p;
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   p.Wp = W + 2;
   p.n_cig = (Cin + 63) / 64;
-  p.n_cog = (Cout + 95) / 96;
+  p.has_b1 = has_b1;
+  const int slots = 5 + has_b1;
+  const int max_group = ((kTmemCols / slots) / 16) * 16;   // 96 (5 slots) or 80 (6 slots)
+  p.n_cog = (Cout + max_group - 1) / max_group;
   p.co_group = (((Cout + p.n_cog - 1) / p.n_cog) + 15) & ~15;
   p.ngroups = p.n_cig * p.n_cog;
   p.co_chunks = (p.co_group + 63) / 64;
   p.ncols = p.co_group;
-  if (5 * p.ncols > kTmemCols || p.ngroups > 16) return false;
+  if (slots * p.ncols > kTmemCols || p.ngroups > 16) return false;
   int tro = H < 16 ? H : 16;
   for (; tro >= 1; --tro) {
     const int ks = (tro * p.Wp + 15) / 16;
@@ -171,9 +210,9 @@ bool plan_wrows(WRowsPlan& pl, int N, int H, int W, int Cin, int Cout, int num_c
     const int xrows = 2 * p.Wp + 2 + ks * 16;
     const int xbytes = ((xrows > (tro + 2) * p.Wp ? xrows : (tro + 2) * p.Wp) * 128 + 1023) & ~1023;
     const int ybytes = ((ks * 16) * 128 + 1023) & ~1023;
-    if (2 * (xbytes + p.co_chunks * ybytes) <= 220 * 1024) {
+    if (2 * (xbytes + (1 + has_b1) * p.co_chunks * ybytes) <= 220 * 1024) {
       p.TRO = tro; p.KS = ks; p.xbuf_bytes = xbytes; p.ybuf_chunk_bytes = ybytes;
-      p.stage_bytes = xbytes + p.co_chunks * ybytes;
+      p.stage_bytes = xbytes + (1 + has_b1) * p.co_chunks * ybytes;
       break;
     }
   }
@@ -181,6 +220,7 @@ bool plan_wrows(WRowsPlan& pl, int N, int H, int W, int Cin, int Cout, int num_c
   p.tiles_per_img = (H + p.TRO - 1) / p.TRO;
   p.num_tiles = N * p.tiles_per_img;
   p.dw_elems = (long long)Cout * 9 * Cin;
+  p.slice_elems = p.dw_elems + (has_b1 ? (long long)Cout * Cin : 0);
   const int ctas = num_ctas > 0 ? num_ctas : HB_NUM_SMS;
   int members = ctas / p.ngroups;
   if (members > p.num_tiles) members = p.num_tiles;
@@ -195,22 +235,24 @@ bool plan_wrows(WRowsPlan& pl, int N, int H, int W, int Cin, int Cout, int num_c
 
 // workspace bytes wanted by the row-window variant (0 = shape not eligible)
 size_t hb_wgrad_rows_workspace_bytes(int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int dil,
-                                     int num_ctas) {
+                                     int num_ctas, int has_b1) {
   if (R != 3 || S != 3 || stride != 1 || pad != 1 || dil != 1) return 0;
   WRowsPlan pl{};
-  if (!plan_wrows(pl, N, H, W, Cin, Cout, num_ctas)) return 0;
-  return (size_t)pl.members * pl.p.dw_elems * sizeof(float);
+  if (!plan_wrows(pl, N, H, W, Cin, Cout, num_ctas, has_b1)) return 0;
+  return (size_t)pl.members * pl.p.slice_elems * sizeof(float);
 }
 
-// launches the partial-sum kernel; *grid_out = number of partial slices written to ws. Returns 0 / -1 (not eligible) / -2.
-int hb_wgrad_rows_try(const void* x, const void* dy, float* ws, size_t ws_bytes, int N, int H, int W, int Cin, int Cout,
-                      int num_ctas, cudaStream_t stream, int* grid_out) {
+// launches the partial-sum kernel; *slices_out = number of partial slices written to ws (each slice_elems floats:
+// dW3 [Cout,3,3,Cin] then, with dy1, dW1 [Cout,Cin]). Returns 0 / -1 (not eligible) / -2 (launch failure).
+int hb_wgrad_rows_try(const void* x, const void* dy, const void* dy1, float* ws, size_t ws_bytes, int N, int H, int W, int Cin,
+                      int Cout, int num_ctas, cudaStream_t stream, int* slices_out) {
   WRowsPlan pl{};
-  if (!plan_wrows(pl, N, H, W, Cin, Cout, num_ctas)) return -1;
+  const int has_b1 = dy1 != nullptr;
+  if (!plan_wrows(pl, N, H, W, Cin, Cout, num_ctas, has_b1)) return -1;
   WRowsParams& p = pl.p;
-  if (!ws || ws_bytes < (size_t)pl.members * p.dw_elems * sizeof(float)) return -1;
+  if (!ws || ws_bytes < (size_t)pl.members * p.slice_elems * sizeof(float)) return -1;
   p.ws = ws;
-  CUtensorMap tmX, tmDY;
+  CUtensorMap tmX, tmDY, tmDY1;
   {
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
     uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
@@ -220,6 +262,7 @@ int hb_wgrad_rows_try(const void* x, const void* dy, float* ws, size_t ws_bytes,
     uint64_t ystrides[3] = {(uint64_t)Cout * 2, (uint64_t)W * Cout * 2, (uint64_t)H * W * Cout * 2};
     uint32_t ybox[4] = {64, (uint32_t)p.Wp, (uint32_t)p.TRO, 1};
     if (tmap::encode_tiled_bf16(&tmDY, dy, 4, ydims, ystrides, ybox, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
+    if (tmap::encode_tiled_bf16(&tmDY1, has_b1 ? dy1 : dy, 4, ydims, ystrides, ybox, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
   }
   static bool attr_set = false;
   if (!attr_set) {
@@ -228,8 +271,8 @@ int hb_wgrad_rows_try(const void* x, const void* dy, float* ws, size_t ws_bytes,
     attr_set = true;
   }
   if (pl.smem > 227 * 1024) return -1;
-  conv_wgrad_rows_kernel<<<pl.grid, kThreads, pl.smem, stream>>>(tmX, tmDY, p);
+  conv_wgrad_rows_kernel<<<pl.grid, kThreads, pl.smem, stream>>>(tmX, tmDY, tmDY1, p);
   g_hb_launches.fetch_add(1, std::memory_order_relaxed);
-  *grid_out = pl.members;
+  *slices_out = pl.members;
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }

@@ -54,13 +54,16 @@ inline int encode_tiled_bf16(CUtensorMap* out, const void* base, int rank, const
 //   traversal stride = conv stride. channels/pixels per load = the smem tile (64 x 128 here).
 inline int encode_im2col_bf16(CUtensorMap* out, const void* base, int N, int H, int W, int C, int pad_h, int pad_w,
                               int kh, int kw, int dil, int stride, uint32_t channels_per_pixel,
-                              uint32_t pixels_per_column, CUtensorMapSwizzle swz) {
+                              uint32_t pixels_per_column, CUtensorMapSwizzle swz, int pad_after_h = -1,
+                              int pad_after_w = -1) {
   const Api& a = api();
+  if (pad_after_h < 0) pad_after_h = pad_h;   // symmetric padding unless stated
+  if (pad_after_w < 0) pad_after_w = pad_w;
   if (!a.ok) return (int)cudaErrorNotSupported;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
   int lower[2] = {-pad_w, -pad_h};
-  int upper[2] = {pad_w - (kw - 1) * dil, pad_h - (kh - 1) * dil};
+  int upper[2] = {pad_after_w - (kw - 1) * dil, pad_after_h - (kh - 1) * dil};
   cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   CUresult r = a.im2col(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, lower, upper,
                         channels_per_pixel, pixels_per_column, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,

@@ -9,6 +9,7 @@ Reference call sites being replaced: ``nn.Conv2d`` / ``nn.BatchNorm2d`` / activa
 (holocron/models/classification/repvgg.py:71-73).
 """
 import ctypes
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -68,7 +69,8 @@ def to_channels_last_bf16(x: Tensor, c_pad: Optional[int] = None) -> Tensor:
     cp = c if c_pad is None else c_pad
     if cp == c and x.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last):
         return x
-    if x.is_contiguous() and x.dtype in (torch.float32, torch.bfloat16, torch.float16) and (cp != c or c < 8):
+    no_grad = not (x.requires_grad and torch.is_grad_enabled())   # the raw kernel is invisible to autograd
+    if no_grad and x.is_contiguous() and x.dtype in (torch.float32, torch.bfloat16, torch.float16) and (cp != c or c < 8):
         from .._lib import dtype_code
         out = torch.empty((n, cp, h, w), device=x.device, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
         check(lib().hb_nchw_to_nhwc_pad_bf16(ptr(x), ptr(out), n, c, h, w, cp, dtype_code(x), stream_ptr()),
@@ -123,6 +125,41 @@ def pack_filter(weight: Tensor, need_dgrad: bool, cin_p: Optional[int] = None) -
                                      ent.cout_p, stream_ptr()), "hb_pack_conv_weights")
     _pack_cache[id(weight)] = ent
     return ent
+
+
+_s2_cache = {}
+
+
+def dgrad_s2_filters(weight: Tensor, cin_d: int, cout_p: int) -> Tensor:
+    """bf16 class filters of the stride-2 3x3 data gradient (hb_pack_dgrad_s2_weights), cached per parameter version."""
+    key = (weight.data_ptr(), weight._version, tuple(weight.stride()), cin_d, cout_p)
+    ent = _s2_cache.get(id(weight))
+    if ent is not None and ent[0] == key:
+        return ent[1]
+    cout, cin = weight.shape[0], weight.shape[1]
+    w_krsc = weight.detach().float().permute(0, 2, 3, 1)
+    if not w_krsc.is_contiguous():
+        w_krsc = w_krsc.contiguous()
+    out = torch.empty(9 * cin_d * cout_p, device=weight.device, dtype=torch.bfloat16)
+    check(lib().hb_pack_dgrad_s2_weights(ptr(w_krsc), ptr(out), cout, cin, cin_d, cout_p, stream_ptr()),
+          "hb_pack_dgrad_s2_weights")
+    _s2_cache[id(weight)] = (key, out)
+    return out
+
+
+def dgrad_s2_raw(dyb: Tensor, weight: Tensor, cin_d: int, h: int, w: int, dy1: Optional[Tensor] = None,
+                 wd1: Optional[Tensor] = None) -> Tensor:
+    """dx [N, cin_d, h, w] of a stride-2 3x3 pad-1 convolution from dy [N, cout_p, ho, wo] (+ the 1x1 stride-2 branch
+    of a RepVGG block) by parity classes - no zero insertion."""
+    n, cout_p, ho, wo = dyb.shape
+    dxp = _empty_cl(n, cin_d, h, w, dyb.device)
+    wcls = dgrad_s2_filters(weight, cin_d, cout_p)
+    info = dict(N=n, H=h, W=w, Cin=cout_p, Cout=cin_d, R=3, S=3, stride=1, Ho=h, Wo=w, dgrad_of_stride=2, parity=1,
+                fused=int(dy1 is not None))
+    _timed("dgrad", info, lambda: check(
+        lib().hb_conv2d_dgrad_s2_bf16(ptr(dyb), ptr(wcls), ptr(dy1), ptr(wd1), ptr(dxp), n, h, w, ho, wo, cout_p, cin_d, 0,
+                                      stream_ptr()), "hb_conv2d_dgrad_s2_bf16"))
+    return dxp
 
 
 def _pad_vec(v: Optional[Tensor], n: int) -> Optional[Tensor]:
@@ -188,16 +225,20 @@ class _Conv2dFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             if dil != 1:
                 raise NotImplementedError("dgrad with dilation > 1")
-            src = dyb
-            if stride > 1:
-                src = _empty_cl(n, cout_p, h, w, dyb.device)
-                check(L.hb_zero_insert_bf16(ptr(dyb), ptr(src), n, ho, wo, h, w, cout_p, stride, stream_ptr()),
-                      "hb_zero_insert_bf16")
-            dxp = _empty_cl(n, cin_d, h, w, dyb.device)
-            info = dict(N=n, H=h, W=w, Cin=cout_p, Cout=cin_d, R=r, S=s, stride=1, Ho=h, Wo=w, dgrad_of_stride=stride)
-            _timed("dgrad", info, lambda: check(
-                L.hb_conv2d_fprop_bf16(ptr(src), ptr(wd), ptr(dxp), ptr(None), ptr(None), n, h, w, cout_p, cin_d, r, s, 1,
-                                       (r - 1) * dil - pad, 1, ACT_NONE, 0, stream_ptr()), "hb_conv2d_fprop_bf16[dgrad]"))
+            if stride == 2 and r == 3 and s == 3 and pad == 1 and h >= 2 and w >= 2:
+                dxp = dgrad_s2_raw(dyb, weight, cin_d, h, w)
+            else:
+                src = dyb
+                if stride > 1:
+                    src = _empty_cl(n, cout_p, h, w, dyb.device)
+                    check(L.hb_zero_insert_bf16(ptr(dyb), ptr(src), n, ho, wo, h, w, cout_p, stride, stream_ptr()),
+                          "hb_zero_insert_bf16")
+                dxp = _empty_cl(n, cin_d, h, w, dyb.device)
+                info = dict(N=n, H=h, W=w, Cin=cout_p, Cout=cin_d, R=r, S=s, stride=1, Ho=h, Wo=w, dgrad_of_stride=stride)
+                _timed("dgrad", info, lambda: check(
+                    L.hb_conv2d_fprop_bf16(ptr(src), ptr(wd), ptr(dxp), ptr(None), ptr(None), n, h, w, cout_p, cin_d, r, s,
+                                           1, (r - 1) * dil - pad, 1, ACT_NONE, 0, stream_ptr()),
+                    "hb_conv2d_fprop_bf16[dgrad]"))
             dx = dxp if cin_d == cin_x else dxp[:, :cin_x]
         if ctx.needs_input_grad[1]:
             if r != s:
@@ -469,8 +510,13 @@ class _RepBlockFn(torch.autograd.Function):
         dx = None
         if need_dx:
             cin_d = wd3.shape[0]
-            dxp = _empty_cl(n, cin_d, h, w, dev)
             fused = False
+            if stride == 2 and h >= 2 and w >= 2 and wd3.shape[3] == c:
+                # parity-class data gradient of the stride-2 3x3 branch; the 1x1 branch lands in class (0, 0)
+                dxp = dgrad_s2_raw(dy3, w3, cin_d, h, w, dy1, wd1)
+                fused = True
+            else:
+                dxp = _empty_cl(n, cin_d, h, w, dev)
             if stride == 1 and wd3.shape[3] == c and (dxid is None or cin_d == c):
                 # one kernel, one accumulator: dgrad3x3(dY3) + dgrad1x1(dY1) + I * dXid
                 eye = _identity_filter(cin_d, c, dev) if dxid is not None else None
@@ -515,9 +561,25 @@ class _RepBlockFn(torch.autograd.Function):
             g1 = wgrad_raw(xb, dy1, c, 1, 1, 0).view(c, -1)[:, 4 * cin:5 * cin].reshape(c, cin, 1, 1)
             return (None, None, g3, g1, *[dgb[0][i] for i in range(nb)], *[dgb[1][i] for i in range(nb)])
         grads_w = []
-        for wt, dy, k, pad in ((w3, dy3, 3, 1), (w1, dy1, 1, 0)):
+        fused_w = None
+        if stride == 1 and not os.environ.get("HB_DISABLE_FUSED_WGRAD"):
+            # both branches' weight gradients in one pass over x (the 1x1 branch = centre-tap window of the same rows)
+            ws_bytes = L.hb_repvgg_wgrad_workspace_bytes(n, h, w, cin_p, c, 0)
+            if ws_bytes:
+                dwcat = torch.empty(c * 10 * cin_p, device=dev, dtype=torch.float32)
+                ws = torch.empty(ws_bytes // 4, device=dev, dtype=torch.float32)
+                rc = []
+                info = dict(N=n, H=h, W=w, Cin=cin_p, Cout=c, R=3, S=3, stride=1, Ho=ho, Wo=wo, fused=1)
+                _timed("wgrad", info, lambda: rc.append(
+                    L.hb_repvgg_wgrad_bf16(ptr(xb), ptr(dy3), ptr(dy1), ptr(dwcat), ptr(ws), ws_bytes, n, h, w, cin_p, c, 0,
+                                           stream_ptr())))
+                if rc[0] == 0:
+                    fused_w = (dwcat[:c * 9 * cin_p].view(c, 3, 3, cin_p), dwcat[c * 9 * cin_p:].view(c, 1, 1, cin_p))
+                elif rc[0] != 801:
+                    check(rc[0], "hb_repvgg_wgrad_bf16")
+        for i, (wt, dy, k, pad) in enumerate(((w3, dy3, 3, 1), (w1, dy1, 1, 0))):
             cin = wt.shape[1]
-            dwp = wgrad_raw(xb, dy, c, k, stride, pad)
+            dwp = fused_w[i] if fused_w is not None else wgrad_raw(xb, dy, c, k, stride, pad)
             dw = dwp.permute(0, 3, 1, 2)
             if cin_p != cin:
                 dw = dw[:, :cin].contiguous(memory_format=torch.channels_last)

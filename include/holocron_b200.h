@@ -51,10 +51,27 @@ size_t hb_conv2d_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout, i
                                        int num_ctas);
 int hb_conv2d_wgrad_bf16(const void* x, const void* dy, float* dw, float* workspace, size_t workspace_bytes, int N, int H,
                          int W, int Cin, int Cout, int R, int S, int stride, int pad, int dil, int num_ctas, void* stream);
+/* Both weight gradients of a stride-1 RepVGG block in ONE pass over x (the 1x1 branch reads x through the centre-tap
+ * window of the rows the 3x3 branch already holds in shared memory; holocron/models/classification/repvgg.py:55-73):
+ * dw = [dW3 (Cout,3,3,Cin) | dW1 (Cout,Cin)] fp32, overwritten. hb_repvgg_wgrad_workspace_bytes == 0 / return code
+ * cudaErrorNotSupported (801): shape outside the row-window scheme, use hb_conv2d_wgrad_bf16 per branch. */
+size_t hb_repvgg_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout, int num_ctas);
+int hb_repvgg_wgrad_bf16(const void* x, const void* dy3, const void* dy1, float* dw, float* workspace, size_t workspace_bytes,
+                         int N, int H, int W, int Cin, int Cout, int num_ctas, void* stream);
 /* fp32 KRSC master filter -> bf16 KRSC [CoutF][R][S][CinP] (zero-padded rows / channels) and, if wd != NULL, the
  * flipped + transposed bf16 filter [CinD][R][S][CoutP] used by the data-gradient pass */
 int hb_pack_conv_weights(const float* w, void* wf, void* wd, int Cout, int Cin, int R, int S, int CinP, int CinD,
                          int CoutP, int CoutF, void* stream);
+/* Data gradient of a stride-2 3x3 pad-1 convolution (the backward of the stride-2 nn.Conv2d at the head of every
+ * RepVGG / Darknet / ReXNet stage, holocron/models/classification/repvgg.py:55-73, utils.py:28-86) without zero insertion:
+ * the 4 parity classes of dx [N,H,W,Cd] are 1/2/2/4-tap correlations over dy [N,Ho,Wo,C] written to their sub-grids.
+ * wcls: class filters from hb_pack_dgrad_s2_weights. dy1/wd1 (may be NULL): output gradient and [Cd,1,1,C] filter of a
+ * parallel 1x1 stride-2 branch, accumulated into class (0,0). Ho = (H-1)/2+1, Wo = (W-1)/2+1. */
+int hb_conv2d_dgrad_s2_bf16(const void* dy, const void* wcls, const void* dy1, const void* wd1, void* dx, int N, int H, int W,
+                            int Ho, int Wo, int C, int Cd, int num_ctas, void* stream);
+/* fp32 KRSC master filter [Cout,3,3,Cin] -> the four bf16 class filters [CinD][1+a][1+b][CoutP], (a,b) = (0,0), (0,1),
+ * (1,0), (1,1), stored back to back (9*CinD*CoutP elements) */
+int hb_pack_dgrad_s2_weights(const float* w, void* out, int Cout, int Cin, int CinD, int CoutP, void* stream);
 /* y[N,Ho,Wo,C] = zeros, y[n, sp*p, sp*q, :] = x[n,p,q,:]  (input of a stride-sp transposed convolution) */
 int hb_zero_insert_bf16(const void* x, void* y, int N, int Hi, int Wi, int Ho, int Wo, int C, int sp, void* stream);
 /* NCHW image (dtype code) -> NHWC bf16 with channels zero-padded to CP (CP % 8 == 0) */

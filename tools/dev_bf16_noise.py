@@ -45,6 +45,27 @@ def rel(a, b):
 
 
 golden = torch.load("tests/golden/zoo.pt")
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+# conditioning sweep: distance of both bf16 executions to the eager fp32 run on random inputs of several sizes
+for name in names:
+    for (b, sz) in [(2, 64), (8, 64), (4, 128), (16, 64), (8, 128)]:
+        torch.manual_seed(5)
+        x = torch.rand(b, 3, sz, sz, device="cuda")
+        outs = {}
+        for mode in ("eager fp32", "eager autocast", "fused"):
+            torch.manual_seed(0)
+            m = getattr(hb.models, name)(num_classes=10).cuda().train()
+            set_unit(orig_unit if mode == "fused" else eager_unit)
+            with torch.no_grad():
+                if mode == "eager autocast":
+                    with torch.autocast("cuda", dtype=torch.bfloat16):
+                        outs[mode] = m(x).float()
+                else:
+                    outs[mode] = m(x).float()
+        set_unit(orig_unit)
+        print(f"{name} b{b} {sz}x{sz}: autocast {rel(outs['eager autocast'], outs['eager fp32']):.4f} "
+              f"fused {rel(outs['fused'], outs['eager fp32']):.4f}", flush=True)
 for name in names:
     g = golden[name]
     x = g["x"].cuda()

@@ -68,6 +68,60 @@ def run_dgrad(N, H, W, Cin, Cout, k, stride, pad):
     return check(f"dgrad rc={rc} N{N} {H}x{W} C{Cin}->{Cout} k{k} s{stride} p{pad}", dx, gx.permute(0, 2, 3, 1), 2e-2)
 
 
+def run_repvgg_wgrad(N, H, W, Cin, Cout):
+    torch.manual_seed(6)
+    x = torch.randn(N, Cin, H, W, device="cuda").to(torch.bfloat16)
+    dy3 = torch.randn(N, Cout, H, W, device="cuda").to(torch.bfloat16)
+    dy1 = torch.randn(N, Cout, H, W, device="cuda").to(torch.bfloat16)
+    xn, d3, d1 = (t.permute(0, 2, 3, 1).contiguous() for t in (x, dy3, dy1))
+    wsb = L.hb_repvgg_wgrad_workspace_bytes(N, H, W, Cin, Cout, 0)
+    if wsb == 0:
+        print(f"--  repvgg_wgrad N{N} {H}x{W} C{Cin}->{Cout}: not eligible")
+        return True
+    ws = torch.empty(wsb // 4, device="cuda")
+    dw = torch.full((Cout * 10 * Cin,), float("nan"), device="cuda")
+    rc = L.hb_repvgg_wgrad_bf16(ptr(xn), ptr(d3), ptr(d1), ptr(dw), ptr(ws), wsb, N, H, W, Cin, Cout, 0, stream_ptr())
+    torch.cuda.synchronize()
+    w3 = torch.zeros(Cout, Cin, 3, 3, device="cuda", requires_grad=True)
+    w1 = torch.zeros(Cout, Cin, 1, 1, device="cuda", requires_grad=True)
+    tot = (F.conv2d(x.float(), w3, padding=1) * dy3.float()).sum() + (F.conv2d(x.float(), w1) * dy1.float()).sum()
+    g3, g1 = torch.autograd.grad(tot, (w3, w1))
+    ok = check(f"repvgg_wgrad3 rc={rc} N{N} {H}x{W} C{Cin}->{Cout}", dw[:Cout * 9 * Cin].view(Cout, 3, 3, Cin),
+               g3.permute(0, 2, 3, 1), 5e-3)
+    ok &= check("   repvgg_wgrad1", dw[Cout * 9 * Cin:].view(Cout, 1, 1, Cin), g1.permute(0, 2, 3, 1), 5e-3)
+    return ok
+
+
+def run_dgrad_s2(N, H, W, Cin, Cout, with1x1):
+    """parity-class stride-2 data gradient (+ the 1x1 stride-2 branch) vs torch autograd."""
+    torch.manual_seed(4)
+    w3 = torch.randn(Cout, Cin, 3, 3, device="cuda") / (Cin * 9) ** 0.5
+    w1 = torch.randn(Cout, Cin, 1, 1, device="cuda") / Cin ** 0.5
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    dy3 = torch.randn(N, Ho, Wo, Cout, device="cuda").to(torch.bfloat16)
+    dy1 = torch.randn(N, Ho, Wo, Cout, device="cuda").to(torch.bfloat16)
+    CinD = (Cin + 15) // 16 * 16
+    wcls = torch.empty(9 * CinD * Cout, device="cuda", dtype=torch.bfloat16)
+    rc = L.hb_pack_dgrad_s2_weights(ptr(w3.permute(0, 2, 3, 1).contiguous()), ptr(wcls), Cout, Cin, CinD, Cout, stream_ptr())
+    wd1 = torch.zeros(CinD, 1, 1, Cout, device="cuda", dtype=torch.bfloat16)
+    wd1[:Cin, 0, 0, :] = w1[:, :, 0, 0].t().to(torch.bfloat16)
+    dx = torch.full((N, H, W, CinD), float("nan"), device="cuda", dtype=torch.bfloat16)
+    rc |= L.hb_conv2d_dgrad_s2_bf16(ptr(dy3), ptr(wcls), ptr(dy1) if with1x1 else ptr(None), ptr(wd1) if with1x1 else ptr(None),
+                                    ptr(dx), N, H, W, Ho, Wo, Cout, CinD, 0, stream_ptr())
+    torch.cuda.synchronize()
+    xz = torch.zeros(N, Cin, H, W, device="cuda", requires_grad=True)
+    y = F.conv2d(xz, w3.to(torch.bfloat16).float(), stride=2, padding=1)
+    tot = (y * dy3.permute(0, 3, 1, 2).float()).sum()
+    if with1x1:
+        y1 = F.conv2d(xz, w1.to(torch.bfloat16).float(), stride=2, padding=0)
+        tot = tot + (y1 * dy1.permute(0, 3, 1, 2).float()).sum()
+    (gx,) = torch.autograd.grad(tot, xz)
+    ok = check(f"dgrad_s2 rc={rc} N{N} {H}x{W} C{Cin}<-{Cout} 1x1={with1x1}", dx[..., :Cin], gx.permute(0, 2, 3, 1), 2e-2)
+    if CinD != Cin:
+        ok &= bool((dx[..., Cin:] == 0).all())
+    return ok
+
+
 def run_bn(M, C, B, act, residual):
     torch.manual_seed(3)
     dev = "cuda"
@@ -154,6 +208,18 @@ def main():
             ok &= run_dgrad(*cfg)
         except Exception as e:  # noqa: BLE001
             print("EXC dgrad", cfg, repr(e)); ok = False
+    for cfg in [(3, 112, 112, 48, 48), (5, 28, 28, 96, 96), (40, 14, 14, 192, 192), (2, 30, 20, 32, 48), (2, 16, 16, 72, 200),
+                (2, 9, 11, 16, 16), (300, 14, 14, 48, 48)]:
+        try:
+            ok &= run_repvgg_wgrad(*cfg)
+        except Exception as e:  # noqa: BLE001
+            print("EXC repvgg_wgrad", cfg, repr(e)); ok = False
+    for cfg in [(2, 16, 16, 48, 48, True), (2, 16, 16, 48, 96, False), (3, 15, 9, 24, 32, True), (2, 14, 14, 192, 1280, True),
+                (2, 7, 7, 64, 64, False), (4, 56, 56, 48, 96, True), (1, 2, 2, 16, 16, True), (2, 224, 224, 8, 48, False)]:
+        try:
+            ok &= run_dgrad_s2(*cfg)
+        except Exception as e:  # noqa: BLE001
+            print("EXC dgrad_s2", cfg, repr(e)); ok = False
     for cfg in [(1000, 48, 3, 1, False), (4096, 64, 1, 1, False), (777, 1280, 2, 1, False), (2048, 96, 3, 0, True),
                 (2048, 320, 1, 3, False), (2048, 32, 1, 4, True), (2048, 64, 1, 5, False), (512, 8, 2, 6, False),
                 (3000, 192, 1, 2, True)]:
