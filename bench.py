@@ -41,27 +41,81 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+    """Samples SM clocks / throttle reasons while the timed region runs: NVML from a background thread (4 Hz; a
+    100 ms `nvidia-smi -lms` poller was measured to slow kernel launches of the process under test by 2x), falling
+    back to a 500 ms `nvidia-smi` loop when the NVML binding is unavailable."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int) -> None:
         self.index, self.proc, self.lines = index, None, []
+        self.samples, self.max_mhz, self.reasons = [], None, set()
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.mode = None
+
+    def _nvml_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.index])
+            except (ValueError, IndexError):
+                return self.index
+        return self.index
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._nvml_index())
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.mode = "nvml"
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:  # noqa: BLE001
+            self.mode = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "500",
+                                          "-i", str(self._nvml_index())], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                         text=True)
+            self.mode = "smi"
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
             self.proc = None
+
+    def _poll_nvml(self):
+        nv = self.nvml
+        masks = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                for name, m in masks.items():
+                    if r & m:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            self.stop_flag.wait(0.25)
 
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.mode == "nvml":
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            clocks = sorted(self.samples)
+            med = clocks[len(clocks) // 2] if clocks else None
+            return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(clocks),
+                    "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -70,7 +124,6 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
         clocks, maxes, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 7:
@@ -79,12 +132,13 @@ class ClockSampler:
                 clocks.append(float(parts[0])); maxes.append(float(parts[1]))
             except ValueError:
                 continue
-            for nm, v in zip(names, parts[3:7]):
+            for nm, v in zip(self.NAMES, parts[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         clocks.sort()
         med = clocks[len(clocks) // 2] if clocks else None
-        return {"sm_mhz": med, "sm_max_mhz": max(maxes) if maxes else None, "reasons": sorted(reasons), "samples": len(clocks)}
+        return {"sm_mhz": med, "sm_max_mhz": max(maxes) if maxes else None, "reasons": sorted(reasons), "samples": len(clocks),
+                "source": "nvidia-smi"}
 
 
 def synthetic_batch(batch: int, seed: int, device):
@@ -206,6 +260,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel of the step eagerly (no CUDA graph)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -221,6 +276,7 @@ def main():
     from holocron_b200.nn import _fused as K
     from holocron_b200.distributed import GradBucket, broadcast_parameters
     from holocron_b200._lib import lib
+    from holocron_b200.graphs import GraphedTrainStep
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (impl b200) needs a CUDA device: there is no CPU fallback")
@@ -235,20 +291,31 @@ def main():
     model = hb.models.repvgg_a0(num_classes=NUM_CLASSES).to(dev).to(memory_format=torch.channels_last).train()
     broadcast_parameters(model)
     bucket = GradBucket(model.parameters())
-    opt = hb.optim.AdaBelief(model.parameters(), lr=1e-3, betas=(0.95, 0.99), eps=1e-6)
+    opt = hb.optim.AdaBelief(model.parameters(), lr=1e-3, betas=(0.95, 0.99), eps=1e-6, capturable=not args.no_graph)
     batch = args.batch
     x_dev, t_dev = synthetic_batch(batch, 1000 + rank, dev)
     # end-to-end leg: host-resident batch in pinned memory
     x_host = x_dev.cpu().pin_memory()
     t_host = t_dev.cpu().pin_memory()
 
-    def train_step(x, t):
+    def eager_step(x, t):
         loss = F.cross_entropy(model(x), t, label_smoothing=0.1)
         loss.backward()
         bucket.all_reduce_mean()
         opt.step()
         bucket.zero_()
         return loss
+
+    # The whole step (forward, loss, backward, all-reduce, optimizer) is captured once into a CUDA graph and replayed:
+    # ~650 kernel launches and the autograd bookkeeping per step become one graph launch (holocron_b200/graphs.py).
+    train_step, graphed = eager_step, None
+    if not args.no_graph:
+        try:
+            graphed = GraphedTrainStep(eager_step, (x_dev, t_dev), warmup=3)
+            train_step = graphed
+        except Exception as e:  # noqa: BLE001 - capture is an optimisation: report and run the same CUDA path eagerly
+            print(f"[bench] CUDA-graph capture failed ({e!r}); running the step eagerly", file=sys.stderr)
+            torch.cuda.synchronize()
 
     def barrier():
         if world > 1:
@@ -274,7 +341,7 @@ def main():
     host_ms = (time.perf_counter() - h0) * 1e3 / args.steps   # host time to ENQUEUE a step (no sync inside the loop)
     e1.record()
     barrier()
-    launches = lib().hb_launch_count()
+    launches = lib().hb_launch_count() + (graphed.launches_per_replay * args.steps if graphed is not None else 0)
     ms = e0.elapsed_time(e1) / args.steps
     clocks = sampler.stop() if rank == 0 else None
 
@@ -316,7 +383,11 @@ def main():
     if rank == 0:
         # ---- roofline leg: per-launch CUDA-event timing of the tensor-core conv kernels (one extra step) ----
         K.KERNEL_TIMER = []
-        train_step(x_dev, t_dev)
+        # park the stream behind a ~40 ms spin kernel first: the whole step is then enqueued before its first kernel runs,
+        # so the per-launch event pairs bracket GPU time only (otherwise the host gap between "record start" and the
+        # launch it precedes is counted whenever the host is slower than the GPU)
+        torch.cuda._sleep(int(8e7))
+        eager_step(x_dev, t_dev)
         torch.cuda.synchronize()
         recs = K.KERNEL_TIMER
         K.KERNEL_TIMER = None
@@ -358,7 +429,8 @@ def main():
             "config": {"workload": "repvgg_a0 (train form, 1000 classes) 224x224 bf16 train step: fwd + CE(label_smoothing=0.1)"
                                    " + bwd + AdaBelief(lr=1e-3, betas=(0.95,0.99), eps=1e-6)",
                        "batch_per_gpu": batch, "global_batch": images, "parallelism": f"dp{world}",
-                       "l2": "per-step working set (>4 GB of activations) exceeds the 126 MB L2; no explicit flush"},
+                       "l2": "per-step working set (>4 GB of activations) exceeds the 126 MB L2; no explicit flush",
+                       "launch": "cuda_graph" if graphed is not None else "eager"},
             "e2e": {"value": images / ms_e2e * 1e3, "unit": "images/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": x_host.numel() * 4 + t_host.numel() * 8, "d2h_bytes_per_step": 4,
                     "last_loss": loss_host},

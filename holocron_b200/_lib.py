@@ -40,6 +40,9 @@ SIGNATURES = {
     "hb_repvgg_wgrad_bf16": "pppppz" + "i" * 6 + "p",
     "hb_pack_conv_weights": "ppp" + "i" * 8 + "p",
     "hb_zero_insert_bf16": "pp" + "i" * 7 + "p",
+    "hb_pack_conv_weights_multi": "ppip",
+    "hb_pack_chunk_elems": "",
+    "hb_pack_meta_bytes": "",
     "hb_conv2d_dgrad_s2_bf16": "ppppp" + "i" * 8 + "p",
     "hb_pack_dgrad_s2_weights": "pp" + "i" * 4 + "p",
     "hb_nchw_to_nhwc_pad_bf16": "pp" + "i" * 6 + "p",

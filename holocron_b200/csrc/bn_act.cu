@@ -586,12 +586,12 @@ __global__ void bn_param_grads_kernel(const double* sums, const float* mean, con
 }
 
 // persistent grid: `per_sm` blocks per SM, grid-stride over rows
-inline dim3 make_grid(const Geo& g, int M, int z, int per_sm = 4) {
+inline dim3 make_grid(const Geo& g, int M, int z, int per_sm = 4, int min_rows = 4) {
   const int slabs = (g.cg_total + g.cg_t - 1) / g.cg_t;
   long long row_blocks = ((long long)M + g.rows_t - 1) / g.rows_t;
   long long cap = (HB_NUM_SMS * per_sm) / slabs;
   if (cap < 1) cap = 1;
-  long long want = (row_blocks + 3) / 4;   // at least ~4 rows per lane when there is enough work
+  long long want = (row_blocks + min_rows - 1) / min_rows;   // at least ~min_rows rows per lane when there is enough work
   if (want < 1) want = 1;
   if (want > cap) want = cap;
   return dim3((unsigned)want, (unsigned)slabs, (unsigned)z);
@@ -635,7 +635,9 @@ int hb_bn_stats_bf16(const void* u0, const void* u1, const void* u2, int B, int 
   if (C % 8 != 0 || B < 1 || B > kMaxBranches) return (int)cudaErrorInvalidValue;
   Branches br{{(const __nv_bfloat16*)u0, (const __nv_bfloat16*)u1, (const __nv_bfloat16*)u2}, B};
   Geo g = Geo::make(C);
-  bn_stats_kernel<<<make_grid(g, M, B), kThreads, 0, (cudaStream_t)stream>>>(br, M, C, g, sums);
+  // every block ends with 2*C fp64 atomics per branch: keep the block count down on small problems
+  static const int min_rows = env_int("HB_BN_STATS_ROWS", 16);
+  bn_stats_kernel<<<make_grid(g, M, B, 4, min_rows), kThreads, 0, (cudaStream_t)stream>>>(br, M, C, g, sums);
   HB_LAUNCH_CHECK();
   return 0;
 }

@@ -10,6 +10,7 @@ Reference call sites being replaced: ``nn.Conv2d`` / ``nn.BatchNorm2d`` / activa
 """
 import ctypes
 import os
+import weakref
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -91,10 +92,65 @@ def _empty_cl(n: int, c: int, h: int, w: int, device, dtype=torch.bfloat16) -> T
 # ------------------------------------------------------------------------------------------------------
 # filter packing cache: fp32 master (any layout) -> bf16 KRSC for fprop, flipped+transposed bf16 for dgrad
 class PackedFilter:
-    __slots__ = ("wf", "wd", "key", "cin_p", "cout_p", "cin_d", "cout", "cin", "r", "s")
+    __slots__ = ("wf", "wd", "key", "cin_p", "cout_p", "cin_d", "cout", "cin", "r", "s", "wref", "w_krsc", "need_dgrad")
 
 
 _pack_cache = {}
+
+
+class _PackTable:
+    """Device table of every registered filter, so that ONE launch (hb_pack_conv_weights_multi) re-packs the whole
+    network when the optimizer has changed the parameters (all of them change every step) instead of one launch per
+    layer. Filters join the table the first time they are packed; the table is rebuilt only when its membership or a
+    pointer changes, so under CUDA-graph capture the multi-tensor launch is the only packing work in the graph."""
+
+    def __init__(self) -> None:
+        self.sig = None
+        self.metas = None
+        self.chunks = None
+        self.num_chunks = 0
+
+    def repack_all(self) -> bool:
+        ents = []
+        for k, e in list(_pack_cache.items()):
+            w = e.wref()
+            if w is None:
+                del _pack_cache[k]
+                continue
+            if e.w_krsc is None:          # non-channels_last master: needs its own permuted copy, packed individually
+                continue
+            ents.append((e, w))
+        if len(ents) < 2:
+            return False
+        sig = tuple((e.w_krsc.data_ptr(), e.wf.data_ptr(), 0 if e.wd is None else e.wd.data_ptr()) for e, _ in ents)
+        L = lib()
+        if sig != self.sig:
+            import numpy as np
+            chunk = L.hb_pack_chunk_elems()
+            dt = np.dtype([("ptrs", "<u8", (3,)), ("ints", "<i4", (8,))])
+            assert dt.itemsize == L.hb_pack_meta_bytes()
+            metas = np.zeros(len(ents), dtype=dt)
+            rows = []
+            for i, (e, _) in enumerate(ents):
+                metas[i]["ptrs"] = sig[i]
+                metas[i]["ints"] = (e.cout, e.cin, e.r, e.s, e.cin_p, e.cin_d, e.cout_p, e.cout_p)
+                n = e.wf.numel() + (0 if e.wd is None else e.wd.numel())
+                nch = (n + chunk - 1) // chunk
+                rows.append(np.stack([np.full(nch, i, dtype=np.int32), np.arange(nch, dtype=np.int32)], 1))
+            chunks = np.ascontiguousarray(np.concatenate(rows, 0))
+            dev = ents[0][0].wf.device
+            self.metas = torch.from_numpy(metas.view(np.uint8).reshape(len(ents), -1).copy()).to(dev)
+            self.chunks = torch.from_numpy(chunks).to(dev)
+            self.num_chunks = int(chunks.shape[0])
+            self.sig = sig
+        check(L.hb_pack_conv_weights_multi(ptr(self.metas), ptr(self.chunks), self.num_chunks, stream_ptr()),
+              "hb_pack_conv_weights_multi")
+        for e, w in ents:
+            e.key = (w.data_ptr(), w._version, e.need_dgrad, tuple(w.stride()), e.cin_p)
+        return True
+
+
+_pack_table = _PackTable()
 
 
 def pack_filter(weight: Tensor, need_dgrad: bool, cin_p: Optional[int] = None) -> PackedFilter:
@@ -108,17 +164,25 @@ def pack_filter(weight: Tensor, need_dgrad: bool, cin_p: Optional[int] = None) -
     ent = _pack_cache.get(id(weight))
     if ent is not None and ent.key == key:
         return ent
+    if ent is not None and ent.key[0] == key[0] and ent.key[2:] == key[2:] and ent.wref() is weight and ent.w_krsc is not None:
+        # same filter, new parameter values (an optimizer step): refresh every registered filter in one launch
+        if _pack_table.repack_all() and ent.key == key:
+            return ent
     w = weight.detach()
     if w.dtype != torch.float32:
         w = w.float()
     # physical KRSC fp32 view (zero-copy when the parameter is stored channels_last)
     w_krsc = w.permute(0, 2, 3, 1)
+    zero_copy = w_krsc.is_contiguous() and w.dtype == weight.dtype
     if not w_krsc.is_contiguous():
         w_krsc = w_krsc.contiguous()
     ent = PackedFilter()
     ent.key, ent.cin_p, ent.cout, ent.cin, ent.r, ent.s = key, cin_p, cout, cin, r, s
     ent.cout_p = round_up(cout, 16)
     ent.cin_d = round_up(cin_p, 16)
+    ent.need_dgrad = need_dgrad
+    ent.wref = weakref.ref(weight)
+    ent.w_krsc = w_krsc if zero_copy else None     # only views of the live parameter can sit in the device table
     ent.wf = torch.empty((ent.cout_p, r, s, cin_p), device=w.device, dtype=torch.bfloat16)
     ent.wd = torch.empty((ent.cin_d, r, s, ent.cout_p), device=w.device, dtype=torch.bfloat16) if need_dgrad else None
     check(lib().hb_pack_conv_weights(ptr(w_krsc), ptr(ent.wf), ptr(ent.wd), cout, cin, r, s, cin_p, ent.cin_d, ent.cout_p,
@@ -530,11 +594,16 @@ class _RepBlockFn(torch.autograd.Function):
                 elif rc[0] != 801:   # 801 = cudaErrorNotSupported: shape not eligible, use the composition below
                     check(rc[0], "hb_conv3x3_accum_bf16")
             if not fused:
+                res_chain = False
                 if stride == 1:
                     src3 = dy3
                     dxa = _empty_cl(n, cin_d, h, w, dev)
+                    # the generic kernel adds a residual in its epilogue: dXa = dgrad1x1(dY1) + dXid, dX = dgrad3x3(dY3) + dXa
+                    # (tensor-bound layers: the extra epilogue read is free, two full-tensor add kernels are not)
+                    res_chain = cin_d == c and wd3.shape[3] == c
+                    res1 = dxid if (res_chain and dxid is not None) else None
                     _timed("dgrad", dict(N=n, H=h, W=w, Cin=c, Cout=cin_d, R=1, S=1, stride=1, Ho=h, Wo=w), lambda: check(
-                        L.hb_conv2d_fprop_bf16(ptr(dy1), ptr(wd1), ptr(dxa), ptr(None), ptr(None), n, h, w, c, cin_d, 1, 1, 1,
+                        L.hb_conv2d_fprop_bf16(ptr(dy1), ptr(wd1), ptr(dxa), ptr(None), ptr(res1), n, h, w, c, cin_d, 1, 1, 1,
                                                0, 1, ACT_NONE, 0, stream_ptr()), "hb_conv2d_fprop_bf16[dgrad1x1]"))
                 else:
                     lo = _empty_cl(n, cin_d, ho, wo, dev)
@@ -549,11 +618,13 @@ class _RepBlockFn(torch.autograd.Function):
                           "hb_zero_insert_bf16")
                 _timed("dgrad", dict(N=n, H=h, W=w, Cin=c, Cout=cin_d, R=3, S=3, stride=1, Ho=h, Wo=w,
                                      dgrad_of_stride=stride), lambda: check(
-                    L.hb_conv2d_fprop_bf16(ptr(src3), ptr(wd3), ptr(dxp), ptr(None), ptr(None), n, h, w, c, cin_d, 3, 3, 1, 1,
-                                           1, ACT_NONE, 0, stream_ptr()), "hb_conv2d_fprop_bf16[dgrad3x3]"))
-                dxp.add_(dxa)
-                if dxid is not None:
-                    dxp[:, :c].add_(dxid)
+                    L.hb_conv2d_fprop_bf16(ptr(src3), ptr(wd3), ptr(dxp), ptr(None), ptr(dxa) if res_chain else ptr(None), n, h,
+                                           w, c, cin_d, 3, 3, 1, 1, 1, ACT_NONE, 0, stream_ptr()),
+                    "hb_conv2d_fprop_bf16[dgrad3x3]"))
+                if not res_chain:
+                    dxp.add_(dxa)
+                    if dxid is not None:
+                        dxp[:, :c].add_(dxid)
             dx = dxp if cin_d == cin_x else dxp[:, :cin_x]
         if stem:
             cin = w3.shape[1]

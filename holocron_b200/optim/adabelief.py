@@ -15,9 +15,9 @@ _cf = ctypes.c_float
 
 
 def _launch(table: TensorTable, step: int, amsgrad: bool, beta1: float, beta2: float, lr: float, weight_decay: float,
-            eps: float) -> None:
+            eps: float, step_dev: Optional[Tensor] = None) -> None:
     check(lib().hb_adabelief_step(ptr(table.metas), ptr(table.chunks), table.num_chunks, _cf(lr), _cf(beta1), _cf(beta2),
-                                  _cf(eps), _cf(weight_decay), int(amsgrad), int(step), None, stream_ptr()),
+                                  _cf(eps), _cf(weight_decay), int(amsgrad), int(step), ptr(step_dev), stream_ptr()),
           "hb_adabelief_step")
 
 
@@ -27,8 +27,12 @@ class AdaBelief(Optimizer):
 
     Same constructor arguments and ``state_dict`` layout (``step`` python int, ``exp_avg``, ``exp_avg_sq``,
     ``max_exp_avg_sq``) as the reference, which inherits ``torch.optim.Adam.__init__``; Adam's implementation
-    switches (``foreach``, ``fused``, ``capturable``, ...) are accepted and ignored. One kernel launch per
-    parameter group and step value instead of ~9 per tensor.
+    switches (``foreach``, ``fused``, ...) are accepted and ignored. One kernel launch per parameter group and
+    step value instead of ~9 per tensor.
+
+    ``capturable=True`` (Adam's flag) keeps the step count of each group in a device counter that the kernels read for
+    the bias corrections, so that a captured CUDA graph of ``step()`` stays correct when replayed
+    (:class:`holocron_b200.utils.GraphedTrainStep`); ``state['step']`` then only advances when Python runs ``step()``.
     """
 
     def __init__(self, params: Iterable, lr: float = 1e-3, betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
@@ -48,12 +52,14 @@ class AdaBelief(Optimizer):
                                                                  "fused")})
         super().__init__(params, defaults)
         self._tables = {}
+        self._step_dev = {}
 
     def __setstate__(self, state) -> None:
         super().__setstate__(state)
         for group in self.param_groups:
             group.setdefault("amsgrad", False)
         self._tables = {}
+        self._step_dev = {}
 
     @torch.no_grad()
     def step(self, closure: Optional[Callable[[], float]] = None) -> Optional[float]:  # type: ignore[override]
@@ -84,7 +90,16 @@ class AdaBelief(Optimizer):
                 table.update([p.data for p in plist], grads, [self.state[p]["exp_avg"] for p in plist],
                              [self.state[p]["exp_avg_sq"] for p in plist],
                              [self.state[p]["max_exp_avg_sq"] for p in plist] if group["amsgrad"] else None, None)
-                _launch(table, step, group["amsgrad"], beta1, beta2, group["lr"], group["weight_decay"], group["eps"])
+                step_dev = None
+                if group.get("capturable"):
+                    key = (gi, step if len(by_step) > 1 else -1)
+                    step_dev = self._step_dev.get(key)
+                    if step_dev is None:
+                        step_dev = torch.full((1,), step - 1, device=plist[0].device, dtype=torch.int32)
+                        self._step_dev[key] = step_dev
+                    check(lib().hb_step_increment(ptr(step_dev), stream_ptr()), "hb_step_increment")
+                _launch(table, step, group["amsgrad"], beta1, beta2, group["lr"], group["weight_decay"], group["eps"],
+                        step_dev)
                 bump_versions(plist)
         return loss
 

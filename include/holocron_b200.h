@@ -62,6 +62,12 @@ int hb_repvgg_wgrad_bf16(const void* x, const void* dy3, const void* dy1, float*
  * flipped + transposed bf16 filter [CinD][R][S][CoutP] used by the data-gradient pass */
 int hb_pack_conv_weights(const float* w, void* wf, void* wd, int Cout, int Cin, int R, int S, int CinP, int CinD,
                          int CoutP, int CoutF, void* stream);
+/* The same for a whole network in ONE launch. metas: device array of hb_pack_meta_bytes()-byte rows
+ * {const float* w; bf16* wf; bf16* wd (NULL allowed); int32 Cout, Cin, R, S, CinP, CinD, CoutP, CoutF}; chunks: device array
+ * of int32 pairs (row index, chunk index), hb_pack_chunk_elems() output elements (wf then wd) per chunk. */
+int hb_pack_conv_weights_multi(const void* metas, const void* chunks, int num_chunks, void* stream);
+int hb_pack_chunk_elems(void);
+int hb_pack_meta_bytes(void);
 /* Data gradient of a stride-2 3x3 pad-1 convolution (the backward of the stride-2 nn.Conv2d at the head of every
  * RepVGG / Darknet / ReXNet stage, holocron/models/classification/repvgg.py:55-73, utils.py:28-86) without zero insertion:
  * the 4 parity classes of dx [N,H,W,Cd] are 1/2/2/4-tap correlations over dy [N,Ho,Wo,C] written to their sub-grids.
@@ -86,7 +92,7 @@ int hb_im2col_smallc_bf16(const void* x, void* col, int N, int C, int H, int W, 
  *      (holocron/models/utils.py:73-78) and the branch sum of RepBlock.forward (repvgg.py:71-73) ------------- */
 /* per-channel sum / sum of squares of up to 3 tensors [M,C] bf16 into sums (double [B][2][C], pre-zeroed) */
 int hb_bn_stats_bf16(const void* u0, const void* u1, const void* u2, int B, int M, int C, double* sums, void* stream);
-/* gamma/beta/running_*/num_batches_tracked: HOST arrays of B device pointers (entries may be NULL). Outputs fp32
+/* gamma, beta, running_mean/var, num_batches_tracked: HOST arrays of B device pointers (entries may be NULL). Outputs fp32
  * [B][C]. Updates the running statistics with `momentum` (unbiased variance) and increments the int64
  * num_batches_tracked counters, like nn.BatchNorm2d in training mode. */
 int hb_bn_finalize(const double* sums, const float* const* gamma, const float* const* beta, float* const* running_mean,

@@ -4,9 +4,12 @@ import ctypes
 import re
 from pathlib import Path
 
+import pytest
+
 from holocron_b200 import _lib
 
 ROOT = Path(__file__).resolve().parents[1]
+HEADER = ROOT / "include" / "holocron_b200.h"
 
 
 def _header_decls():
@@ -56,3 +59,16 @@ def test_library_exports_every_declared_symbol():
 def test_every_reference_citation_in_header():
     hdr = (ROOT / "include" / "holocron_b200.h").read_text()
     assert hdr.count("holocron/") >= 6  # each group cites the reference file:line it replaces
+
+
+def test_header_is_valid_c_and_cxx(tmp_path):
+    """include/holocron_b200.h must compile on its own as C and as C++ (it is the contract other hosts bind)."""
+    import shutil
+    import subprocess
+    for compiler, lang in (("gcc", "c"), ("g++", "c++")):
+        if shutil.which(compiler) is None:
+            pytest.skip(f"{compiler} not available")
+        src = tmp_path / f"use_header.{'c' if lang == 'c' else 'cpp'}"
+        src.write_text('#include "holocron_b200.h"\nint main(void) { return 0; }\n')
+        r = subprocess.run([compiler, "-fsyntax-only", "-Wall", f"-I{HEADER.parent}", str(src)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr

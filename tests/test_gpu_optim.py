@@ -43,6 +43,19 @@ def test_trajectories_vs_reference(name, cls):
     opt2.step()
 
 
+def test_adabelief_capturable_matches_default():
+    """capturable=True (device-side step counter for CUDA-graph replay) follows the same trajectory."""
+    g = load_golden("optim")
+    params = [torch.nn.Parameter(p.clone().cuda()) for p in g["p0"]]
+    opt = hb.optim.AdaBelief(params, capturable=True, **g["adabelief_kw"])
+    for step in range(3):
+        for p, gr in zip(params, g["grads"][step]):
+            p.grad = gr.clone().cuda()
+        opt.step()
+        for p, ref in zip(params, g["adabelief"][step]):
+            close(p, ref)
+
+
 def test_optimizer_changes_params_like_reference_test():
     # reference tests/test_optim.py:10-39: one step on a 1024 -> 10 classifier layer must change its weight
     # (for TAdam the first update is ~1e-10 - the first w_t is (dof+d)/(sum(g^2)/eps) - so only tiny weights move,

@@ -86,3 +86,43 @@ def test_train_step_loss_parity_and_update():
     assert all(not torch.equal(a, b) for a, b in zip(before, m.parameters()))
     # state_dict stays interchangeable with the oracle / reference layout
     o.load_state_dict({k: v.cpu() for k, v in m.state_dict().items()})
+
+
+def test_cuda_graph_train_step_matches_eager():
+    """holocron_b200.graphs.GraphedTrainStep: replaying the captured step (forward + CE + backward + AdaBelief with a
+    device-side step counter) gives the same losses as launching every kernel eagerly with the same history
+    (2 warm-up steps on the first batch; the capture itself records without executing). fp64 atomics make the BN
+    statistics summation order-dependent, hence 2e-3 relative instead of equality."""
+    from holocron_b200.distributed import GradBucket
+    from holocron_b200.graphs import GraphedTrainStep
+
+    torch.manual_seed(1)
+    xs = [torch.rand(8, 3, 64, 64, device="cuda") for _ in range(3)]
+    ts = [torch.randint(0, 10, (8,), device="cuda") for _ in range(3)]
+
+    def build(capturable):
+        torch.manual_seed(0)
+        m = hb.models.repvgg_a0(num_classes=10).cuda().to(memory_format=torch.channels_last).train()
+        bucket = GradBucket(m.parameters())
+        opt = hb.optim.AdaBelief(m.parameters(), lr=1e-3, betas=(0.95, 0.99), eps=1e-6, capturable=capturable)
+
+        def step(x, t):
+            loss = TF.cross_entropy(m(x), t, label_smoothing=0.1)
+            loss.backward()
+            opt.step()
+            bucket.zero_()
+            return loss
+        return m, step
+
+    _, step_e = build(False)
+    for _ in range(2):
+        step_e(xs[0], ts[0])
+    losses_e = [step_e(x, t).item() for x, t in zip(xs, ts)]
+
+    _, step_g = build(True)
+    graphed = GraphedTrainStep(step_g, (xs[0], ts[0]), warmup=2)
+    assert graphed.launches_per_replay > 100
+    losses_g = [graphed(x, t).item() for x, t in zip(xs, ts)]
+    for a, b in zip(losses_g, losses_e):
+        assert abs(a - b) / abs(b) < 2e-3, (losses_g, losses_e)
+    assert losses_g[0] != losses_g[1]   # the replays really consumed the new inputs / updated parameters
