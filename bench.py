@@ -10,6 +10,7 @@ backward + gradient all-reduce (N > 1) + AdaBelief(lr=1e-3, betas=(0.95, 0.99), 
 ImageNet-shaped batch of 256 images per GPU (weak scaling). Prints ONE JSON line on rank 0.
 """
 import argparse
+import datetime
 import json
 import os
 import subprocess
@@ -284,7 +285,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
     warmup = max(args.warmup, 3)
 
     torch.manual_seed(0)
@@ -298,10 +299,11 @@ def main():
     x_host = x_dev.cpu().pin_memory()
     t_host = t_dev.cpu().pin_memory()
 
-    def eager_step(x, t):
+    def eager_step(x, t, collective=True):
         loss = F.cross_entropy(model(x), t, label_smoothing=0.1)
         loss.backward()
-        bucket.all_reduce_mean()
+        if collective:
+            bucket.all_reduce_mean()
         opt.step()
         bucket.zero_()
         return loss
@@ -387,14 +389,15 @@ def main():
         # so the per-launch event pairs bracket GPU time only (otherwise the host gap between "record start" and the
         # launch it precedes is counted whenever the host is slower than the GPU)
         torch.cuda._sleep(int(8e7))
-        eager_step(x_dev, t_dev)
+        eager_step(x_dev, t_dev, collective=False)   # rank 0 only: no collective may be issued here
         torch.cuda.synchronize()
         recs = K.KERNEL_TIMER
         K.KERNEL_TIMER = None
         agg = {}
         for kind, info, a, b in recs:
             fl, by = conv_algorithmic(info, kind)
-            kname = "conv_wgrad_kernel" if kind == "wgrad" else "conv_fprop_kernel"
+            # kernel families: the generic implicit-GEMM kernel and its row-window twin share each role
+            kname = "conv_wgrad_kernel+conv_wgrad_rows_kernel" if kind == "wgrad" else "conv_fprop_kernel+conv_rows_kernel"
             d = agg.setdefault(kname, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
             d["ms"] += a.elapsed_time(b); d["flops"] += fl; d["bytes"] += by; d["launches"] += 1
         if os.environ.get("HB_BENCH_DETAIL"):
@@ -415,7 +418,19 @@ def main():
         else:
             roof = {"bound": "tensor", "achieved": d["flops"] / d["ms"] / 1e9, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s"}
         roof["frac"] = roof["achieved"] / roof["peak"]
+        # DRAM traffic of the same kernel family from an ncu capture of one step (tools/collect_traffic.py ->
+        # profiles/r01_traffic.json), averaged per launch like `achieved`; null when the capture is not there
         roof["traffic"] = None
+        roof["algorithmic_bytes"] = d["bytes"] / d["launches"]
+        try:
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")) as f:
+                tk = json.load(f)["kernels"]
+            fam = [tk[k] for k in dom.split("+") if k in tk]
+            if fam and sum(k["launches"] for k in fam) == d["launches"]:
+                roof["traffic"] = sum(k["dram_read_bytes"] + k["dram_write_bytes"] for k in fam) / d["launches"]
+                roof["traffic_source"] = "ncu dram__bytes_read.sum + dram__bytes_write.sum (profiles/r01_traffic.json), per launch"
+        except (OSError, KeyError, ValueError):
+            pass
         roof["kernel"] = dom
         roof["peak_source"] = peaks["src"]
         roof["per_step"] = {k: {"ms": round(v["ms"], 3), "launches": v["launches"], "TFLOP/s": round(v["flops"] / v["ms"] / 1e9, 1),
