@@ -457,8 +457,13 @@ def main():
             result["cpu_baseline"] = cpu
         print(json.dumps(result), flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        # No collective after the timing all-reduce: rank 0's extra legs above are local, the other ranks are done.
+        # Communicator teardown with captured NCCL kernels still alive was seen to block at exit (2 x B200, NCCL 2.28),
+        # so every rank leaves through a hard exit once its output is flushed.
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

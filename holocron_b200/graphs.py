@@ -42,7 +42,8 @@ class GraphedTrainStep:
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         before = lib().hb_launch_count()
-        with torch.cuda.graph(self.graph):
+        # capture on the stream of the warm-up: autograd's AccumulateGrad nodes were created there
+        with torch.cuda.graph(self.graph, stream=side):
             self.static_loss = step_fn(*self.static_inputs)
         #: kernels of this library recorded in the graph (= launched by every replay)
         self.launches_per_replay = int(lib().hb_launch_count() - before)
