@@ -93,6 +93,89 @@ __global__ void __launch_bounds__(kThreads) dw_bwd_data_kernel(const __nv_bfloat
   }
 }
 
+// ---- 3x3 specialisations: fixed channel group per thread (block = channel groups x pixel lanes, as in the BN
+// kernels), the block's slab of the filter sits in shared memory (float4 reads). The generic kernels above
+// re-read 72 scalar weights per output vector and recompute the channel group of every element: 9x slower than the
+// HBM time on the ReXNet expansions (profiles/r01_rexnet_launches.md).
+template <bool kBackward>
+__global__ void __launch_bounds__(kThreads) dw3x3_kernel(const __nv_bfloat16* __restrict__ src, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ dst,
+                                                         DwParams p, int cg_t, int rows_t) {
+  // forward:  src = x [N,H,W,C],   dst = y  [N,Ho,Wo,C]: y[ho,wo]  = b + sum_{r,s} x[ho*st+r-pad, wo*st+s-pad] * w[r,s]
+  // backward: src = dy [N,Ho,Wo,C], dst = dx [N,H,W,C]:  dx[hi,wi] = sum_{r,s} dy[(hi+pad-r)/st, (wi+pad-s)/st] * w[r,s]
+  __shared__ __align__(16) float ws[9][256];   // the block's channel slab of the filter, tap-major
+  const int cv = p.C / 8;
+  const int tx = threadIdx.x % cg_t, ty = threadIdx.x / cg_t;
+  const int cg = blockIdx.y * cg_t + tx;
+  for (int i = threadIdx.x; i < 9 * cg_t * 8; i += kThreads) {
+    const int k = i / (cg_t * 8), ch = i % (cg_t * 8);
+    const int c = blockIdx.y * cg_t * 8 + ch;
+    ws[k][ch] = c < p.C ? w[c * 9 + k] : 0.f;
+  }
+  __syncthreads();
+  if (ty >= rows_t || cg >= cv) return;
+  float b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) b[j] = (!kBackward && bias) ? bias[cg * 8 + j] : 0.f;
+  const int OH = kBackward ? p.H : p.Ho, OW = kBackward ? p.W : p.Wo;   // grid walked by this kernel
+  const int IH = kBackward ? p.Ho : p.H, IW = kBackward ? p.Wo : p.W;   // grid of src
+  const long long M = (long long)p.N * OH * OW;
+  const long long stride_m = (long long)gridDim.x * rows_t;
+  for (long long m = (long long)blockIdx.x * rows_t + ty; m < M; m += stride_m) {
+    const int ow = (int)(m % OW);
+    const int oh = (int)((m / OW) % OH);
+    const long long n = m / ((long long)OW * OH);
+    const __nv_bfloat16* sn = src + n * IH * IW * p.C + cg * 8;
+    Vec16<__nv_bfloat16> v[9];
+    bool ok[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+      for (int s2 = 0; s2 < 3; ++s2) {
+        int ih, iw;
+        bool good;
+        if (!kBackward) {
+          ih = oh * p.stride + r - p.pad; iw = ow * p.stride + s2 - p.pad;
+          good = ih >= 0 && ih < IH && iw >= 0 && iw < IW;
+        } else {
+          const int hn = oh + p.pad - r, wn = ow + p.pad - s2;
+          good = hn >= 0 && wn >= 0 && (p.stride == 1 || ((hn % p.stride) == 0 && (wn % p.stride) == 0));
+          ih = hn / p.stride; iw = wn / p.stride;
+          good = good && ih < IH && iw < IW;
+        }
+        ok[r * 3 + s2] = good;
+        if (good) v[r * 3 + s2] = ld16(sn + ((long long)ih * IW + iw) * p.C);   // all 9 loads issued before the first use
+      }
+    }
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = b[j];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      if (ok[k]) {
+        const float4 w0 = *reinterpret_cast<const float4*>(&ws[k][tx * 8]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&ws[k][tx * 8 + 4]);
+        const float wk[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(__bfloat162float(v[k].v[j]), wk[j], acc[j]);
+      }
+    }
+    store8(dst + m * p.C + cg * 8, acc);
+  }
+}
+
+inline dim3 dw_grid(long long M, int cv, int& cg_t, int& rows_t, int per_sm) {
+  cg_t = cv < 32 ? cv : 32;
+  rows_t = kThreads / cg_t;
+  const int slabs = (cv + cg_t - 1) / cg_t;
+  long long gx = (M + rows_t * 4 - 1) / (rows_t * 4);
+  long long cap = (HB_NUM_SMS * per_sm) / slabs;
+  if (cap < 1) cap = 1;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  return dim3((unsigned)gx, (unsigned)slabs);
+}
+
 // dw[c,r,s] = sum_{n,ho,wo} dy * x_shifted ; db[c] = sum dy.  sums: double [C][KK+1] (last column = bias grad)
 // block geometry as in the BN kernels: tx = channel group within a 32-group slab, ty = pixel lane
 template <int KS>
@@ -118,6 +201,30 @@ __global__ void __launch_bounds__(kThreads) dw_bwd_weight_kernel(const __nv_bflo
       const int ho = (int)((m / p.Wo) % p.Ho);
       const int n = (int)(m / ((long long)p.Wo * p.Ho));
       float g[8];
+      if constexpr (KS == 3) {
+        // all 10 loads of the pixel are issued before the first use
+        Vec16<__nv_bfloat16> gv = ld16(dy + m * p.C + cg * 8), xv9[9];
+        bool ok[9];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            const int hi = ho * p.stride + r - p.pad, wi = wo * p.stride + s - p.pad;
+            ok[r * 3 + s] = hi >= 0 && hi < p.H && wi >= 0 && wi < p.W;
+            if (ok[r * 3 + s]) xv9[r * 3 + s] = ld16(x + (((long long)n * p.H + hi) * p.W + wi) * p.C + cg * 8);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { g[j] = __bfloat162float(gv.v[j]); acc[KK][j] += g[j]; }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          if (ok[k]) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[k][j] = fmaf(g[j], __bfloat162float(xv9[k].v[j]), acc[k][j]);
+          }
+        }
+        continue;
+      }
       load8(dy + m * p.C + cg * 8, g);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[KK][j] += g[j];
@@ -181,6 +288,14 @@ int hb_dwconv_fwd_bf16(const void* x, const float* w, const float* bias, void* y
   DwParams p = make_params(N, H, W, C, K, stride, pad);
   const long long total = (long long)N * p.Ho * p.Wo * (C / 8);
   if (total <= 0) return 0;
+  if (K == 3) {
+    int cg_t, rows_t;
+    const dim3 grid = dw_grid((long long)N * p.Ho * p.Wo, C / 8, cg_t, rows_t, 4);
+    dw3x3_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, w, bias, (__nv_bfloat16*)y, p,
+                                                                       cg_t, rows_t);
+    HB_LAUNCH_CHECK();
+    return 0;
+  }
   dw_fwd_kernel<<<stream_grid((size_t)total, kThreads, 16), kThreads, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)x, w, bias, (__nv_bfloat16*)y, p);
   HB_LAUNCH_CHECK();
@@ -193,6 +308,14 @@ int hb_dwconv_bwd_data_bf16(const void* dy, const float* w, void* dx, int N, int
   DwParams p = make_params(N, H, W, C, K, stride, pad);
   const long long total = (long long)N * H * W * (C / 8);
   if (total <= 0) return 0;
+  if (K == 3) {
+    int cg_t, rows_t;
+    const dim3 grid = dw_grid((long long)N * H * W, C / 8, cg_t, rows_t, 3);
+    dw3x3_kernel<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, w, nullptr, (__nv_bfloat16*)dx, p,
+                                                                      cg_t, rows_t);
+    HB_LAUNCH_CHECK();
+    return 0;
+  }
   dw_bwd_data_kernel<<<stream_grid((size_t)total, kThreads, 16), kThreads, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)dy, w, (__nv_bfloat16*)dx, p);
   HB_LAUNCH_CHECK();

@@ -126,11 +126,10 @@ def test_frelu_vs_golden():
     assert len(repr(fr).split("\n")) == 4   # reference tests/test_nn_activation.py:44
 
 
-@pytest.mark.parametrize("stride", [1, 2])
-def test_depthwise_conv_vs_oracle(stride):
+@pytest.mark.parametrize("stride,c", [(1, 96), (2, 96), (1, 328), (2, 16)])
+def test_depthwise_conv_vs_oracle(stride, c):
     from holocron_b200.nn._dwconv import dwconv2d
     torch.manual_seed(2)
-    c = 96
     x = torch.randn(2, c, 15, 17).bfloat16()
     w = torch.randn(c, 1, 3, 3) * 0.3
     b = torch.randn(c) * 0.1
