@@ -78,7 +78,10 @@ struct Geo {
   __host__ static Geo make(int C) {
     Geo g;
     g.cg_total = C / 8;
-    g.cg_t = g.cg_total < 32 ? g.cg_total : 32;
+    // balanced channel slabs: 38 groups -> 2 x 19 rather than 32 + 6 (the ragged last slab kept 80 % of its block's
+    // threads idle on ReXNet's widths: 300, 366, 432, 576, ... channels)
+    const int slabs = (g.cg_total + 31) / 32;
+    g.cg_t = (g.cg_total + slabs - 1) / slabs;
     g.rows_t = kThreads / g.cg_t;
     return g;
   }
@@ -681,7 +684,9 @@ int hb_bn_act_fwd_bf16(const void* u0, const void* u1, const void* u2, int B, co
   p.scale = scale; p.shift = shift; p.residual = (const __nv_bfloat16*)residual; p.out = (__nv_bfloat16*)out;
   p.M = M; p.C = C; p.act = act; p.slope = slope; p.res_after = res_after;
   Geo g = Geo::make(C);
-  static const int per_sm = env_int("HB_BN_CAP_FWD", 3);
+  static const int per_sm_env = env_int("HB_BN_CAP_FWD", 0);
+  // resident blocks per SM: 3 with three input tensors (64 KB ring each), 4 with fewer
+  const int per_sm = per_sm_env > 0 ? per_sm_env : (B + (residual != nullptr) >= 3 ? 3 : 4);
   const dim3 grid = make_grid(g, M, 1, per_sm);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = ring_bytes(B + 1);
@@ -706,7 +711,10 @@ int hb_bn_act_bwd_bf16(const void* dout, const void* u0, const void* u1, const v
   p.M = M; p.C = C; p.act = act; p.slope = slope; p.train = train; p.res_after = res_after;
   Geo g = Geo::make(C);
   cudaStream_t st = (cudaStream_t)stream;
-  static const int cap_red = env_int("HB_BN_CAP_RED", 2), cap_app = env_int("HB_BN_CAP_APPLY", 2);
+  static const int cap_red_env = env_int("HB_BN_CAP_RED", 0), cap_app_env = env_int("HB_BN_CAP_APPLY", 0);
+  // one branch (Darknet / ReXNet / UNet blocks): ~70 registers and a 48 KB ring -> three resident blocks per SM
+  const int cap_red = cap_red_env > 0 ? cap_red_env : (B <= 1 ? 3 : 2);
+  const int cap_app = cap_app_env > 0 ? cap_app_env : (B <= 1 ? 3 : 2);
   if (train || (dgamma && dbeta)) {
     const dim3 grid = make_grid(g, M, 1, cap_red);
     const size_t smem = sizeof(SlabConsts) + kThreads * 8 * sizeof(float) + ring_bytes(B + 2);

@@ -165,7 +165,8 @@ __global__ void __launch_bounds__(kThreads) dw3x3_kernel(const __nv_bfloat16* __
 }
 
 inline dim3 dw_grid(long long M, int cv, int& cg_t, int& rows_t, int per_sm) {
-  cg_t = cv < 32 ? cv : 32;
+  const int nslab = (cv + 31) / 32;
+  cg_t = (cv + nslab - 1) / nslab;      // balanced channel slabs (see bn_act.cu)
   rows_t = kThreads / cg_t;
   const int slabs = (cv + cg_t - 1) / cg_t;
   long long gx = (M + rows_t * 4 - 1) / (rows_t * 4);
@@ -332,7 +333,8 @@ int hb_dwconv_bwd_weight_bf16(const void* x, const void* dy, float* dw, float* d
   cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * C * (KK + 1), st);
   if (e != cudaSuccess) return (int)e;
   const int cv = C / 8;
-  const int cg_t = cv < 32 ? cv : 32;
+  const int nslab = (cv + 31) / 32;
+  const int cg_t = (cv + nslab - 1) / nslab;
   const int rows_t = kThreads / cg_t;
   const int slabs = (cv + cg_t - 1) / cg_t;
   const long long M = (long long)N * p.Ho * p.Wo;
