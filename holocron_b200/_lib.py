@@ -57,6 +57,8 @@ SIGNATURES = {
     "hb_dwconv_bwd_weight_bf16": "ppppp" + "iiiiiiip",
     "hb_gap_fwd_bf16": "ppiiip",
     "hb_gap_bwd_bf16": "ppiiip",
+    "hb_gate_act_fwd_bf16": "ppp" + "iiii" + "f" + "p",
+    "hb_gate_act_bwd_bf16": "ppppp" + "iiii" + "f" + "p",
     "hb_box_pairwise": "pppiiip",
     "hb_box_degenerate": "pipp",
     "hb_box_pairwise_bwd": "pppppiiip",

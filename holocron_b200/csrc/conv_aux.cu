@@ -223,30 +223,6 @@ __global__ void im2col_c3k3_kernel(const T* __restrict__ x, __nv_bfloat16* __res
   }
 }
 
-// GAP forward: x [N, HW, C] bf16 -> y [N, C] (fp32 accumulation, output bf16). One warp-free design:
-// thread owns 8 channels of one image and walks the HW rows.
-__global__ void gap_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int HW, int C) {
-  const int cv = C / 8;
-  const size_t total = (size_t)N * cv;
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const size_t n = i / cv, c = i % cv;
-  float acc[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  const __nv_bfloat16* p = x + n * HW * C + c * 8;
-  for (int r = 0; r < HW; ++r) {
-    Vec16<__nv_bfloat16> v = ld16(p + (size_t)r * C);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] += __bfloat162float(v.v[j]);
-  }
-  Vec16<__nv_bfloat16> o;
-  const float inv = 1.f / (float)HW;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) o.v[j] = __float2bfloat16_rn(acc[j] * inv);
-  st16(y + n * C + c * 8, o);
-}
-
 // GAP backward: dx[n, r, c] = dy[n, c] / HW
 __global__ void gap_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int N, int HW, int C) {
   const int cv = C / 8;
@@ -357,16 +333,6 @@ int hb_im2col_smallc_bf16(const void* x, void* col, int N, int C, int H, int W, 
     case HB_DTYPE_F16: im2col_smallc_kernel<__half><<<grid, 256, 0, st>>>((const __half*)x, c, N, C, H, W, Ho, Wo, R, S, stride, pad, Kp); break;
     default: return (int)cudaErrorInvalidValue;
   }
-  HB_LAUNCH_CHECK();
-  return 0;
-}
-
-int hb_gap_fwd_bf16(const void* x, void* y, int N, int HW, int C, void* stream) {
-  if (C % 8 != 0) return (int)cudaErrorInvalidValue;
-  const size_t n = (size_t)N * (C / 8);
-  if (n == 0) return 0;
-  gap_fwd_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x,
-                                                                                (__nv_bfloat16*)y, N, HW, C);
   HB_LAUNCH_CHECK();
   return 0;
 }

@@ -7,13 +7,14 @@
 // Replaces the cuDNN calls behind nn.Conv2d in holocron.models.utils.conv_sequence
 // (reference holocron/models/utils.py:28-86) and RepBlock (models/classification/repvgg.py:55-73).
 //
-// Pipeline (one persistent CTA per SM, 192 threads):
+// Pipeline (one persistent CTA per SM, 320 threads):
 //   warp 0      TMA producer: im2col-mode loads of the activation tile (hardware handles padding, stride,
 //               row/image wrap; out-of-range channels are zero-filled) + tiled loads of the filter slab,
 //               both landing 128B-swizzled in a multi-stage smem ring (mbarrier complete_tx).
 //   warp 1      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=BN, K=16) x4 per stage,
 //               tcgen05.commit releases the smem stage / publishes the accumulator.
-//   warps 2-5   epilogue: tcgen05.ld the accumulator (double-buffered in TMEM, so the epilogue of tile i
+//   warps 2-9   two epilogue warpgroups taking alternate tiles (one per TMEM accumulator): tcgen05.ld the accumulator
+//               (double-buffered in TMEM, so the epilogue of tile i
 //               overlaps the MMAs of tile i+1), fuse bias / activation, stage the bf16 tile in shared memory
 //               (bank-conflict-free padded rows) and write it out with fully coalesced 128-bit stores
 //               (+ residual add in that pass). The first version stored one 96-byte row per thread straight

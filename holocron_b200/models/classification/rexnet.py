@@ -105,9 +105,11 @@ class ReXBlock(nn.Module):
         tdw = K.bn_act([tdw], [bn_dw], K.ACT_NONE)
         i += 2
         if isinstance(mods[i], SEBlock):
-            tdw = tdw * mods[i].gate(tdw, self._dw_channels)
+            gate = mods[i].gate(tdw, self._dw_channels)
+            u = K.gate_act(tdw, gate, *K.act_code(mods[i + 1]))                # x * gate -> ReLU6 in one pass
             i += 1
-        u = K.act_only(tdw, *K.act_code(mods[i]))                            # ReLU6
+        else:
+            u = K.act_only(tdw, *K.act_code(mods[i]))                        # ReLU6
         proj, bn_proj = mods[i + 1], mods[i + 2]                             # 1x1 projection -> BN (+ shortcut)
         out = K.conv2d(u, proj.weight, proj.bias, 1, 0, keep_padded=True)
         res = _pad_channels(xin, out.shape[1]) if self.use_shortcut else None

@@ -716,6 +716,43 @@ class _GapFn(torch.autograd.Function):
         return dx
 
 
+class _GateActFn(torch.autograd.Function):
+    """out = act(x * gate) with gate broadcast over space (squeeze-excite), one pass forward, one pass backward."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, gate: Tensor, act: int, slope: float) -> Tensor:
+        xb = to_channels_last_bf16(x)
+        n, c, h, w = xb.shape
+        g = gate.detach().reshape(n, c).float().contiguous()
+        out = _empty_cl(n, c, h, w, xb.device)
+        check(lib().hb_gate_act_fwd_bf16(ptr(xb), ptr(g), ptr(out), n, h * w, c, act, _c_float(slope), stream_ptr()),
+              "hb_gate_act_fwd_bf16")
+        ctx.save_for_backward(xb, g)
+        ctx.cfg = (act, slope, gate.dtype, tuple(gate.shape))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout: Tensor):
+        xb, g = ctx.saved_tensors
+        act, slope, gdtype, gshape = ctx.cfg
+        n, c, h, w = xb.shape
+        dob = to_channels_last_bf16(dout)
+        dx = _empty_cl(n, c, h, w, xb.device)
+        dg = torch.empty((n, c), device=xb.device, dtype=torch.float32)
+        check(lib().hb_gate_act_bwd_bf16(ptr(dob), ptr(xb), ptr(g), ptr(dx), ptr(dg), n, h * w, c, act, _c_float(slope),
+                                         stream_ptr()), "hb_gate_act_bwd_bf16")
+        return dx, dg.to(gdtype).reshape(gshape), None, None
+
+
+def gate_act(x: Tensor, gate: Tensor, act: int = ACT_NONE, slope: float = 0.0) -> Tensor:
+    """act(x * gate): x (N, C, H, W), gate (N, C, 1, 1) — SEBlock's `x * y` fused with the activation that follows it
+    (reference rexnet.py:63-66 + 125-131)."""
+    require_cuda(x, gate)
+    if gate.shape[:2] != x.shape[:2] or gate.numel() != x.shape[0] * x.shape[1]:
+        raise ValueError(f"gate of shape {tuple(gate.shape)} does not match input {tuple(x.shape)}")
+    return _GateActFn.apply(x, gate, int(act), float(slope))
+
+
 def global_avg_pool_flat(x: Tensor) -> Tensor:
     """(N, C, H, W) -> (N, C) mean over space (bf16 channels_last in, bf16 out; fp32 accumulation)."""
     return _GapFn.apply(x)

@@ -129,6 +129,15 @@ int hb_dwconv_bwd_weight_bf16(const void* x, const void* dy, float* dw, float* d
 int hb_gap_fwd_bf16(const void* x, void* y, int N, int HW, int C, void* stream);
 int hb_gap_bwd_bf16(const void* dy, void* dx, int N, int HW, int C, void* stream);
 
+/* ---- squeeze-excite gate: SEBlock.forward `x * y` followed by the block's activation,
+ *      holocron/models/classification/rexnet.py:63-66, 125-131 --------------------------------------------- */
+/* out[n,p,c] = act(x[n,p,c] * gate[n,c]);  x/out [N,HW,C] bf16, gate fp32 [N,C]; act codes as hb_bn_act_fwd_bf16 (0-6) */
+int hb_gate_act_fwd_bf16(const void* x, const float* gate, void* out, int N, int HW, int C, int act, float slope,
+                         void* stream);
+/* dz = dout * act'(x*gate); dx = dz * gate (bf16); dgate[n,c] = sum_p dz * x (fp32, overwritten, deterministic) */
+int hb_gate_act_bwd_bf16(const void* dout, const void* x, const float* gate, void* dx, float* dgate, int N, int HW, int C,
+                         int act, float slope, void* stream);
+
 /* ---- box operators: holocron/ops/boxes.py:16-211 (+ torchvision.ops.boxes.box_iou, boxes.py:11) ---------- */
 /* mode: 0 IoU, 1 GIoU, 2 DIoU penalty rho^2/c^2, 3 DIoU loss (== the reference's ciou_loss, boxes.py:208-209),
  * 4 aspect-ratio consistency. boxes fp32 [M,4]/[N,4] xyxy; out fp32 [M,N]. */

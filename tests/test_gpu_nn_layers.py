@@ -168,3 +168,29 @@ def test_dropblock_vs_golden_and_edge_cases():
     assert mod(xi).data_ptr() == xi.data_ptr()
     assert hb.nn.DropBlock2d(0.5, 3).eval()(xx) is xx
     assert repr(hb.nn.DropBlock2d()) == "DropBlock2d(p=0.1, block_size=7, inplace=False)"
+
+
+@pytest.mark.parametrize("c,hw,act", [(96, (14, 14), 2), (304, (7, 9), 3), (16, (56, 56), 0), (1280, (7, 7), 1)])
+def test_se_gate_activation_and_pooling(c, hw, act):
+    """hb_gate_act_{fwd,bwd}_bf16 / hb_gap_fwd_bf16 (SEBlock `x * y` + the block's activation, rexnet.py:63-66, 125-131)
+    against torch fp32 on the same bf16-rounded inputs."""
+    from holocron_b200.nn import _fused as K
+    torch.manual_seed(3)
+    n = 3
+    x = (torch.randn(n, c, *hw) * 2).bfloat16()
+    g = torch.rand(n, c, 1, 1)
+    acts = {0: lambda t: t, 1: torch.relu, 2: TF.relu6, 3: TF.silu}
+    xo, go = x.float().requires_grad_(True), g.clone().requires_grad_(True)
+    yo = acts[act](xo * go)
+    up = torch.randn_like(yo).bfloat16()
+    yo.backward(up.float())
+    xd = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    gd = g.cuda().requires_grad_(True)
+    y = K.gate_act(xd, gd, act)
+    assert y.dtype == torch.bfloat16 and y.shape == yo.shape
+    y.backward(up.cuda())
+    assert rel_l2(y, yo) < 4e-3
+    assert rel_l2(xd.grad, xo.grad) < 6e-3
+    assert rel_l2(gd.grad, go.grad) < 2e-3 and gd.grad.shape == gd.shape
+    pooled = K.global_avg_pool_flat(xd.detach())
+    assert rel_l2(pooled, x.float().mean((2, 3))) < 4e-3
