@@ -192,9 +192,11 @@ __global__ void im2col_c3k3_kernel(const T* __restrict__ x, __nv_bfloat16* __res
   const size_t tstride = (size_t)gridDim.x * blockDim.x;
   const size_t plane = (size_t)H * W;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += tstride) {
-    const int wo = (int)(i % Wo);
-    const int ho = (int)((i / Wo) % Ho);
-    const size_t n = i / ((size_t)Wo * Ho);
+    const unsigned iu = (unsigned)i;              // total < 2^32 checked by the launcher: 32-bit divisions
+    const unsigned t1 = iu / (unsigned)Wo;
+    const int wo = (int)(iu - t1 * (unsigned)Wo);
+    const size_t n = t1 / (unsigned)Ho;
+    const int ho = (int)(t1 - (unsigned)n * (unsigned)Ho);
     const T* xn = x + n * 3 * plane;
     float v[32];
 #pragma unroll
@@ -317,7 +319,7 @@ int hb_im2col_smallc_bf16(const void* x, void* col, int N, int C, int H, int W, 
   const int grid = stream_grid(n, 256, 16);
   cudaStream_t st = (cudaStream_t)stream;
   __nv_bfloat16* c = (__nv_bfloat16*)col;
-  if (C == 3 && R == 3 && S == 3 && Kp == 32) {
+  if (C == 3 && R == 3 && S == 3 && Kp == 32 && n < 0xffffffffull) {
     switch (dtype) {
       case HB_DTYPE_F32: im2col_c3k3_kernel<float><<<grid, 256, 0, st>>>((const float*)x, c, N, H, W, Ho, Wo, stride, pad); break;
       case HB_DTYPE_BF16: im2col_c3k3_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, c, N, H, W, Ho, Wo, stride, pad); break;

@@ -97,7 +97,9 @@ __global__ void __launch_bounds__(kThreads) dw_bwd_data_kernel(const __nv_bfloat
 // kernels), the block's slab of the filter sits in shared memory (float4 reads). The generic kernels above
 // re-read 72 scalar weights per output vector and recompute the channel group of every element: 9x slower than the
 // HBM time on the ReXNet expansions (profiles/r01_rexnet_launches.md).
-template <bool kBackward>
+// kStride: 1 or 2 known at compile time (the backward index arithmetic divides by the stride: a runtime divisor costs
+// ~40 instructions per tap and made the data-gradient pass 2.4x slower than the forward one); 0 = runtime stride.
+template <bool kBackward, int kStride>
 __global__ void __launch_bounds__(kThreads) dw3x3_kernel(const __nv_bfloat16* __restrict__ src, const float* __restrict__ w,
                                                          const float* __restrict__ bias, __nv_bfloat16* __restrict__ dst,
                                                          DwParams p, int cg_t, int rows_t) {
@@ -117,14 +119,18 @@ __global__ void __launch_bounds__(kThreads) dw3x3_kernel(const __nv_bfloat16* __
   float b[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) b[j] = (!kBackward && bias) ? bias[cg * 8 + j] : 0.f;
+  const int stride = kStride > 0 ? kStride : p.stride;
   const int OH = kBackward ? p.H : p.Ho, OW = kBackward ? p.W : p.Wo;   // grid walked by this kernel
   const int IH = kBackward ? p.Ho : p.H, IW = kBackward ? p.Wo : p.W;   // grid of src
   const long long M = (long long)p.N * OH * OW;
   const long long stride_m = (long long)gridDim.x * rows_t;
   for (long long m = (long long)blockIdx.x * rows_t + ty; m < M; m += stride_m) {
-    const int ow = (int)(m % OW);
-    const int oh = (int)((m / OW) % OH);
-    const long long n = m / ((long long)OW * OH);
+    // 32-bit index arithmetic (the launcher checks M < 2^31): 64-bit runtime divisions cost ~100 instructions each
+    const unsigned mu = (unsigned)m;
+    const unsigned t1 = mu / (unsigned)OW;
+    const int ow = (int)(mu - t1 * (unsigned)OW);
+    const long long n = t1 / (unsigned)OH;
+    const int oh = (int)(t1 - (unsigned)n * (unsigned)OH);
     const __nv_bfloat16* sn = src + n * IH * IW * p.C + cg * 8;
     Vec16<__nv_bfloat16> v[9];
     bool ok[9];
@@ -135,12 +141,12 @@ __global__ void __launch_bounds__(kThreads) dw3x3_kernel(const __nv_bfloat16* __
         int ih, iw;
         bool good;
         if (!kBackward) {
-          ih = oh * p.stride + r - p.pad; iw = ow * p.stride + s2 - p.pad;
+          ih = oh * stride + r - p.pad; iw = ow * stride + s2 - p.pad;
           good = ih >= 0 && ih < IH && iw >= 0 && iw < IW;
         } else {
           const int hn = oh + p.pad - r, wn = ow + p.pad - s2;
-          good = hn >= 0 && wn >= 0 && (p.stride == 1 || ((hn % p.stride) == 0 && (wn % p.stride) == 0));
-          ih = hn / p.stride; iw = wn / p.stride;
+          good = hn >= 0 && wn >= 0 && (stride == 1 || ((hn % stride) == 0 && (wn % stride) == 0));
+          ih = hn / stride; iw = wn / stride;
           good = good && ih < IH && iw < IW;
         }
         ok[r * 3 + s2] = good;
@@ -198,9 +204,11 @@ __global__ void __launch_bounds__(kThreads) dw_bwd_weight_kernel(const __nv_bflo
     const long long M = (long long)p.N * p.Ho * p.Wo;
     const long long stride_m = (long long)gridDim.x * rows_t;
     for (long long m = (long long)blockIdx.x * rows_t + ty; m < M; m += stride_m) {
-      const int wo = (int)(m % p.Wo);
-      const int ho = (int)((m / p.Wo) % p.Ho);
-      const int n = (int)(m / ((long long)p.Wo * p.Ho));
+      const unsigned mu = (unsigned)m;            // M < 2^31 checked by the launcher
+      const unsigned t1 = mu / (unsigned)p.Wo;
+      const int wo = (int)(mu - t1 * (unsigned)p.Wo);
+      const int n = (int)(t1 / (unsigned)p.Ho);
+      const int ho = (int)(t1 - (unsigned)n * (unsigned)p.Ho);
       float g[8];
       if constexpr (KS == 3) {
         // all 10 loads of the pixel are issued before the first use
@@ -289,11 +297,15 @@ int hb_dwconv_fwd_bf16(const void* x, const float* w, const float* bias, void* y
   DwParams p = make_params(N, H, W, C, K, stride, pad);
   const long long total = (long long)N * p.Ho * p.Wo * (C / 8);
   if (total <= 0) return 0;
-  if (K == 3) {
+  if (K == 3 && (long long)N * p.Ho * p.Wo < 0x7fffffffLL) {
     int cg_t, rows_t;
     const dim3 grid = dw_grid((long long)N * p.Ho * p.Wo, C / 8, cg_t, rows_t, 4);
-    dw3x3_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, w, bias, (__nv_bfloat16*)y, p,
-                                                                       cg_t, rows_t);
+    const __nv_bfloat16* xb = (const __nv_bfloat16*)x;
+    __nv_bfloat16* yb = (__nv_bfloat16*)y;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (stride == 1) dw3x3_kernel<false, 1><<<grid, kThreads, 0, st>>>(xb, w, bias, yb, p, cg_t, rows_t);
+    else if (stride == 2) dw3x3_kernel<false, 2><<<grid, kThreads, 0, st>>>(xb, w, bias, yb, p, cg_t, rows_t);
+    else dw3x3_kernel<false, 0><<<grid, kThreads, 0, st>>>(xb, w, bias, yb, p, cg_t, rows_t);
     HB_LAUNCH_CHECK();
     return 0;
   }
@@ -309,11 +321,15 @@ int hb_dwconv_bwd_data_bf16(const void* dy, const float* w, void* dx, int N, int
   DwParams p = make_params(N, H, W, C, K, stride, pad);
   const long long total = (long long)N * H * W * (C / 8);
   if (total <= 0) return 0;
-  if (K == 3) {
+  if (K == 3 && (long long)N * H * W < 0x7fffffffLL) {
     int cg_t, rows_t;
     const dim3 grid = dw_grid((long long)N * H * W, C / 8, cg_t, rows_t, 3);
-    dw3x3_kernel<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, w, nullptr, (__nv_bfloat16*)dx, p,
-                                                                      cg_t, rows_t);
+    const __nv_bfloat16* dyb = (const __nv_bfloat16*)dy;
+    __nv_bfloat16* dxb = (__nv_bfloat16*)dx;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (stride == 1) dw3x3_kernel<true, 1><<<grid, kThreads, 0, st>>>(dyb, w, nullptr, dxb, p, cg_t, rows_t);
+    else if (stride == 2) dw3x3_kernel<true, 2><<<grid, kThreads, 0, st>>>(dyb, w, nullptr, dxb, p, cg_t, rows_t);
+    else dw3x3_kernel<true, 0><<<grid, kThreads, 0, st>>>(dyb, w, nullptr, dxb, p, cg_t, rows_t);
     HB_LAUNCH_CHECK();
     return 0;
   }
@@ -338,6 +354,7 @@ int hb_dwconv_bwd_weight_bf16(const void* x, const void* dy, float* dw, float* d
   const int rows_t = kThreads / cg_t;
   const int slabs = (cv + cg_t - 1) / cg_t;
   const long long M = (long long)N * p.Ho * p.Wo;
+  if (M >= 0x7fffffffLL) return (int)cudaErrorInvalidValue;
   long long gx = (M + rows_t * 8 - 1) / (rows_t * 8);
   long long cap = (HB_NUM_SMS * 4) / slabs;
   if (cap < 1) cap = 1;
