@@ -100,6 +100,46 @@ __global__ void __launch_bounds__(128, 1) mma_rate_probe_kernel(int N, int count
 }
 }  // namespace
 
+// ---- probe 3: the same with the A window starting `shift_rows` 128-byte rows into the (128B-swizzled) buffer, like the
+// tap windows of conv_rows.cu: does a start that is not a multiple of the 1024-byte swizzle atom cost fetch bandwidth?
+namespace {
+__global__ void __launch_bounds__(128, 1) mma_shift_rate_probe_kernel(int N, int count, int shift_rows, int cycle) {
+  extern __shared__ __align__(1024) uint8_t smem_raw3[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw3) + 1023) & ~uintptr_t(1023));
+  uint64_t* done = reinterpret_cast<uint64_t*>(smem + 96 * 1024);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done + 1);
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 96 * 1024 / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) { tc::mbar_init(done, 1); tc::fence_barrier_init(); }
+  if (warp == 0) tc::tmem_alloc(tmem_ptr, 512);
+  tc::fence_proxy_async();
+  tc::tc_fence_before(); __syncthreads(); tc::tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = tc::make_idesc_bf16(128, N, 0, 0);
+    const uint32_t dhi = tc::desc_hi(1024, tc::kLayoutSW128);
+    const uint32_t a_lo = tc::desc_lo(tc::smem_u32(smem), 16);
+    const uint32_t b_lo = tc::desc_lo(tc::smem_u32(smem + 64 * 1024), 16);
+    for (int i = 0; i < count; ++i) {
+      // cycle > 0: walk `cycle` different windows (shift_rows apart) like consecutive taps; else always the same window
+      const int w = cycle > 0 ? (i / 4) % cycle : 1;
+      tc::umma_f16_lh(tmem, a_lo + (uint32_t)(w * shift_rows * 8) + 2 * (i & 3), dhi, b_lo + 2 * (i & 3), dhi, idesc, 1u);
+    }
+    tc::umma_commit(done);
+    tc::mbar_wait(done, 0);
+  }
+  tc::tc_fence_before(); __syncthreads();
+  if (warp == 0) { tc::tc_fence_after(); tc::tmem_dealloc(tmem, 512); }
+}
+}  // namespace
+
+extern "C" int hb_dev_mma_shift_rate_probe(int N, int count, int shift_rows, int cycle, int ctas, void* stream) {
+  cudaFuncSetAttribute(mma_shift_rate_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  mma_shift_rate_probe_kernel<<<ctas, 128, 98 * 1024, (cudaStream_t)stream>>>(N, count, shift_rows, cycle);
+  HB_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int hb_dev_mma_rate_probe(int N, int count, int distinct_acc, int ctas, void* stream) {
   cudaFuncSetAttribute(mma_rate_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
   mma_rate_probe_kernel<<<ctas, 128, 70 * 1024, (cudaStream_t)stream>>>(N, count, distinct_acc);
