@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(kThreads) dw_bwd_data_kernel(const __nv_bfloat
 // kStride: 1 or 2 known at compile time (the backward index arithmetic divides by the stride: a runtime divisor costs
 // ~40 instructions per tap and made the data-gradient pass 2.4x slower than the forward one); 0 = runtime stride.
 template <bool kBackward, int kStride>
-__global__ void __launch_bounds__(kThreads) dw3x3_kernel(const __nv_bfloat16* __restrict__ src, const float* __restrict__ w,
+__global__ void __launch_bounds__(kThreads, 3) dw3x3_kernel(const __nv_bfloat16* __restrict__ src, const float* __restrict__ w,
                                                          const float* __restrict__ bias, __nv_bfloat16* __restrict__ dst,
                                                          DwParams p, int cg_t, int rows_t) {
   // forward:  src = x [N,H,W,C],   dst = y  [N,Ho,Wo,C]: y[ho,wo]  = b + sum_{r,s} x[ho*st+r-pad, wo*st+s-pad] * w[r,s]
@@ -186,7 +186,7 @@ inline dim3 dw_grid(long long M, int cv, int& cg_t, int& rows_t, int per_sm) {
 // dw[c,r,s] = sum_{n,ho,wo} dy * x_shifted ; db[c] = sum dy.  sums: double [C][KK+1] (last column = bias grad)
 // block geometry as in the BN kernels: tx = channel group within a 32-group slab, ty = pixel lane
 template <int KS>
-__global__ void __launch_bounds__(kThreads) dw_bwd_weight_kernel(const __nv_bfloat16* __restrict__ x,
+__global__ void __launch_bounds__(kThreads, KS == 3 ? 2 : 1) dw_bwd_weight_kernel(const __nv_bfloat16* __restrict__ x,
                                                                  const __nv_bfloat16* __restrict__ dy, double* sums,
                                                                  DwParams p, int cg_t, int rows_t) {
   constexpr int KK = KS * KS;
@@ -211,25 +211,28 @@ __global__ void __launch_bounds__(kThreads) dw_bwd_weight_kernel(const __nv_bflo
       const int ho = (int)(t1 - (unsigned)n * (unsigned)p.Ho);
       float g[8];
       if constexpr (KS == 3) {
-        // all 10 loads of the pixel are issued before the first use
-        Vec16<__nv_bfloat16> gv = ld16(dy + m * p.C + cg * 8), xv9[9];
-        bool ok[9];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-#pragma unroll
-          for (int s = 0; s < 3; ++s) {
-            const int hi = ho * p.stride + r - p.pad, wi = wo * p.stride + s - p.pad;
-            ok[r * 3 + s] = hi >= 0 && hi < p.H && wi >= 0 && wi < p.W;
-            if (ok[r * 3 + s]) xv9[r * 3 + s] = ld16(x + (((long long)n * p.H + hi) * p.W + wi) * p.C + cg * 8);
-          }
-        }
+        // loads are issued one filter row (3 taps) ahead of their use: 80 accumulators leave no room for all 9 vectors
+        Vec16<__nv_bfloat16> gv = ld16(dy + m * p.C + cg * 8);
 #pragma unroll
         for (int j = 0; j < 8; ++j) { g[j] = __bfloat162float(gv.v[j]); acc[KK][j] += g[j]; }
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
-          if (ok[k]) {
+        for (int r = 0; r < 3; ++r) {
+          const int hi = ho * p.stride + r - p.pad;
+          const bool hok = hi >= 0 && hi < p.H;
+          Vec16<__nv_bfloat16> xv3[3];
+          bool ok[3];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[k][j] = fmaf(g[j], __bfloat162float(xv9[k].v[j]), acc[k][j]);
+          for (int s = 0; s < 3; ++s) {
+            const int wi = wo * p.stride + s - p.pad;
+            ok[s] = hok && wi >= 0 && wi < p.W;
+            if (ok[s]) xv3[s] = ld16(x + (((long long)n * p.H + hi) * p.W + wi) * p.C + cg * 8);
+          }
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            if (ok[s]) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[r * 3 + s][j] = fmaf(g[j], __bfloat162float(xv3[s].v[j]), acc[r * 3 + s][j]);
+            }
           }
         }
         continue;
@@ -299,7 +302,7 @@ int hb_dwconv_fwd_bf16(const void* x, const float* w, const float* bias, void* y
   if (total <= 0) return 0;
   if (K == 3 && (long long)N * p.Ho * p.Wo < 0x7fffffffLL) {
     int cg_t, rows_t;
-    const dim3 grid = dw_grid((long long)N * p.Ho * p.Wo, C / 8, cg_t, rows_t, 4);
+    const dim3 grid = dw_grid((long long)N * p.Ho * p.Wo, C / 8, cg_t, rows_t, 3);
     const __nv_bfloat16* xb = (const __nv_bfloat16*)x;
     __nv_bfloat16* yb = (__nv_bfloat16*)y;
     cudaStream_t st = (cudaStream_t)stream;
