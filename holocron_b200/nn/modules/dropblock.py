@@ -1,27 +1,31 @@
-"""DropBlock2d module — mirrors holocron/nn/modules/dropblock.py:14-41."""
+"""``DropBlock2d`` on the fused mask / apply kernels (csrc/dropblock.cu).
+
+Public surface of holocron/nn/modules/dropblock.py:14-41: constructor ``(p=0.1, block_size=7, inplace=False)``, attributes
+``p`` / ``block_size`` / ``inplace``, the ``repr`` string, identity in eval mode.
+"""
 from torch import Tensor, nn
 
-from .. import functional as F
+from ..functional import dropblock2d
 
 __all__ = ["DropBlock2d"]
 
+_REPR_FIELDS = ("p", "block_size", "inplace")
+
 
 class DropBlock2d(nn.Module):
-    """DropBlock (https://arxiv.org/abs/1810.12890). As in the reference the module hands ``p / block_size**2`` to the
-    functional, which divides by ``block_size**2`` again (effective seed probability ``p / block_size**4``)."""
+    """Drops contiguous ``block_size`` x ``block_size`` regions of every feature map (Ghiasi et al., 2018).
+
+    Reference quirk kept on purpose: the module already divides ``p`` by the block area before calling the functional,
+    which divides by the block area once more - seeds are therefore drawn with probability ``p / block_size**4``.
+    """
 
     def __init__(self, p: float = 0.1, block_size: int = 7, inplace: bool = False) -> None:
         super().__init__()
-        self.p = p
-        self.block_size = block_size
-        self.inplace = inplace
-
-    @property
-    def drop_prob(self) -> float:
-        return self.p / self.block_size**2
-
-    def forward(self, x: Tensor) -> Tensor:
-        return F.dropblock2d(x, self.drop_prob, self.block_size, self.inplace, self.training)
+        self.p, self.block_size, self.inplace = p, block_size, inplace
 
     def extra_repr(self) -> str:
-        return f"p={self.p}, block_size={self.block_size}, inplace={self.inplace}"
+        return ", ".join(f"{name}={getattr(self, name)}" for name in _REPR_FIELDS)
+
+    def forward(self, x: Tensor) -> Tensor:
+        seed_prob = self.p / (self.block_size * self.block_size)
+        return dropblock2d(x, seed_prob, self.block_size, self.inplace, self.training)
