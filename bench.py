@@ -387,10 +387,10 @@ def main():
     if rank == 0:
         # ---- roofline leg: per-launch CUDA-event timing of the tensor-core conv kernels (one extra step) ----
         K.KERNEL_TIMER = []
-        # park the stream behind a ~40 ms spin kernel first: the whole step is then enqueued before its first kernel runs,
+        # park the stream behind a ~130 ms spin kernel first: the whole step is then enqueued before its first kernel runs,
         # so the per-launch event pairs bracket GPU time only (otherwise the host gap between "record start" and the
         # launch it precedes is counted whenever the host is slower than the GPU)
-        torch.cuda._sleep(int(8e7))
+        torch.cuda._sleep(int(2.5e8))
         eager_step(x_dev, t_dev, collective=False)   # rank 0 only: no collective may be issued here
         torch.cuda.synchronize()
         recs = K.KERNEL_TIMER
