@@ -119,6 +119,9 @@ class _PackTable:
                 continue
             if e.w_krsc is None:          # non-channels_last master: needs its own permuted copy, packed individually
                 continue
+            if e.w_krsc.data_ptr() != w.data_ptr():   # the parameter moved to new storage: its view here is stale
+                del _pack_cache[k]
+                continue
             ents.append((e, w))
         if len(ents) < 2:
             return False
