@@ -191,3 +191,39 @@ def test_multi_tensor_filter_packing_matches_single():
         assert torch.equal(wf.view(torch.int16), wf1.view(torch.int16))
         if wd is not None:
             assert torch.equal(wd.view(torch.int16), wd1.view(torch.int16))
+
+
+def test_filter_pack_table_follows_parameter_updates_and_moves():
+    """The host-side packing cache (holocron_b200/nn/_fused.py::_PackTable): in-place parameter updates are picked up by
+    ONE multi-tensor launch for all registered filters, and a parameter that moved to new storage is re-registered
+    instead of being re-packed from its stale view. Scaling fp32 master weights by 2 is exact in bf16, so outputs must
+    double exactly."""
+    from holocron_b200.nn import _fused as K
+    torch.manual_seed(0)
+    convs = [torch.nn.Conv2d(16, 32, 3, padding=1, bias=False).cuda().to(memory_format=torch.channels_last) for _ in range(3)]
+    x = torch.randn(2, 16, 8, 8, device="cuda")
+
+    def run():
+        with torch.no_grad():
+            return [K.conv2d(x, c.weight, None, 1, 1).float() for c in convs]
+
+    y0 = run()                                   # first use: every filter packed on its own and registered
+    with torch.no_grad():
+        for c in convs:
+            c.weight.mul_(2.0)                   # in-place update: version bump, same storage
+    before = lib().hb_launch_count()
+    y1 = run()
+    launches = lib().hb_launch_count() - before
+    assert launches == 1 + len(convs)            # one multi-tensor packing launch + one convolution per layer
+    for a, b in zip(y0, y1):
+        assert torch.equal(b, 2 * a)
+    with torch.no_grad():                        # move one parameter to fresh storage, then update all of them again
+        convs[1].weight.data = (convs[1].weight.data * 0.5).clone(memory_format=torch.channels_last)
+    y2 = run()
+    assert torch.equal(y2[1], y0[1]) and torch.equal(y2[0], y1[0])
+    with torch.no_grad():
+        for c in convs:
+            c.weight.mul_(2.0)
+    y3 = run()
+    for a, b in zip(y2, y3):
+        assert torch.equal(b, 2 * a)
