@@ -164,7 +164,9 @@ class YoloLayer(nn.Module):
         noobj_mask[img, cell_y, cell_x, :] = False
         for idx in range(b):
             if counts[idx] > 0:
-                ious, gt_idx = box_iou(pred_boxes[idx][obj_mask[idx]].detach(), gt_boxes[idx].float()).max(dim=1)
+                # no detach: like the reference (yolov4.py:380-382) the objectness target stays attached to the predicted
+                # boxes, so obj_loss also back-propagates through the IoU
+                ious, gt_idx = box_iou(pred_boxes[idx][obj_mask[idx]], gt_boxes[idx].float()).max(dim=1)
                 target_o[idx][obj_mask[idx]] = ious
                 sel = obj_mask[idx].nonzero(as_tuple=True)
                 target_scores[idx][sel[0], sel[1], sel[2], gt_labels[idx][gt_idx]] = 1.0
