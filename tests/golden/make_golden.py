@@ -258,7 +258,7 @@ def gen_models():
     torch.save(d, OUT / "models.pt")
 
 
-if __name__ == "__main__" and "--zoo" not in sys.argv:
+if __name__ == "__main__" and "--zoo" not in sys.argv and "--api" not in sys.argv:
     gen_activations()
     gen_losses()
     gen_boxes()
@@ -334,3 +334,47 @@ def gen_zoo():
 if __name__ == "__main__" and "--zoo" in sys.argv:
     gen_zoo()
     print("zoo.pt", (OUT / "zoo.pt").stat().st_size)
+
+
+# ------------------------------------------------------------------------------------------------ public API surface
+API_SURFACE = {
+    "nn.functional": ["hard_mish", "nl_relu", "focal_loss", "poly_loss", "dice_loss", "norm_conv2d", "add2d", "dropblock2d"],
+    "nn": ["HardMish", "NLReLU", "FReLU", "NormConv2d", "Add2d", "SlimConv2d", "FocalLoss", "PolyLoss", "DiceLoss", "DropBlock2d",
+           "GlobalAvgPool2d", "SPP"],
+    "ops.boxes": ["box_giou", "diou_loss", "ciou_loss", "iou_penalty", "aspect_ratio", "aspect_ratio_consistency"],
+    "optim": ["AdaBelief", "LAMB", "TAdam"],
+    "models": ["repvgg_a0", "repvgg_a1", "repvgg_a2", "repvgg_b0", "repvgg_b1", "repvgg_b2", "repvgg_b3", "rexnet1_0x", "rexnet1_3x",
+               "rexnet1_5x", "rexnet2_0x", "rexnet2_2x", "darknet24", "darknet19", "darknet53", "cspdarknet53", "cspdarknet53_mish"],
+    "models.detection": ["yolov4"],
+    "models.segmentation": ["unet3p"],
+}
+
+
+def describe_signature(obj):
+    """[(name, kind, repr(default))] of a callable / of a class' constructor - annotations left out on purpose."""
+    import inspect
+    target = obj.__init__ if inspect.isclass(obj) else obj
+    out = []
+    for name, p in inspect.signature(target).parameters.items():
+        if name == "self":
+            continue
+        default = None if p.default is inspect.Parameter.empty else repr(p.default)
+        out.append([name, p.kind.name, default])
+    return out
+
+
+def gen_api():
+    """Signatures of the reference's public hot-path surface -> tests/golden/api_signatures.json."""
+    import functools
+    import json
+    d = {}
+    for mod_path, names in API_SURFACE.items():
+        mod = functools.reduce(getattr, mod_path.split("."), holocron)
+        for name in names:
+            d[f"{mod_path}.{name}"] = describe_signature(getattr(mod, name))
+    (OUT / "api_signatures.json").write_text(json.dumps(d, indent=1, sort_keys=True))
+
+
+if __name__ == "__main__" and "--api" in sys.argv:
+    gen_api()
+    print("api_signatures.json", (OUT / "api_signatures.json").stat().st_size)

@@ -1,0 +1,48 @@
+"""Drop-in boundary: names, parameter order, kinds and defaults of the public hot-path surface must equal the
+reference's, recorded from the unmodified reference by `tests/golden/make_golden.py --api`. Annotations are not compared."""
+import functools
+import inspect
+import json
+
+import holocron_b200 as hb
+
+from conftest import GOLDEN
+
+
+def _describe(obj):
+    target = obj.__init__ if inspect.isclass(obj) else obj
+    out = []
+    for name, p in inspect.signature(target).parameters.items():
+        if name == "self":
+            continue
+        out.append([name, p.kind.name, None if p.default is inspect.Parameter.empty else repr(p.default)])
+    return out
+
+
+# deliberate, documented deviations: (path, parameter) -> our default
+DEVIATIONS = {("models.detection.yolov4", "pretrained_backbone"): "False"}   # no network: nothing to download
+
+
+def test_public_signatures_match_reference():
+    ref = json.loads((GOLDEN / "api_signatures.json").read_text())
+    assert len(ref) >= 45
+    problems = []
+    for path, sig in ref.items():
+        *mods, name = path.split(".")
+        try:
+            obj = getattr(functools.reduce(getattr, mods, hb), name)
+        except AttributeError:
+            problems.append(f"{path}: missing")
+            continue
+        ours = _describe(obj)
+        for p in sig:
+            if DEVIATIONS.get((path, p[0])) is not None:
+                p[2] = DEVIATIONS[(path, p[0])]
+        # an optimizer may accept the reference's (Adam's) extra keyword switches through **kwargs
+        ref_core = [p for p in sig if p[1] != "VAR_KEYWORD"]
+        ours_core = [p for p in ours if p[1] != "VAR_KEYWORD"]
+        if ours_core[:len(ref_core)] != ref_core and ref_core[:len(ours_core)] != ours_core:
+            problems.append(f"{path}: reference {sig} != ours {ours}")
+        elif len(ours_core) < len(ref_core) and not any(p[1] == "VAR_KEYWORD" for p in ours):
+            problems.append(f"{path}: parameters {ref_core[len(ours_core):]} not accepted")
+    assert not problems, "\n".join(problems)
