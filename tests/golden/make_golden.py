@@ -378,3 +378,36 @@ def gen_api():
 if __name__ == "__main__" and "--api" in sys.argv:
     gen_api()
     print("api_signatures.json", (OUT / "api_signatures.json").stat().st_size)
+
+
+def describe_state_dict(model):
+    """(number of entries, total elements, sha1 over 'key:shape:dtype' lines, sha1 over the seeded VALUES)."""
+    import hashlib
+    sd = model.state_dict()
+    lines = [f"{k}:{tuple(v.shape)}:{str(v.dtype).replace('torch.', '')}" for k, v in sd.items()]
+    h_vals = hashlib.sha1()
+    for v in sd.values():
+        h_vals.update(v.detach().contiguous().cpu().numpy().tobytes())
+    return {"entries": len(lines), "numel": int(sum(v.numel() for v in sd.values())),
+            "layout_sha1": hashlib.sha1("\n".join(lines).encode()).hexdigest(), "values_sha1": h_vals.hexdigest(),
+            "first": lines[:3], "last": lines[-3:]}
+
+
+def gen_state_dicts():
+    """state_dict layout and seeded initial values of every factory -> tests/golden/state_dicts.json (checkpoint
+    compatibility + init RNG order: torch.manual_seed(0) before each constructor)."""
+    import json
+    d = {}
+    for name in API_SURFACE["models"]:
+        torch.manual_seed(0)
+        d[name] = describe_state_dict(getattr(holocron.models, name)(num_classes=10))
+    torch.manual_seed(0)
+    d["yolov4"] = describe_state_dict(holocron.models.detection.yolov4(pretrained_backbone=False, num_classes=80))
+    torch.manual_seed(0)
+    d["unet3p"] = describe_state_dict(holocron.models.segmentation.unet3p(num_classes=21))
+    (OUT / "state_dicts.json").write_text(json.dumps(d, indent=1, sort_keys=True))
+
+
+if __name__ == "__main__" and "--api" in sys.argv:
+    gen_state_dicts()
+    print("state_dicts.json", (OUT / "state_dicts.json").stat().st_size)
