@@ -142,10 +142,10 @@ class ClockSampler:
                 "source": "nvidia-smi"}
 
 
-def synthetic_batch(batch: int, seed: int, device):
+def synthetic_batch(batch: int, seed: int, device, size: int = 224):
     """ImageNet-like synthetic batch: U[0,1) pixels normalised with the ImageNet mean/std, uniform random labels."""
     g = torch.Generator(device="cpu").manual_seed(seed)
-    x = torch.rand(batch, 3, 224, 224, generator=g)
+    x = torch.rand(batch, 3, size, size, generator=g)
     mean = torch.tensor(IMAGENET_MEAN).view(1, 3, 1, 1)
     std = torch.tensor(IMAGENET_STD).view(1, 3, 1, 1)
     x = (x - mean) / std
@@ -153,11 +153,77 @@ def synthetic_batch(batch: int, seed: int, device):
     return x.to(device), t.to(device)
 
 
+# ------------------------------------------------------------------------------------------------ workloads
+class Workload:
+    """One BASELINE.json configuration: model factory, synthetic batch and loss."""
+
+    def __init__(self, key: str):
+        self.key = key
+        table = {
+            # key: (model factory, kwargs, default batch / GPU, image size, CUDA-graph capturable, description)
+            "repvgg_a0": ("repvgg_a0", {"num_classes": NUM_CLASSES}, 256, 224, True,
+                          "repvgg_a0 (train form, 1000 classes) 224x224 bf16 train step: fwd + CE(label_smoothing=0.1) + bwd + "
+                          "AdaBelief(lr=1e-3, betas=(0.95,0.99), eps=1e-6)"),
+            "rexnet1_0x": ("rexnet1_0x", {"num_classes": NUM_CLASSES}, 256, 224, True,
+                           "rexnet1_0x 224x224 bf16 train step (BASELINE configs[1]): fwd + CE(label_smoothing=0.1) + bwd + AdaBelief"),
+            "repvgg_a1": ("repvgg_a1", {"num_classes": NUM_CLASSES}, 512, 224, True,
+                          "repvgg_a1 224x224 bf16 train step (BASELINE configs[2]): fwd + CE(label_smoothing=0.1) + bwd + AdaBelief, "
+                          "batch 512/GPU"),
+            "yolov4": ("yolov4", {"num_classes": 80}, 16, 512, False,
+                       "yolov4 (CSP-Darknet53) 512x512 detection train step (BASELINE configs[3]): fwd + CIoU/objectness/class "
+                       "losses + bwd + AdaBelief; synthetic COCO-like boxes (1-19 per image)"),
+            "unet3p": ("unet3p", {"num_classes": 21}, 16, 256, True,
+                       "unet3p 256x256 segmentation train step (BASELINE configs[4]): fwd + DiceLoss(softmax, one-hot) + bwd + "
+                       "AdaBelief; synthetic masks"),
+        }
+        self.factory, self.kwargs, self.batch, self.size, self.graphable, self.desc = table[key]
+        self.metric = METRIC if key == "repvgg_a0" else f"images/sec {key} {self.size}^2 bf16 train"
+
+    def model(self, hb, dev):
+        torch.manual_seed(0)
+        m = getattr(hb.models, self.factory)(**self.kwargs)
+        return m.to(dev).to(memory_format=torch.channels_last).train()
+
+    def host_batch(self, batch: int, seed: int):
+        """Synthetic batch on the HOST (pinned); structure depends on the task."""
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        if self.key in ("repvgg_a0", "rexnet1_0x", "repvgg_a1"):
+            x, t = synthetic_batch(batch, seed, "cpu", self.size)
+            return [x.pin_memory(), t.pin_memory()]
+        x = torch.rand(batch, 3, self.size, self.size, generator=g)
+        if self.key == "unet3p":
+            mask = torch.randint(0, 21, (batch, self.size, self.size), generator=g)
+            return [x.pin_memory(), mask.pin_memory()]
+        # yolov4: n ~ U{1..19} boxes per image, xy1 ~ U[0,0.8), wh ~ U[0.05,0.2), clipped to [0,1] (SURVEY §8d);
+        # padded to 20 rows per image, the row counts stay on the host (they define tensor shapes)
+        counts = torch.randint(1, 20, (batch,), generator=g)
+        xy = torch.rand(batch, 20, 2, generator=g) * 0.8
+        wh = torch.rand(batch, 20, 2, generator=g) * 0.15 + 0.05
+        boxes = torch.cat([xy, (xy + wh).clamp(max=1.0)], -1)
+        labels = torch.randint(0, 80, (batch, 20), generator=g)
+        self.counts = counts.tolist()
+        return [x.pin_memory(), boxes.pin_memory(), labels.pin_memory()]
+
+    def loss(self, model, hbF, *batch):
+        if self.key in ("repvgg_a0", "rexnet1_0x", "repvgg_a1"):
+            x, t = batch
+            return F.cross_entropy(model(x), t, label_smoothing=0.1)
+        if self.key == "unet3p":
+            x, mask = batch
+            out = model(x)
+            onehot = F.one_hot(mask, 21).movedim(-1, 1).float()
+            return hbF.dice_loss(torch.softmax(out.float(), 1), onehot)
+        x, boxes, labels = batch
+        target = [{"boxes": boxes[i, :c], "labels": labels[i, :c]} for i, c in enumerate(self.counts)]
+        losses = model(x, target)
+        return sum(losses.values())
+
+
 # ------------------------------------------------------------------------------------------------ reference arm
 def run_reference(args, rank):
     """The reference algorithm for the same step (oracle = CPU restatement of Holocron's RepVGG + AdaBelief on stock
     torch CPU kernels, pinned to the reference by tests/golden) timed on the host cores. Each step is a bounded
-    sample of the workload (a 16-image batch instead of 256)."""
+    sample of the workload (an 8-image batch instead of 256)."""
     if rank != 0:
         return
     from oracle.models import RepVGGOracle
@@ -196,38 +262,6 @@ def run_reference(args, rank):
                          "sample": f"{sample}-image batches, {args.steps} steps (full workload: 256/GPU)"},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
-
-
-def secondary_rexnet(hb, GradBucket, GraphedTrainStep, x_dev, t_dev, dev, steps: int = 10):
-    """ReXNet-1.0x 224^2 bf16 training step on the same synthetic batch (BASELINE.json configs[1]): CUDA-graph replay of
-    forward + CE + backward + AdaBelief, device-timed with CUDA events."""
-    torch.manual_seed(0)
-    model = hb.models.rexnet1_0x(num_classes=NUM_CLASSES).to(dev).to(memory_format=torch.channels_last).train()
-    bucket = GradBucket(model.parameters())
-    opt = hb.optim.AdaBelief(model.parameters(), lr=1e-3, betas=(0.95, 0.99), eps=1e-6, capturable=True)
-
-    def step(x, t):
-        loss = F.cross_entropy(model(x), t, label_smoothing=0.1)
-        loss.backward()
-        opt.step()
-        bucket.zero_()
-        return loss
-
-    graphed = GraphedTrainStep(step, (x_dev, t_dev), warmup=3)
-    for _ in range(3):
-        graphed(x_dev, t_dev)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        loss = graphed(x_dev, t_dev)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
-    batch = x_dev.shape[0]
-    return {"workload": "rexnet1_0x 224x224 bf16 train step (BASELINE configs[1]): fwd + CE(label_smoothing=0.1) + bwd + AdaBelief, "
-                        f"batch {batch}, CUDA-graph replay, inputs resident in HBM",
-            "images_per_s": batch / ms * 1e3, "ms_per_step": ms, "steps": steps, "last_loss": float(loss.item())}
 
 
 def cpu_threads() -> int:
@@ -270,85 +304,162 @@ def cpu_baseline(budget_s: float = 20.0):
             "sample": f"{max(n, 1)} steps of an {sample}-image batch (oracle: RepVGG-A0 train step, fp32, torch CPU)"}
 
 
-# ------------------------------------------------------------------------------------------------ main arm
-def conv_algorithmic(info, kind):
-    """FLOPs and HBM bytes of one conv launch: 2*M*Cout*Cin*R*S; (in + out)*2 B + weights."""
-    m_out = info["N"] * info["Ho"] * info["Wo"]
-    flops = 2.0 * m_out * info["Cout"] * info["Cin"] * info["R"] * info["S"]
-    in_b = info["N"] * info["H"] * info["W"] * info["Cin"] * 2
-    out_b = m_out * info["Cout"] * 2
-    w_elems = info["Cout"] * info["Cin"] * info["R"] * info["S"]
-    if kind == "wgrad":
-        byts = in_b + out_b + w_elems * 4     # reads x and dy (bf16), writes fp32 dW
+def gpu_eager_baseline(batch: int, dev, steps: int = 5):
+    """The reference's own execution model on the SAME B200: stock torch eager modules
+    (cuDNN / ATen kernels), bf16 autocast, channels_last, per-tensor AdaBelief update written as the reference writes it
+    (~9 ATen launches per parameter tensor). Uses the oracle's module tree (reference algorithm, stock torch layers); it
+    is a reported baseline measured beside the product, never part of it."""
+    from oracle.models import RepVGGOracle
+    from oracle.optim import adabelief_step
+    torch.manual_seed(0)
+    model = RepVGGOracle("repvgg_a0", num_classes=NUM_CLASSES).to(dev).to(memory_format=torch.channels_last).train()
+    params = list(model.parameters())
+    state = [(torch.zeros_like(p), torch.zeros_like(p)) for p in params]
+    x, t = synthetic_batch(batch, 7, dev)
+    x = x.contiguous(memory_format=torch.channels_last)
+
+    def step(i):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = F.cross_entropy(model(x).float(), t, label_smoothing=0.1)
+        loss.backward()
+        for p, (m, s) in zip(params, state):
+            adabelief_step(p.data, p.grad, m, s, i, 1e-3, 0.95, 0.99, 1e-6)
+            p.grad = None
+
+    for i in range(1, 4):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(4 + i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"images_per_s": batch / ms * 1e3, "ms_per_step": ms, "steps": steps,
+            "what": "torch eager (cuDNN), bf16 autocast, channels_last, reference-style per-tensor AdaBelief; same step, same GPU"}
+
+
+# ------------------------------------------------------------------------------------------------ roofline leg
+FAMILIES = {
+    # timer kind -> (family label = the kernels it covers, bound)
+    "fprop": "conv_fprop_kernel+conv_rows_kernel",
+    "dgrad": "conv_fprop_kernel+conv_rows_kernel",
+    "wgrad": "conv_wgrad_kernel+conv_wgrad_rows_kernel+wgrad_reduce_kernel",
+    "bn_stats": "bn_act_fwd_kernel+bn_act_bwd_reduce_kernel+bn_act_bwd_apply_kernel",
+    "bn_fwd": "bn_act_fwd_kernel+bn_act_bwd_reduce_kernel+bn_act_bwd_apply_kernel",
+    "bn_bwd": "bn_act_fwd_kernel+bn_act_bwd_reduce_kernel+bn_act_bwd_apply_kernel",
+    "optimizer": "adabelief_kernel",
+}
+
+
+def roofline_leg(K, run_step, opt_step, n_params: int, step_ms: float, images: int, train_macs_per_image: float):
+    """Per-launch CUDA-event timing of ONE extra eager step (stream parked behind a spin kernel so that host gaps are not
+    counted) -> per-family {ms, algorithmic GFLOP / GB, achieved TFLOP/s / GB/s, fraction of the measured peak}."""
+    K.KERNEL_TIMER = []
+    torch.cuda._sleep(int(2.5e8))
+    run_step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    opt_step()
+    e1.record()
+    torch.cuda.synchronize()
+    recs = K.KERNEL_TIMER
+    K.KERNEL_TIMER = None
+    # AdaBelief: read p, g, m, s + write p, m, s = 28 B / parameter (SURVEY §8d)
+    recs.append(("optimizer", {"flops": 0.0, "bytes": 28.0 * n_params, "launches": 1, "shape": ("adabelief", n_params)}, e0, e1))
+    peaks = measured_peaks()
+    fam, by_shape = {}, {}
+    for kind, info, a, b in recs:
+        ms = a.elapsed_time(b)
+        d = fam.setdefault(FAMILIES[kind], {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+        d["ms"] += ms; d["flops"] += info["flops"]; d["bytes"] += info["bytes"]; d["launches"] += info.get("launches", 1)
+        e = by_shape.setdefault((kind,) + tuple(info.get("shape", ())), [0, 0.0, 0.0])
+        e[0] += 1; e[1] += ms; e[2] += info["flops"]
+    if os.environ.get("HB_BENCH_DETAIL"):
+        for key, (cnt, t, fl) in sorted(by_shape.items(), key=lambda kv: -kv[1][1]):
+            print(f"DETAIL {key}: n={cnt} total {t:.3f} ms  {fl / max(t, 1e-9) / 1e9:.0f} TFLOP/s", file=sys.stderr)
+    per = {}
+    for name, d in fam.items():
+        t_fl = d["flops"] / (peaks["bf16_tflops"] * 1e12) * 1e3
+        t_by = d["bytes"] / (peaks["hbm_gbs"] * 1e9) * 1e3
+        tf, gb = d["flops"] / d["ms"] / 1e9, d["bytes"] / d["ms"] / 1e6
+        bound = "tensor" if t_fl > t_by else "hbm"
+        per[name] = {"ms": round(d["ms"], 3), "launches": d["launches"], "GFLOP": round(d["flops"] / 1e9, 1),
+                     "GB": round(d["bytes"] / 1e9, 3), "TFLOP/s": round(tf, 1), "GB/s": round(gb, 1), "bound": bound,
+                     "frac": round(tf / peaks["bf16_tflops"] if bound == "tensor" else gb / peaks["hbm_gbs"], 4)}
+    conv_fams = [k for k in per if k.startswith("conv_")]
+    dom = max(conv_fams or per, key=lambda k: fam[k]["ms"])
+    d = fam[dom]
+    if per[dom]["bound"] == "tensor":
+        roof = {"bound": "tensor", "achieved": d["flops"] / d["ms"] / 1e9, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s"}
     else:
-        byts = in_b + out_b + w_elems * 2
-    return flops, byts
+        roof = {"bound": "hbm", "achieved": d["bytes"] / d["ms"] / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s"}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    roof["traffic"] = None
+    roof["algorithmic_bytes"] = d["bytes"] / d["launches"]
+    roof["algorithmic_flops"] = d["flops"] / d["launches"]
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+            tk = json.load(f)["kernels"]
+        famk = [tk[k] for k in dom.split("+") if k in tk]
+        if famk:
+            roof["traffic"] = sum(k["dram_read_bytes"] + k["dram_write_bytes"] for k in famk) / max(sum(k["launches"] for k in famk), 1)
+            roof["traffic_source"] = "ncu dram__bytes_read.sum + dram__bytes_write.sum (profiles/r02_traffic.json), per launch"
+    except (OSError, KeyError, ValueError):
+        pass
+    roof["kernel"] = dom
+    roof["peak_source"] = peaks["src"]
+    roof["peaks"] = {"bf16_tflops_sustained": peaks["bf16_tflops"], "hbm_gbs": peaks["hbm_gbs"]}
+    roof["per_family"] = per
+    # whole step: all convolution FLOPs of fwd + dgrad + wgrad (6 x MACs, SURVEY §8d) over the measured step time
+    if train_macs_per_image:
+        roof["whole_step_tflops"] = round(6.0 * train_macs_per_image * images / (step_ms * 1e-3) / 1e12, 1)
+    roof["timed_ms_sum"] = round(sum(v["ms"] for v in per.values()), 3)
+    return roof
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
-    ap.add_argument("--model", default="repvgg_a0", help="zoo model of the secondary measurements (the contract metric is "
-                    "the default, repvgg_a0; e.g. rexnet1_0x is north_star's second target)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-graph", action="store_true", help="launch every kernel of the step eagerly (no CUDA graph)")
-    ap.add_argument("--no-secondary", action="store_true", help="skip the ReXNet-1.0x leg (BASELINE configs[1]) at N=1")
-    args = ap.parse_args()
+TRAIN_MACS = {"repvgg_a0": 2.821e9, "repvgg_a1": 4.329e9, "rexnet1_0x": 0.398e9, "yolov4": 45.52e9, "unet3p": 195.49e9}
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
 
-    if args.impl == "reference":
-        run_reference(args, rank)
-        return
-
+# ------------------------------------------------------------------------------------------------ main arm
+def measure(args, wl: Workload, rank: int, local_rank: int, world: int, full: bool):
+    """Times `wl` on this process' GPU (all ranks); rank 0 returns the result dict. `full`: roofline / baselines legs."""
     import torch.distributed as dist
     import holocron_b200 as hb
     from holocron_b200.nn import _fused as K
+    from holocron_b200.nn import functional as hbF
     from holocron_b200.distributed import GradBucket, broadcast_parameters
     from holocron_b200._lib import lib
     from holocron_b200.graphs import GraphedTrainStep
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py (impl b200) needs a CUDA device: there is no CPU fallback")
-    torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
     warmup = max(args.warmup, 3)
-
-    torch.manual_seed(0)
-    model = getattr(hb.models, args.model)(num_classes=NUM_CLASSES).to(dev).to(memory_format=torch.channels_last).train()
+    model = wl.model(hb, dev)
     broadcast_parameters(model)
-    bucket = GradBucket(model.parameters())
-    opt = hb.optim.AdaBelief(model.parameters(), lr=1e-3, betas=(0.95, 0.99), eps=1e-6, capturable=not args.no_graph)
-    batch = args.batch
-    x_dev, t_dev = synthetic_batch(batch, 1000 + rank, dev)
-    # end-to-end leg: host-resident batch in pinned memory
-    x_host = x_dev.cpu().pin_memory()
-    t_host = t_dev.cpu().pin_memory()
+    bucket = GradBucket(model.parameters(), direct=not args.no_direct_grads)
+    use_graph = wl.graphable and not args.no_graph
+    opt = hb.optim.AdaBelief(model.parameters(), lr=1e-3, betas=(0.95, 0.99), eps=1e-6, capturable=use_graph)
+    batch = args.batch or wl.batch
+    host = wl.host_batch(batch, 1000 + rank)
+    devb = [t.to(dev) for t in host]
+    if devb[0].ndim == 4:
+        devb[0] = devb[0].contiguous()
 
-    def eager_step(x, t, collective=True):
-        loss = F.cross_entropy(model(x), t, label_smoothing=0.1)
+    def eager_step(*b, collective=True, optimizer=True):
+        loss = wl.loss(model, hbF, *b)
         loss.backward()
         if collective:
             bucket.all_reduce_mean()
-        opt.step()
-        bucket.zero_()
+        if optimizer:
+            opt.step()
+            bucket.zero_()
         return loss
 
-    # The whole step (forward, loss, backward, all-reduce, optimizer) is captured once into a CUDA graph and replayed:
-    # ~650 kernel launches and the autograd bookkeeping per step become one graph launch (holocron_b200/graphs.py).
     train_step, graphed = eager_step, None
-    if not args.no_graph:
+    if use_graph:
         try:
-            graphed = GraphedTrainStep(eager_step, (x_dev, t_dev), warmup=3)
+            graphed = GraphedTrainStep(eager_step, devb, warmup=3)
             train_step = graphed
         except Exception as e:  # noqa: BLE001 - capture is an optimisation: report and run the same CUDA path eagerly
             print(f"[bench] CUDA-graph capture failed ({e!r}); running the step eagerly", file=sys.stderr)
@@ -359,9 +470,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # two settle steps first (cudaFuncSetAttribute / tensor-map encoder / caching-allocator growth), then the W warm-up steps
     for _ in range(2 + warmup):
-        train_step(x_dev, t_dev)
+        train_step(*devb)
     barrier()
 
     # ---- timed region 1: inputs resident in HBM ----------------------------------------------------
@@ -374,7 +484,7 @@ def main():
     e0.record()
     h0 = time.perf_counter()
     for _ in range(args.steps):
-        loss = train_step(x_dev, t_dev)
+        loss = train_step(*devb)
     host_ms = (time.perf_counter() - h0) * 1e3 / args.steps   # host time to ENQUEUE a step (no sync inside the loop)
     e1.record()
     barrier()
@@ -384,13 +494,13 @@ def main():
 
     # ---- timed region 2: end to end through the public API with host buffers -----------------------
     copy_stream = torch.cuda.Stream()
-    bufs = [(torch.empty_like(x_dev), torch.empty_like(t_dev)) for _ in range(2)]
+    bufs = [[torch.empty_like(t) for t in devb] for _ in range(2)]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
 
     def prefetch(i):
         with torch.cuda.stream(copy_stream):
-            bufs[i][0].copy_(x_host, non_blocking=True)
-            bufs[i][1].copy_(t_host, non_blocking=True)
+            for dst, src in zip(bufs[i], host):
+                dst.copy_(src, non_blocking=True)
             ready[i].record(copy_stream)
 
     loss_host = 0.0
@@ -410,106 +520,134 @@ def main():
     barrier()
     ms_e2e = e2.elapsed_time(e3) / args.steps
 
-    # max over ranks
     if world > 1:
         tt = torch.tensor([ms, ms_e2e], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms, ms_e2e = tt.tolist()
+    if rank != 0:
+        return None
 
-    result = None
-    if rank == 0:
-        # ---- roofline leg: per-launch CUDA-event timing of the tensor-core conv kernels (one extra step) ----
-        K.KERNEL_TIMER = []
-        # park the stream behind a ~130 ms spin kernel first: the whole step is then enqueued before its first kernel runs,
-        # so the per-launch event pairs bracket GPU time only (otherwise the host gap between "record start" and the
-        # launch it precedes is counted whenever the host is slower than the GPU)
-        torch.cuda._sleep(int(2.5e8))
-        eager_step(x_dev, t_dev, collective=False)   # rank 0 only: no collective may be issued here
-        torch.cuda.synchronize()
-        recs = K.KERNEL_TIMER
-        K.KERNEL_TIMER = None
-        agg = {}
-        for kind, info, a, b in recs:
-            fl, by = conv_algorithmic(info, kind)
-            # kernel families: the generic implicit-GEMM kernel and its row-window twin share each role
-            kname = "conv_wgrad_kernel+conv_wgrad_rows_kernel" if kind == "wgrad" else "conv_fprop_kernel+conv_rows_kernel"
-            d = agg.setdefault(kname, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
-            d["ms"] += a.elapsed_time(b); d["flops"] += fl; d["bytes"] += by; d["launches"] += 1
-        if os.environ.get("HB_BENCH_DETAIL"):
-            by_shape = {}
-            for kind, info, a, b in recs:
-                key = (kind, info["H"], info["Cin"], info["Cout"], info["R"], info["stride"], info.get("dgrad_of_stride", 0))
-                e = by_shape.setdefault(key, [0, 0.0])
-                e[0] += 1; e[1] += a.elapsed_time(b)
-            for key, (cnt, t) in sorted(by_shape.items(), key=lambda kv: -kv[1][1]):
-                print(f"DETAIL {key}: n={cnt} total {t:.3f} ms", file=sys.stderr)
-        peaks = measured_peaks()
-        dom = max(agg, key=lambda k: agg[k]["ms"])
-        d = agg[dom]
-        t_flops = d["flops"] / (peaks["bf16_tflops"] * 1e12) * 1e3
-        t_bytes = d["bytes"] / (peaks["hbm_gbs"] * 1e9) * 1e3
-        if t_bytes >= t_flops:
-            roof = {"bound": "hbm", "achieved": d["bytes"] / d["ms"] / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s"}
-        else:
-            roof = {"bound": "tensor", "achieved": d["flops"] / d["ms"] / 1e9, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s"}
-        roof["frac"] = roof["achieved"] / roof["peak"]
-        # DRAM traffic of the same kernel family from an ncu capture of one step (tools/collect_traffic.py ->
-        # profiles/r01_traffic.json), averaged per launch like `achieved`; null when the capture is not there
-        roof["traffic"] = None
-        roof["algorithmic_bytes"] = d["bytes"] / d["launches"]
-        try:
-            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")) as f:
-                tk = json.load(f)["kernels"]
-            fam = [tk[k] for k in dom.split("+") if k in tk]
-            if fam and sum(k["launches"] for k in fam) == d["launches"]:
-                roof["traffic"] = sum(k["dram_read_bytes"] + k["dram_write_bytes"] for k in fam) / d["launches"]
-                roof["traffic_source"] = "ncu dram__bytes_read.sum + dram__bytes_write.sum (profiles/r01_traffic.json), per launch"
-        except (OSError, KeyError, ValueError):
-            pass
-        roof["kernel"] = dom
-        roof["peak_source"] = peaks["src"]
-        roof["per_step"] = {k: {"ms": round(v["ms"], 3), "launches": v["launches"], "TFLOP/s": round(v["flops"] / v["ms"] / 1e9, 1),
-                                "GB/s": round(v["bytes"] / v["ms"] / 1e6, 1)} for k, v in agg.items()}
-        cpu = None if args.no_cpu_baseline or world > 1 else cpu_baseline()
-        secondary = None
-        if world == 1 and args.model == "repvgg_a0" and not args.no_secondary:
-            # BASELINE.json configs[1] (north_star's second target) measured with the same harness, reported beside the
-            # contract metric; never allowed to disturb it
+    images = batch * world
+    n_params = sum(p.numel() for p in model.parameters())
+    roof = roofline_leg(K, lambda: eager_step(*devb, collective=False, optimizer=False),
+                        lambda: (opt.step(), bucket.zero_()), n_params, ms, batch, TRAIN_MACS.get(wl.key, 0.0))
+    result = {
+        "metric": wl.metric, "value": images / ms * 1e3, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": wl.desc, "batch_per_gpu": batch, "global_batch": images, "parallelism": f"dp{world}",
+                   "l2": "per-step working set (GBs of activations) exceeds the 126 MB L2; no explicit flush",
+                   "launch": "cuda_graph" if graphed is not None else "eager"},
+        "e2e": {"value": images / ms_e2e * 1e3, "unit": "images/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in host)), "d2h_bytes_per_step": 4,
+                "last_loss": loss_host},
+        "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(host_ms, 3),
+        "clocks": clocks,
+        "roofline": roof,
+    }
+    if full and world == 1:
+        if not args.no_cpu_baseline:
+            result["cpu_baseline"] = cpu_baseline()
+        if wl.key == "repvgg_a0" and not args.no_eager_baseline:
             try:
-                secondary = secondary_rexnet(hb, GradBucket, GraphedTrainStep, x_dev, t_dev, dev)
+                del graphed, train_step
+                torch.cuda.empty_cache()
+                g = gpu_eager_baseline(batch, dev)
+                g["speedup_of_this_repo"] = round(g["ms_per_step"] / ms, 2)
+                result["gpu_eager_baseline"] = g
             except Exception as e:  # noqa: BLE001
-                secondary = {"workload": "rexnet1_0x 224x224 bf16 train step, batch 256", "error": repr(e)[:200]}
-        images = batch * world
-        result = {
-            "metric": METRIC if args.model == "repvgg_a0" else f"images/sec {args.model} 224^2 bf16 train",
-            "value": images / ms * 1e3, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-            "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{args.model} (train form, 1000 classes) 224x224 bf16 train step: fwd + CE(label_smoothing=0.1)"
-                                   " + bwd + AdaBelief(lr=1e-3, betas=(0.95,0.99), eps=1e-6)",
-                       "batch_per_gpu": batch, "global_batch": images, "parallelism": f"dp{world}",
-                       "l2": "per-step working set (>4 GB of activations) exceeds the 126 MB L2; no explicit flush",
-                       "launch": "cuda_graph" if graphed is not None else "eager"},
-            "e2e": {"value": images / ms_e2e * 1e3, "unit": "images/s", "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": x_host.numel() * 4 + t_host.numel() * 8, "d2h_bytes_per_step": 4,
-                    "last_loss": loss_host},
-            "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(host_ms, 3),
-            "clocks": clocks,
-            "roofline": roof,
-        }
-        if cpu is not None:
-            result["cpu_baseline"] = cpu
-        if secondary is not None:
-            result["secondary"] = secondary
+                result["gpu_eager_baseline"] = {"error": repr(e)[:200]}
+    return result
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the configuration's own)")
+    ap.add_argument("--model", "--workload", dest="model", default="repvgg_a0",
+                    choices=["repvgg_a0", "rexnet1_0x", "repvgg_a1", "yolov4", "unet3p"],
+                    help="repvgg_a0 = the contract metric (default); the others are BASELINE.json configs[1..4]")
+    ap.add_argument("--config", type=int, default=0, help="BASELINE.json configs index 1..4 (alias of --model)")
+    ap.add_argument("--micro", action="store_true", help="leaf-kernel micro rows (GB/s vs the measured HBM peak) instead of a model")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the torch-eager (cuDNN) baseline leg on the GPU")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel of the step eagerly (no CUDA graph)")
+    ap.add_argument("--no-direct-grads", action="store_true", help="let autograd accumulate parameter gradients (A/B switch)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the ReXNet-1.0x leg (BASELINE configs[1]) at N=1")
+    args = ap.parse_args()
+    if args.config:
+        args.model = {1: "rexnet1_0x", 2: "repvgg_a1", 3: "yolov4", 4: "unet3p"}[args.config]
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl b200) needs a CUDA device: there is no CPU fallback")
+    if args.micro:
+        from tools.micro_bench import run_micro
+        if rank == 0:
+            print(json.dumps(run_micro(measured_peaks())), flush=True)
+        return
+
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
+
+    result = measure(args, Workload(args.model), rank, local_rank, world, full=True)
+    if rank == 0 and world == 1 and args.model == "repvgg_a0" and not args.no_secondary:
+        # BASELINE.json configs[1] (north_star's second target) measured with the same harness, reported beside the
+        # contract metric; never allowed to disturb it
+        try:
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
+            sargs = argparse.Namespace(**vars(args))
+            sargs.steps, sargs.warmup, sargs.batch = 10, 3, 0
+            sec = measure(sargs, Workload("rexnet1_0x"), 0, local_rank, 1, full=False)
+            result["secondary"] = {"workload": sec["config"]["workload"] + ", batch 256, CUDA-graph replay, inputs resident in HBM",
+                                   "images_per_s": sec["value"], "ms_per_step": sec["ms_per_step"], "steps": sec["steps"],
+                                   "last_loss": sec["e2e"]["last_loss"], "e2e_images_per_s": sec["e2e"]["value"],
+                                   "roofline": sec["roofline"]}
+        except Exception as e:  # noqa: BLE001
+            result["secondary"] = {"workload": "rexnet1_0x 224x224 bf16 train step, batch 256", "error": repr(e)[:200]}
+    if rank == 0:
         print(json.dumps(result), flush=True)
     if world > 1:
-        # No collective after the timing all-reduce: rank 0's extra legs above are local, the other ranks are done.
-        # Communicator teardown with captured NCCL kernels still alive was seen to block at exit (2 x B200, NCCL 2.28),
-        # so every rank leaves through a hard exit once its output is flushed.
+        _exit_watchdog()
+        # orderly teardown: every captured graph (it holds NCCL kernels) is released before the communicator goes away
+        import gc
         torch.cuda.synchronize()
+        gc.collect()
+        try:
+            dist.barrier()
+            torch.cuda.synchronize()
+            dist.destroy_process_group()
+        except Exception as e:  # noqa: BLE001
+            print(f"[bench] process-group teardown: {e!r}", file=sys.stderr)
+        sys.stdout.flush()
+        sys.stderr.flush()
+
+
+def _exit_watchdog(seconds: float = 25.0):
+    """Orderly teardown first; if the NCCL communicator teardown blocks (seen once with captured collectives, NCCL 2.28)
+    the process still ends: a daemon timer leaves through os._exit after the result line has been flushed."""
+    def _kill():
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)
+    t = threading.Timer(seconds, _kill)
+    t.daemon = True
+    t.start()
 
 
 if __name__ == "__main__":

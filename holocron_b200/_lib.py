@@ -38,6 +38,8 @@ SIGNATURES = {
     "hb_conv2d_wgrad_workspace_bytes": "i" * 11,
     "hb_repvgg_wgrad_workspace_bytes": "i" * 6,
     "hb_repvgg_wgrad_bf16": "pppppz" + "i" * 6 + "p",
+    "hb_conv2d_wgrad_acc_bf16": "ppppz" + "i" * 11 + "p",
+    "hb_repvgg_wgrad_acc_bf16": "ppppppz" + "i" * 6 + "p",
     "hb_pack_conv_weights": "ppp" + "i" * 8 + "p",
     "hb_zero_insert_bf16": "pp" + "i" * 7 + "p",
     "hb_pack_conv_weights_multi": "ppip",
@@ -47,11 +49,15 @@ SIGNATURES = {
     "hb_pack_dgrad_s2_weights": "pp" + "i" * 4 + "p",
     "hb_nchw_to_nhwc_pad_bf16": "pp" + "i" * 6 + "p",
     "hb_im2col_smallc_bf16": "pp" + "i" * 10 + "p",
-    "hb_bn_stats_bf16": "pppiiipp",
-    "hb_bn_finalize": "pppppp" + "pppp" + "iiiiffp",
+    "hb_conv2d_fused_bf16": "ppp",
+    "hb_conv_stat_slots_max": "",
+    "hb_bn_stats_partials_bf16": "piippp",
+    "hb_bn_stat_slots_max": "",
+    "hb_bn_finalize": "ppppppp" + "pppp" + "iiiiffp",
     "hb_bn_eval_affine": "ppppfiippppp",
-    "hb_bn_act_fwd_bf16": "pppipppp" + "iiifip",
-    "hb_bn_act_bwd_bf16": "ppppi" + "pppppp" + "pppppp" + "iiifiip",
+    "hb_bn_act_fwd_bf16": "pppipppp" + "iiifi" + "ppp",
+    "hb_bn_bwd_scratch_doubles": "iii",
+    "hb_bn_act_bwd_bf16": "ppppi" + "pppppp" + "pppppp" + "pp" + "iiiifiip",
     "hb_dwconv_fwd_bf16": "pppp" + "iiiiiiip",
     "hb_dwconv_bwd_data_bf16": "ppp" + "iiiiiiip",
     "hb_dwconv_bwd_weight_bf16": "ppppp" + "iiiiiiip",
@@ -96,7 +102,7 @@ def lib() -> ctypes.CDLL:
         for name, sig in SIGNATURES.items():
             fn = getattr(handle, name)  # AttributeError here = the library is stale: rebuild it
             fn.argtypes = [_CTYPE[c] for c in sig]
-            fn.restype = ctypes.c_size_t if name.endswith("_bytes") else ctypes.c_int
+            fn.restype = ctypes.c_size_t if name.endswith(("_bytes", "_doubles")) else ctypes.c_int
         handle.hb_launch_count.argtypes = []
         handle.hb_launch_count.restype = ctypes.c_longlong
         handle.hb_launch_count_reset.argtypes = []
@@ -105,6 +111,14 @@ def lib() -> ctypes.CDLL:
         handle.hb_version.restype = ctypes.c_char_p
         _lib = handle
     return _lib
+
+
+class ConvArgs(ctypes.Structure):
+    """``hb_conv_args`` of include/holocron_b200.h (argument block of hb_conv2d_fused_bf16)."""
+    _fields_ = ([(n, ctypes.c_void_p) for n in ("x", "w", "y", "bias", "residual")]
+                + [(n, ctypes.c_int) for n in ("N", "H", "W", "Cin", "Cout", "R", "S", "stride", "pad", "dil", "act", "num_ctas")]
+                + [("xe", ctypes.c_void_p), ("we", ctypes.c_void_p), ("Ce", ctypes.c_int), ("w2", ctypes.c_void_p),
+                   ("y2", ctypes.c_void_p), ("stats", ctypes.c_void_p), ("stats2", ctypes.c_void_p)])
 
 
 def check(rc: int, what: str) -> None:

@@ -6,8 +6,11 @@
 // generalised to B <= 3 normalised branches u_b of identical shape [M, C] plus an optional un-normalised
 // residual. The reference runs one cuDNN/ATen kernel per BN, add and activation (>= 8 HBM passes per
 // RepBlock); here the whole thing is
-//   stats      : one pass over the branch inputs  -> per-channel sum / sum-of-squares (fp32 partials, fp64 merge)
-//   finalize   : C-sized: mean, rstd, scale = gamma*rstd, shift = beta - mean*scale, running-stat update
+//   stats      : per-channel sum / sum-of-squares PARTIALS, normally produced by whoever wrote the tensor (the epilogue of
+//                the tensor-core convolution, conv_fprop.cu / conv_rows.cu, or the forward pass below for a block's own
+//                output); bn_stats_partials_kernel is the stand-alone pass for tensors that come without partials
+//   finalize   : C-sized: fixed-order fp64 sum of the partials (deterministic: no floating-point atomics anywhere),
+//                mean, rstd, scale = gamma*rstd, shift = beta - mean*scale, running-stat update
 //   forward    : one pass: out = act(sum_b (scale_b * u_b + shift_b) + residual)
 //   bwd reduce : one pass: sum(dz), sum(dz * xhat_b)    with dz = dOut * act'(z), z recomputed (not stored)
 //   bwd apply  : one pass: du_b = scale_b * (dz - mean(dz) - xhat_b * mean(dz*xhat_b)), dresidual = dz
@@ -59,14 +62,14 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float* f) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// stats: sums[b][0][c] = sum_m u_b[m,c], sums[b][1][c] = sum_m u_b[m,c]^2     (fp64 global accumulators)
-// grid = (row blocks, channel slabs, branches)
-__global__ void __launch_bounds__(kThreads) bn_stats_kernel(Branches br, int M, int C, Geo g, double* sums) {
+// stand-alone statistics pass: parts[blockIdx.x][c] = (sum, sum of squares) of this block's rows of u [M, C]
+// grid = (row blocks = slots, channel slabs)
+__global__ void __launch_bounds__(kThreads) bn_stats_partials_kernel(const __nv_bfloat16* __restrict__ u, int M, int C, Geo g,
+                                                                     float* __restrict__ parts) {
   __shared__ float red[2][kThreads * 8];
   const int tx = threadIdx.x % g.cg_t, ty = threadIdx.x / g.cg_t;
   const int cg = blockIdx.y * g.cg_t + tx;
   const bool active = ty < g.rows_t && cg < g.cg_total;
-  const __nv_bfloat16* u = br.u[blockIdx.z];
   float s[8], q[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
@@ -91,23 +94,26 @@ __global__ void __launch_bounds__(kThreads) bn_stats_kernel(Branches br, int M, 
 #pragma unroll
   for (int j = 0; j < 8; ++j) { red[0][threadIdx.x * 8 + j] = s[j]; red[1][threadIdx.x * 8 + j] = q[j]; }
   __syncthreads();
-  // threads 0 .. cg_t*8-1 each own one channel of the slab: sum over row lanes in fp64
+  // threads 0 .. cg_t*8-1 each own one channel of the slab: sum over row lanes in a fixed order
   const int nch = g.cg_t * 8;
-  for (int c = threadIdx.x; c < 2 * nch; c += kThreads) {
-    const int which = c / nch, ch = c % nch;
+  for (int ch = threadIdx.x; ch < nch; ch += kThreads) {
     const int ctx = ch / 8, j = ch % 8;
     const int gcg = blockIdx.y * g.cg_t + ctx;
     if (gcg >= g.cg_total) continue;
-    double acc = 0.0;
-    for (int r = 0; r < g.rows_t; ++r) acc += (double)red[which][(r * g.cg_t + ctx) * 8 + j];
-    atomicAdd(&sums[((size_t)blockIdx.z * 2 + which) * C + gcg * 8 + j], acc);
+    double a = 0.0, b = 0.0;
+    for (int r = 0; r < g.rows_t; ++r) {
+      a += (double)red[0][(r * g.cg_t + ctx) * 8 + j];
+      b += (double)red[1][(r * g.cg_t + ctx) * 8 + j];
+    }
+    *reinterpret_cast<float2*>(parts + ((size_t)blockIdx.x * C + gcg * 8 + j) * 2) = make_float2((float)a, (float)b);
   }
 }
 
 // ---------------------------------------------------------------------------------------------------
 // finalize: per branch b and channel c
 struct FinalizeParams {
-  const double* sums;      // [B][2][C]
+  const float* parts[kMaxBranches];   // [slots_b][C][2] (sum, sum of squares) partials
+  int slots[kMaxBranches];
   const float* gamma[kMaxBranches];
   const float* beta[kMaxBranches];
   float* running_mean[kMaxBranches];  // may be null
@@ -121,17 +127,25 @@ struct FinalizeParams {
   int C_logical;  // channels >= C_logical are padding: scale = shift = 0, no parameter / running-stat access
   float eps, momentum;
 };
-__global__ void bn_finalize_kernel(FinalizeParams p) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per (branch, channel): lanes stride over the slots, fixed-shape shuffle tree -> run-to-run identical result
+__global__ void __launch_bounds__(256) bn_finalize_kernel(FinalizeParams p) {
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int b = blockIdx.y;
   if (c >= p.C) return;
+  const size_t o = (size_t)b * p.C + c;
   if (c >= p.C_logical) {
-    const size_t o = (size_t)b * p.C + c;
-    p.mean[o] = 0.f; p.rstd[o] = 0.f; p.scale[o] = 0.f; p.shift[o] = 0.f;
+    if (lane == 0) { p.mean[o] = 0.f; p.rstd[o] = 0.f; p.scale[o] = 0.f; p.shift[o] = 0.f; }
     return;
   }
-  const double s = p.sums[((size_t)b * 2 + 0) * p.C + c];
-  const double q = p.sums[((size_t)b * 2 + 1) * p.C + c];
+  double s = 0.0, q = 0.0;
+  const float* pp = p.parts[b] + (size_t)c * 2;
+  for (int k = lane; k < p.slots[b]; k += 32) {
+    const float2 v = *reinterpret_cast<const float2*>(pp + (size_t)k * p.C * 2);
+    s += (double)v.x; q += (double)v.y;
+  }
+  s = warp_sum(s); q = warp_sum(q);
+  if (lane != 0) return;
   const double mean = s / p.M;
   double var = q / p.M - mean * mean;
   if (var < 0) var = 0;
@@ -139,7 +153,6 @@ __global__ void bn_finalize_kernel(FinalizeParams p) {
   const float g = p.gamma[b] ? p.gamma[b][c] : 1.f;
   const float be = p.beta[b] ? p.beta[b][c] : 0.f;
   const float sc = g * rstd;
-  const size_t o = (size_t)b * p.C + c;
   p.mean[o] = (float)mean;
   p.rstd[o] = rstd;
   p.scale[o] = sc;
@@ -183,6 +196,8 @@ struct FwdParams {
   int M, C, act;
   float slope;
   int res_after;  // 1: out = act(z) + residual (ResNet-style shortcut after the activation); 0: act(z + residual)
+  float* out_stats;  // optional [gridDim.x][C][2]: (sum, sum of squares) partials of the bf16 OUTPUT - the statistics the
+                     // identity-branch BatchNorm of the NEXT RepVGG block needs, produced while the data is in registers
 };
 using RawVec = Vec16<__nv_bfloat16>;
 
@@ -249,66 +264,106 @@ __global__ void __launch_bounds__(kThreads) bn_act_fwd_kernel(FwdParams p, Geo g
   extern __shared__ __align__(16) uint8_t ring_smem[];
   const int tx = threadIdx.x % g.cg_t, ty = threadIdx.x / g.cg_t;
   const int cg = blockIdx.y * g.cg_t + tx;
-  if (ty >= g.rows_t || cg >= g.cg_total) return;
-  float sc[NB > 0 ? NB : 1][8], sh[8];
+  const bool active = ty < g.rows_t && cg < g.cg_total;
+  if (!active && !p.out_stats) return;
+  float os[8], oq[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) sh[j] = 0.f;
+  for (int j = 0; j < 8; ++j) { os[j] = 0.f; oq[j] = 0.f; }
+  if (active) {
+    float sc[NB > 0 ? NB : 1][8], sh[8];
 #pragma unroll
-  for (int b = 0; b < NB; ++b) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      sc[b][j] = p.scale[(size_t)b * p.C + cg * 8 + j];
-      sh[j] += p.shift[(size_t)b * p.C + cg * 8 + j];
-    }
-  }
-  const bool has_res = p.residual != nullptr;
-  RowRing<NB + 1> ring;
-  ring.base = smem_addr(ring_smem) + threadIdx.x * 16;
-  ring.m0 = (size_t)blockIdx.x * g.rows_t + ty;
-  ring.stride = (size_t)gridDim.x * g.rows_t;
-  ring.M = (size_t)p.M;
-  ring.col_off = (size_t)cg * 8;
-  ring.C = p.C;
-#pragma unroll
-  for (int b = 0; b < NB; ++b) ring.src[b] = p.br.u[b];
-  ring.src[NB] = p.residual;
-  ring.prologue();
-  for (size_t k = 0; ring.valid(k); ++k) {
-    ring.wait();
-    const int s = (int)(k % kSlots);
-    RawVec u[NB > 0 ? NB : 1], r;
-#pragma unroll
-    for (int b = 0; b < NB; ++b) u[b] = lds16(ring.addr(s, b));
-    if (has_res) r = lds16(ring.addr(s, NB));
-    ring.issue(k + kDepth);
-    float z[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) z[j] = sh[j];
+    for (int j = 0; j < 8; ++j) sh[j] = 0.f;
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
-      float f[8];
-      unpack8(u[b], f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) z[j] = fmaf(sc[b][j], f[j], z[j]);
+      for (int j = 0; j < 8; ++j) {
+        sc[b][j] = p.scale[(size_t)b * p.C + cg * 8 + j];
+        sh[j] += p.shift[(size_t)b * p.C + cg * 8 + j];
+      }
     }
-    float rr[8];
-    if (has_res) unpack8(r, rr);
-    if (has_res && !p.res_after) {
-      if (p.act == ACT_FRELU) {
+    const bool has_res = p.residual != nullptr;
+    const bool want_stats = p.out_stats != nullptr;
+    RowRing<NB + 1> ring;
+    ring.base = smem_addr(ring_smem) + threadIdx.x * 16;
+    ring.m0 = (size_t)blockIdx.x * g.rows_t + ty;
+    ring.stride = (size_t)gridDim.x * g.rows_t;
+    ring.M = (size_t)p.M;
+    ring.col_off = (size_t)cg * 8;
+    ring.C = p.C;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) z[j] = fmaxf(z[j], rr[j]);
-      } else {
+    for (int b = 0; b < NB; ++b) ring.src[b] = p.br.u[b];
+    ring.src[NB] = p.residual;
+    ring.prologue();
+    for (size_t k = 0; ring.valid(k); ++k) {
+      ring.wait();
+      const int s = (int)(k % kSlots);
+      RawVec u[NB > 0 ? NB : 1], r;
+#pragma unroll
+      for (int b = 0; b < NB; ++b) u[b] = lds16(ring.addr(s, b));
+      if (has_res) r = lds16(ring.addr(s, NB));
+      ring.issue(k + kDepth);
+      float z[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) z[j] = sh[j];
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        float f[8];
+        unpack8(u[b], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) z[j] = fmaf(sc[b][j], f[j], z[j]);
+      }
+      float rr[8];
+      if (has_res) unpack8(r, rr);
+      if (has_res && !p.res_after) {
+        if (p.act == ACT_FRELU) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) z[j] = fmaxf(z[j], rr[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) z[j] += rr[j];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) z[j] = act_fwd(p.act, z[j], p.slope);
+      if (has_res && p.res_after) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) z[j] += rr[j];
       }
-    }
+      Vec16<__nv_bfloat16> ov;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) z[j] = act_fwd(p.act, z[j], p.slope);
-    if (has_res && p.res_after) {
+      for (int j = 0; j < 8; ++j) ov.v[j] = __float2bfloat16_rn(z[j]);
+      st16(p.out + ring.off(k), ov);
+      if (want_stats) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) z[j] += rr[j];
+        for (int j = 0; j < 8; ++j) {
+          const float f = __bfloat162float(ov.v[j]);   // statistics of what the consumer will read
+          os[j] += f; oq[j] = fmaf(f, f, oq[j]);
+        }
+      }
     }
-    store8(p.out + ring.off(k), z);
+  }
+  if (!p.out_stats) return;
+  // block partial of the output statistics: the ring memory is free now (every cp.async group has been waited for)
+  cp_async_wait<0>();
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(ring_smem);   // [2][kThreads * 8] floats = 16 KB <= smallest ring
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[threadIdx.x * 8 + j] = active ? os[j] : 0.f;
+    red[kThreads * 8 + threadIdx.x * 8 + j] = active ? oq[j] : 0.f;
+  }
+  __syncthreads();
+  const int nch = g.cg_t * 8;
+  for (int ch = threadIdx.x; ch < nch; ch += kThreads) {
+    const int ctx = ch / 8, j = ch % 8;
+    const int gcg = blockIdx.y * g.cg_t + ctx;
+    if (gcg >= g.cg_total) continue;
+    double a = 0.0, b = 0.0;
+    for (int r = 0; r < g.rows_t; ++r) {
+      a += (double)red[(r * g.cg_t + ctx) * 8 + j];
+      b += (double)red[kThreads * 8 + (r * g.cg_t + ctx) * 8 + j];
+    }
+    *reinterpret_cast<float2*>(p.out_stats + ((size_t)blockIdx.x * p.C + gcg * 8 + j) * 2) = make_float2((float)a, (float)b);
   }
 }
 
@@ -322,7 +377,8 @@ struct BwdParams {
   const float* shift;
   const float* mean;
   const float* rstd;
-  double* sums;        // [1 + B][C]: sum dz, sum dz*u_b
+  double* sums;        // [1 + B][C]: sum dz, sum dz*u_b (final, written by bn_bwd_finalize_kernel)
+  double* part;        // [row blocks][1 + B][C]: per-block partials of the above (pass 1), summed in a fixed order
   __nv_bfloat16* du[kMaxBranches];
   __nv_bfloat16* dres;  // may be null
   int M, C, act;
@@ -436,7 +492,7 @@ __device__ __forceinline__ void init_bwd_ring(RowRing<NB + 2>& ring, const BwdPa
   ring.src[NB + 1] = p.dout;
 }
 
-// pass 1: sums[0][c] += sum_m dz, sums[1+b][c] += sum_m dz * u_b
+// pass 1: part[blk][0][c] = sum_m dz, part[blk][1+b][c] = sum_m dz * u_b over the rows of this block (no atomics)
 template <int NB>
 __global__ void __launch_bounds__(kThreads, 2) bn_act_bwd_reduce_kernel(BwdParams p, Geo g) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
@@ -489,7 +545,7 @@ __global__ void __launch_bounds__(kThreads, 2) bn_act_bwd_reduce_kernel(BwdParam
       if (gcg >= g.cg_total) continue;
       double a = 0.0;
       for (int r = 0; r < g.rows_t; ++r) a += (double)red[(r * g.cg_t + ctx) * 8 + j];
-      atomicAdd(&p.sums[(size_t)i * p.C + gcg * 8 + j], a);
+      p.part[((size_t)blockIdx.x * (1 + NB) + i) * p.C + gcg * 8 + j] = a;
     }
   }
 }
@@ -535,16 +591,39 @@ __global__ void __launch_bounds__(kThreads, 2) bn_act_bwd_apply_kernel(BwdParams
   }
 }
 
-// dgamma_b = sum dz*xhat_b, dbeta_b = sum dz  (fp32 outputs from the fp64 sums)
-// (sum dz * xhat_b = rstd_b * (sum dz * u_b - mean_b * sum dz), evaluated in fp64)
-__global__ void bn_param_grads_kernel(const double* sums, const float* mean, const float* rstd, int B, int C, float* dgamma,
-                                      float* dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  const int b = blockIdx.y;
-  if (c >= C) return;
-  const size_t o = (size_t)b * C + c;
-  dgamma[o] = (float)((double)rstd[o] * (sums[(size_t)(1 + b) * C + c] - (double)mean[o] * sums[c]));
-  dbeta[o] = (float)sums[c];
+// Between the two passes: sums[i][c] = sum over the row blocks of part[blk][i][c] (one warp per channel, fixed order), then
+//   dgamma_b = sum dz*xhat_b = rstd_b * (sum dz*u_b - mean_b * sum dz),   dbeta_b = sum dz     (evaluated in fp64)
+// written to dgamma/dbeta ([B][C] fp32, optional) and / or ACCUMULATED into the parameters' gradient buffers gacc/bacc
+// (`.grad` storage of the BatchNorm weight / bias: what autograd's AccumulateGrad would do with one more kernel each).
+struct BwdFinalizeParams {
+  const double* part; double* sums; const float* mean; const float* rstd;
+  float* dgamma; float* dbeta;
+  float* gacc[kMaxBranches]; float* bacc[kMaxBranches];
+  int nblocks, B, C, C_logical;
+};
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(BwdFinalizeParams p) {
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= p.C) return;
+  double tot[1 + kMaxBranches];
+  for (int i = 0; i <= p.B; ++i) {
+    double a = 0.0;
+    for (int k = lane; k < p.nblocks; k += 32) a += p.part[((size_t)k * (1 + p.B) + i) * p.C + c];
+    tot[i] = warp_sum(a);
+  }
+  if (lane != 0) return;
+  for (int i = 0; i <= p.B; ++i) p.sums[(size_t)i * p.C + c] = tot[i];
+  for (int b = 0; b < p.B; ++b) {
+    const size_t o = (size_t)b * p.C + c;
+    const float dg = (float)((double)p.rstd[o] * (tot[1 + b] - (double)p.mean[o] * tot[0]));
+    const float db = (float)tot[0];
+    if (p.dgamma) p.dgamma[o] = dg;
+    if (p.dbeta) p.dbeta[o] = db;
+    if (c < p.C_logical) {
+      if (p.gacc[b]) p.gacc[b][c] += dg;
+      if (p.bacc[b]) p.bacc[b][c] += db;
+    }
+  }
 }
 
 // persistent grid: `per_sm` blocks per SM, grid-stride over rows
@@ -592,26 +671,30 @@ inline size_t ring_bytes(int tensors) { return (size_t)kSlots * tensors * kThrea
 
 extern "C" {
 
-// sums must be zero on entry: double [B][2][C].
-int hb_bn_stats_bf16(const void* u0, const void* u1, const void* u2, int B, int M, int C, double* sums, void* stream) {
-  if (C % 8 != 0 || B < 1 || B > kMaxBranches) return (int)cudaErrorInvalidValue;
-  Branches br{{(const __nv_bfloat16*)u0, (const __nv_bfloat16*)u1, (const __nv_bfloat16*)u2}, B};
+// Stand-alone statistics pass over u [M, C] bf16 -> parts float [*slots][C][2] (capacity hb_bn_stat_slots_max()).
+int hb_bn_stats_partials_bf16(const void* u, int M, int C, float* parts, int* slots, void* stream) {
+  if (C % 8 != 0 || !slots) return (int)cudaErrorInvalidValue;
   Geo g = Geo::make(C);
-  // every block ends with 2*C fp64 atomics per branch: keep the block count down on small problems
   static const int min_rows = env_int("HB_BN_STATS_ROWS", 16);
-  bn_stats_kernel<<<make_grid(g, M, B, 4, min_rows), kThreads, 0, (cudaStream_t)stream>>>(br, M, C, g, sums);
+  const dim3 grid = make_grid(g, M, 1, 4, min_rows);
+  *slots = (int)grid.x;
+  bn_stats_partials_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)u, M, C, g, parts);
   HB_LAUNCH_CHECK();
   return 0;
 }
 
-int hb_bn_finalize(const double* sums, const float* const* gamma, const float* const* beta, float* const* running_mean,
-                   float* const* running_var, long long* const* num_batches_tracked, float* mean, float* rstd,
-                   float* scale, float* shift, int B, int C, int C_logical, int M, float eps, float momentum,
-                   void* stream) {
-  if (B < 1 || B > kMaxBranches) return (int)cudaErrorInvalidValue;
+int hb_bn_stat_slots_max(void) { return HB_NUM_SMS * 8; }
+
+int hb_bn_finalize(const float* const* parts, const int* slots, const float* const* gamma, const float* const* beta,
+                   float* const* running_mean, float* const* running_var, long long* const* num_batches_tracked,
+                   float* mean, float* rstd, float* scale, float* shift, int B, int C, int C_logical, int M, float eps,
+                   float momentum, void* stream) {
+  if (B < 1 || B > kMaxBranches || !parts || !slots) return (int)cudaErrorInvalidValue;
   FinalizeParams p{};
-  p.sums = sums;
   for (int b = 0; b < B; ++b) {
+    if (!parts[b] || slots[b] < 1) return (int)cudaErrorInvalidValue;
+    p.parts[b] = parts[b];
+    p.slots[b] = slots[b];
     p.gamma[b] = gamma ? gamma[b] : nullptr;
     p.beta[b] = beta ? beta[b] : nullptr;
     p.running_mean[b] = running_mean ? running_mean[b] : nullptr;
@@ -620,7 +703,7 @@ int hb_bn_finalize(const double* sums, const float* const* gamma, const float* c
   }
   p.mean = mean; p.rstd = rstd; p.scale = scale; p.shift = shift;
   p.B = B; p.C = C; p.M = M; p.C_logical = C_logical; p.eps = eps; p.momentum = momentum;
-  bn_finalize_kernel<<<dim3((C + 127) / 128, B), 128, 0, (cudaStream_t)stream>>>(p);
+  bn_finalize_kernel<<<dim3((C + 7) / 8, B), 256, 0, (cudaStream_t)stream>>>(p);
   HB_LAUNCH_CHECK();
   return 0;
 }
@@ -636,17 +719,20 @@ int hb_bn_eval_affine(const float* gamma, const float* beta, const float* runnin
 
 int hb_bn_act_fwd_bf16(const void* u0, const void* u1, const void* u2, int B, const float* scale, const float* shift,
                        const void* residual, void* out, int M, int C, int act, float slope, int res_after,
-                       void* stream) {
+                       float* out_stats, int* out_stat_slots, void* stream) {
   if (C % 8 != 0 || B < 0 || B > kMaxBranches) return (int)cudaErrorInvalidValue;
   FwdParams p{};
   p.br = Branches{{(const __nv_bfloat16*)u0, (const __nv_bfloat16*)u1, (const __nv_bfloat16*)u2}, B};
   p.scale = scale; p.shift = shift; p.residual = (const __nv_bfloat16*)residual; p.out = (__nv_bfloat16*)out;
   p.M = M; p.C = C; p.act = act; p.slope = slope; p.res_after = res_after;
+  if (out_stats && !out_stat_slots) return (int)cudaErrorInvalidValue;
+  p.out_stats = out_stats;
   Geo g = Geo::make(C);
   static const int per_sm_env = env_int("HB_BN_CAP_FWD", 0);
   // resident blocks per SM: 3 with three input tensors (64 KB ring each), 4 with fewer
   const int per_sm = per_sm_env > 0 ? per_sm_env : (B + (residual != nullptr) >= 3 ? 3 : 4);
   const dim3 grid = make_grid(g, M, 1, per_sm);
+  if (out_stat_slots) *out_stat_slots = (int)grid.x;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = ring_bytes(B + 1);
   HB_BN_DISPATCH(bn_act_fwd_kernel, B, grid, smem, st, p, g)
@@ -654,17 +740,27 @@ int hb_bn_act_fwd_bf16(const void* u0, const void* u1, const void* u2, int B, co
   return 0;
 }
 
-// Backward. sums: double [1+B][C], zero on entry (train=1). du_b / dres may be NULL when not needed.
-// dgamma/dbeta: fp32 [B][C] outputs (optional; when given the reduction pass also runs for train=0).
+// Backward. scratch: double [hb_bn_bwd_scratch_doubles(M, C, B)], no initialisation needed: [1+B][C] final sums followed
+// by the per-block partials of the reduction pass. du_b / dres may be NULL when not needed.
+// dgamma/dbeta: fp32 [B][C] outputs (optional); gamma_grad_acc / beta_grad_acc: optional HOST arrays of B device pointers
+// (entries may be NULL) to fp32 [C_logical] gradient buffers that dgamma_b / dbeta_b are ADDED to.
+size_t hb_bn_bwd_scratch_doubles(int M, int C, int B) {
+  Geo g = Geo::make(C);
+  const dim3 grid = make_grid(g, M, 1, 3);   // upper bound of the reduction pass' row blocks (cap <= 3 per SM)
+  return (size_t)(1 + B) * C * (1 + (size_t)grid.x);
+}
+
 int hb_bn_act_bwd_bf16(const void* dout, const void* u0, const void* u1, const void* u2, int B, const float* scale,
-                       const float* shift, const float* mean, const float* rstd, const void* residual, double* sums,
-                       void* du0, void* du1, void* du2, void* dres, float* dgamma, float* dbeta, int M, int C, int act,
+                       const float* shift, const float* mean, const float* rstd, const void* residual, double* scratch,
+                       void* du0, void* du1, void* du2, void* dres, float* dgamma, float* dbeta,
+                       float* const* gamma_grad_acc, float* const* beta_grad_acc, int C_logical, int M, int C, int act,
                        float slope, int train, int res_after, void* stream) {
   if (C % 8 != 0 || B < 0 || B > kMaxBranches) return (int)cudaErrorInvalidValue;
   BwdParams p{};
   p.br = Branches{{(const __nv_bfloat16*)u0, (const __nv_bfloat16*)u1, (const __nv_bfloat16*)u2}, B};
   p.dout = (const __nv_bfloat16*)dout; p.residual = (const __nv_bfloat16*)residual;
-  p.scale = scale; p.shift = shift; p.mean = mean; p.rstd = rstd; p.sums = sums;
+  p.scale = scale; p.shift = shift; p.mean = mean; p.rstd = rstd;
+  p.sums = scratch; p.part = scratch + (size_t)(1 + B) * C;
   p.du[0] = (__nv_bfloat16*)du0; p.du[1] = (__nv_bfloat16*)du1; p.du[2] = (__nv_bfloat16*)du2;
   p.dres = (__nv_bfloat16*)dres;
   p.M = M; p.C = C; p.act = act; p.slope = slope; p.train = train; p.res_after = res_after;
@@ -672,17 +768,24 @@ int hb_bn_act_bwd_bf16(const void* dout, const void* u0, const void* u1, const v
   cudaStream_t st = (cudaStream_t)stream;
   static const int cap_red_env = env_int("HB_BN_CAP_RED", 0), cap_app_env = env_int("HB_BN_CAP_APPLY", 0);
   // one branch (Darknet / ReXNet / UNet blocks): ~70 registers and a 48 KB ring -> three resident blocks per SM
-  const int cap_red = cap_red_env > 0 ? cap_red_env : (B <= 1 ? 3 : 2);
+  int cap_red = cap_red_env > 0 ? cap_red_env : (B <= 1 ? 3 : 2);
+  if (cap_red > 3) cap_red = 3;   // hb_bn_bwd_scratch_doubles sizes the partials for <= 3 blocks per SM
   const int cap_app = cap_app_env > 0 ? cap_app_env : (B <= 1 ? 3 : 2);
-  if (train || (dgamma && dbeta)) {
+  const bool want_params = (dgamma && dbeta) || gamma_grad_acc || beta_grad_acc;
+  if (train || want_params) {
     const dim3 grid = make_grid(g, M, 1, cap_red);
     const size_t smem = sizeof(SlabConsts) + kThreads * 8 * sizeof(float) + ring_bytes(B + 2);
     HB_BN_DISPATCH(bn_act_bwd_reduce_kernel, B, grid, smem, st, p, g)
     HB_LAUNCH_CHECK();
-    if (dgamma && dbeta && B > 0) {
-      bn_param_grads_kernel<<<dim3((C + 127) / 128, B), 128, 0, st>>>(sums, mean, rstd, B, C, dgamma, dbeta);
-      HB_LAUNCH_CHECK();
+    BwdFinalizeParams f{};
+    f.part = p.part; f.sums = p.sums; f.mean = mean; f.rstd = rstd; f.dgamma = dgamma; f.dbeta = dbeta;
+    for (int b = 0; b < B; ++b) {
+      f.gacc[b] = gamma_grad_acc ? gamma_grad_acc[b] : nullptr;
+      f.bacc[b] = beta_grad_acc ? beta_grad_acc[b] : nullptr;
     }
+    f.nblocks = (int)grid.x; f.B = B; f.C = C; f.C_logical = C_logical > 0 ? C_logical : C;
+    bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(f);
+    HB_LAUNCH_CHECK();
   }
   {
     const dim3 grid = make_grid(g, M, 1, cap_app);

@@ -49,6 +49,7 @@ struct RowsParams {
   __nv_bfloat16* y;
   const float* bias;
   const __nv_bfloat16* residual;
+  float* stats;      // optional [2 * gridDim.x][Cout][2] (sum, sum of squares) partials of the bf16 output, see conv_fprop.cu
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -183,6 +184,11 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const int et = (threadIdx.x - 64) & 127;  // thread index inside the group
     uint8_t* sout = sout0 + (size_t)group * sout_bytes;
     const int chunks_per_row = p.BN / 8;
+    // column statistics: thread = (column pair pr, pixel subset rg) over the valid pixels of every sub-tile it stages
+    const int npairs = p.BN >> 1, rgs = 128 / npairs;
+    const int st_rg = et / npairs, st_pr = et - st_rg * npairs;
+    const bool st_on = p.stats != nullptr && st_rg < rgs;
+    float st0 = 0.f, st1 = 0.f, sq0 = 0.f, sq1 = 0.f;
     int it = 0;
     long long subctr = 0;   // running sub-tile counter: sub-tile j belongs to group j & 1
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -273,8 +279,41 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           if (c8 >= chunks_per_row) { c8 -= chunks_per_row; ++q; }
           if (q >= p.W) { q -= p.W; ++i; }
         }
+        if (st_on && !p.residual) {
+          // statistics of the staged bf16 tile over its valid pixels (junk columns q >= W and rows past the image skipped)
+          const int npix = rows_valid * p.W;
+          int si = st_rg / p.W, sq = st_rg - si * p.W;
+          const int sdi = rgs / p.W, sdq = rgs - sdi * p.W;
+          const uint8_t* sp = sout + st_pr * 4;
+          for (int v = st_rg; v < npix; v += rgs) {
+            const float2 f = __bfloat1622float2(
+                *reinterpret_cast<const __nv_bfloat162*>(sp + (size_t)(si * p.Wp + sq) * p.out_pitch));
+            st0 += f.x; st1 += f.y; sq0 = fmaf(f.x, f.x, sq0); sq1 = fmaf(f.y, f.y, sq1);
+            sq += sdq; si += sdi;
+            if (sq >= p.W) { sq -= p.W; ++si; }
+          }
+        }
       }
       subctr += p.NSUB;
+    }
+    if (p.stats) {
+      // fold the pixel subsets in a fixed order; every (slot, channel) is written (zeros included)
+      if (group == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
+      float4* scratch = reinterpret_cast<float4*>(sout);
+      scratch[et] = make_float4(st0, st1, sq0, sq1);
+      if (group == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (et < p.BN) {
+        const int pr = et >> 1, hi = et & 1;
+        float sv = 0.f, qv = 0.f;
+        for (int rg = 0; rg < rgs; ++rg) {
+          const float4 v = scratch[rg * npairs + pr];
+          sv += hi ? v.y : v.x;
+          qv += hi ? v.w : v.z;
+        }
+        *reinterpret_cast<float2*>(p.stats + ((size_t)(blockIdx.x * 2 + group) * p.Cout + et) * 2) = make_float2(sv, qv);
+      }
     }
   }
 
@@ -291,7 +330,9 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 // same output:  y = conv3x3(x, w) + sum_e conv1x1(xe[e], we[e]).
 int hb_conv_rows_try(const void* x, const void* w, void* y, const float* bias, const void* residual, int N, int H, int W,
                      int Cin, int Cout, int act, int num_ctas, cudaStream_t stream, int nextra = 0,
-                     const void* const* xe = nullptr, const void* const* we = nullptr) {
+                     const void* const* xe = nullptr, const void* const* we = nullptr, float* stats = nullptr,
+                     int* stat_slots = nullptr) {
+  if (stats && (residual || !stat_slots)) return -1;
   if (Cout % 16 != 0 || Cout > 128 || Cin % 8 != 0 || Cin > 128) return -1;
   const int Wp = W + 2;
   if (Wp > 128 || W < 8 || nextra < 0 || nextra > 2) return -1;
@@ -326,6 +367,7 @@ int hb_conv_rows_try(const void* x, const void* w, void* y, const float* bias, c
   p.num_tiles = N * p.tiles_per_img;
   p.act = act;
   p.y = (__nv_bfloat16*)y; p.bias = bias; p.residual = (const __nv_bfloat16*)residual;
+  p.stats = stats;
 
   CUtensorMap tmX, tmW, tmXe[2], tmWe[2];
   {
@@ -359,6 +401,7 @@ int hb_conv_rows_try(const void* x, const void* w, void* y, const float* bias, c
   if (smem_bytes > 227 * 1024) return -1;
   int grid = num_ctas > 0 ? num_ctas : HB_NUM_SMS;
   if (grid > p.num_tiles) grid = p.num_tiles;
+  if (stat_slots) *stat_slots = 2 * grid;
   conv_rows_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmX, tmW, tmXe[0], tmWe[0], tmXe[1], tmWe[1], p);
   g_hb_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;

@@ -216,8 +216,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
 // dw[i] = sum_k ws[k][i] in a fixed order (deterministic). blockDim = (32, 8): threadIdx.x walks float4 columns,
 // threadIdx.y takes the slices k = y, y+8, ...; the 8 partial sums are combined through shared memory in y order.
 // (A single thread per column walking up to 148 slices serially took 23 us per launch: latency, not bandwidth.)
+// Elements [0, n_first) go to dw, [n_first, n) to dw2 (two gradient tensors filled by one launch; n_first % 4 == 0);
+// accumulate != 0: dw += sum instead of dw = sum (gradient accumulation straight into the parameter's .grad storage, what
+// autograd's AccumulateGrad would do with one more element-wise kernel per parameter and step).
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, long long n,
-                                                           int k_splits) {
+                                                           int k_splits, float* __restrict__ dw2, long long n_first,
+                                                           int accumulate) {
   __shared__ float4 part[8][32];
   const long long i4 = ((long long)blockIdx.x * 32 + threadIdx.x) * 4;
   const int y = threadIdx.y;
@@ -243,18 +247,25 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
       const float4 v = part[j][threadIdx.x];
       r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w;
     }
+    float* dst = i4 < n_first ? dw + i4 : dw2 + (i4 - n_first);
     if (i4 + 3 < n) {
-      *reinterpret_cast<float4*>(dw + i4) = r;
+      if (accumulate) {
+        const float4 o = *reinterpret_cast<const float4*>(dst);
+        r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
+      }
+      *reinterpret_cast<float4*>(dst) = r;
     } else {
       const float t[4] = {r.x, r.y, r.z, r.w};
-      for (int j = 0; j < 4 && i4 + j < n; ++j) dw[i4 + j] = t[j];
+      for (int j = 0; j < 4 && i4 + j < n; ++j) dst[j] = accumulate ? dst[j] + t[j] : t[j];
     }
   }
 }
 
-inline void launch_wgrad_reduce(const float* ws, float* dw, long long n, int slices, cudaStream_t st) {
+inline void launch_wgrad_reduce(const float* ws, float* dw, long long n, int slices, cudaStream_t st, float* dw2 = nullptr,
+                                long long n_first = -1, int accumulate = 0) {
   const unsigned blocks = (unsigned)((n / 4 + 32) / 32);
-  wgrad_reduce_kernel<<<blocks, dim3(32, 8), 0, st>>>(ws, dw, n, slices);
+  if (n_first < 0 || !dw2) { n_first = n; dw2 = dw; }
+  wgrad_reduce_kernel<<<blocks, dim3(32, 8), 0, st>>>(ws, dw, n, slices, dw2, n_first, accumulate);
 }
 
 struct WgradPlan {
@@ -329,8 +340,9 @@ size_t hb_conv2d_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout, i
 
 // dW (fp32, [Cout,R,S,Cin]) = wgrad(x [N,H,W,Cin] bf16, dy [N,Ho,Wo,Cout] bf16). Overwrites dW.
 // Requirements: Cin % 8 == 0, Cout % 8 == 0, 16-byte aligned pointers.
-int hb_conv2d_wgrad_bf16(const void* x, const void* dy, float* dw, float* workspace, size_t workspace_bytes, int N, int H,
-                         int W, int Cin, int Cout, int R, int S, int stride, int pad, int dil, int num_ctas, void* stream) {
+static int wgrad_impl(const void* x, const void* dy, float* dw, float* workspace, size_t workspace_bytes, int N, int H,
+                      int W, int Cin, int Cout, int R, int S, int stride, int pad, int dil, int num_ctas, void* stream,
+                      int accumulate) {
   if (Cin % 8 != 0 || Cout % 8 != 0) return (int)cudaErrorInvalidValue;
   if (!hb::aligned16(x) || !hb::aligned16(dy) || !hb::aligned16(dw)) return (int)cudaErrorMisalignedAddress;
   cudaStream_t st = (cudaStream_t)stream;
@@ -340,7 +352,7 @@ int hb_conv2d_wgrad_bf16(const void* x, const void* dy, float* dw, float* worksp
     const int rc = hb_wgrad_rows_try(x, dy, nullptr, workspace, workspace_bytes, N, H, W, Cin, Cout, num_ctas, st, &slices);
     if (rc == 0) {
       const long long n = (long long)Cout * 9 * Cin;
-      launch_wgrad_reduce(workspace, dw, n, slices, st);
+      launch_wgrad_reduce(workspace, dw, n, slices, st, nullptr, -1, accumulate);
       HB_LAUNCH_CHECK();
       return 0;
     }
@@ -349,6 +361,9 @@ int hb_conv2d_wgrad_bf16(const void* x, const void* dy, float* dw, float* worksp
   WgradPlan plan{};
   if (int rc = plan_wgrad(plan, N, H, W, Cin, Cout, R, S, stride, pad, dil, num_ctas)) return rc;
   WgradParams& p = plan.p;
+  // accumulation happens in the fixed-order reduction kernel: it needs the workspace path (more than one pixel range)
+  if (accumulate && !(p.k_splits > 1 && workspace && workspace_bytes >= plan.ws_bytes && hb::aligned16(workspace)))
+    return (int)cudaErrorNotSupported;
   const int RS = R * S;
   const int k_splits = p.k_splits;
   const int base_units = p.num_co_tiles * p.num_ci_tiles * p.num_tap_groups;
@@ -389,10 +404,24 @@ int hb_conv2d_wgrad_bf16(const void* x, const void* dy, float* dw, float* worksp
   HB_LAUNCH_CHECK();
   if (p.use_atomics == 2) {
     const long long n = p.dw_elems;
-    launch_wgrad_reduce(workspace, dw, n, k_splits, st);
+    launch_wgrad_reduce(workspace, dw, n, k_splits, st, nullptr, -1, accumulate);
     HB_LAUNCH_CHECK();
   }
   return 0;
+}
+
+int hb_conv2d_wgrad_bf16(const void* x, const void* dy, float* dw, float* workspace, size_t workspace_bytes, int N, int H,
+                         int W, int Cin, int Cout, int R, int S, int stride, int pad, int dil, int num_ctas, void* stream) {
+  return wgrad_impl(x, dy, dw, workspace, workspace_bytes, N, H, W, Cin, Cout, R, S, stride, pad, dil, num_ctas, stream, 0);
+}
+
+// dW += wgrad(x, dy): the fixed-order reduction adds onto the existing contents of dw (e.g. the parameter's .grad view in
+// the flat gradient bucket). Returns cudaErrorNotSupported (801) without touching dw when the shape runs as a single
+// pixel range (no reduction pass to fold the addition into): compute into a scratch tensor and add then.
+int hb_conv2d_wgrad_acc_bf16(const void* x, const void* dy, float* dw, float* workspace, size_t workspace_bytes, int N, int H,
+                             int W, int Cin, int Cout, int R, int S, int stride, int pad, int dil, int num_ctas,
+                             void* stream) {
+  return wgrad_impl(x, dy, dw, workspace, workspace_bytes, N, H, W, Cin, Cout, R, S, stride, pad, dil, num_ctas, stream, 1);
 }
 
 // Both weight gradients of a stride-1 RepVGG block (3x3 pad-1 branch and 1x1 branch over the same input,
@@ -403,10 +432,12 @@ size_t hb_repvgg_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout, i
   return hb_wgrad_rows_workspace_bytes(N, H, W, Cin, Cout, 3, 3, 1, 1, 1, num_ctas, 1);
 }
 
-int hb_repvgg_wgrad_bf16(const void* x, const void* dy3, const void* dy1, float* dw, float* workspace, size_t workspace_bytes,
-                         int N, int H, int W, int Cin, int Cout, int num_ctas, void* stream) {
+static int repvgg_wgrad_impl(const void* x, const void* dy3, const void* dy1, float* dw, float* dw1, float* workspace,
+                             size_t workspace_bytes, int N, int H, int W, int Cin, int Cout, int num_ctas, void* stream,
+                             int accumulate) {
   if (Cin % 8 != 0 || Cout % 8 != 0) return (int)cudaErrorInvalidValue;
-  if (!hb::aligned16(x) || !hb::aligned16(dy3) || !hb::aligned16(dy1) || !hb::aligned16(dw) || !hb::aligned16(workspace))
+  if (!hb::aligned16(x) || !hb::aligned16(dy3) || !hb::aligned16(dy1) || !hb::aligned16(dw) || !hb::aligned16(workspace) ||
+      !hb::aligned16(dw1))
     return (int)cudaErrorMisalignedAddress;
   cudaStream_t st = (cudaStream_t)stream;
   int slices = 0;
@@ -414,9 +445,22 @@ int hb_repvgg_wgrad_bf16(const void* x, const void* dy3, const void* dy1, float*
   if (rc == -1) return (int)cudaErrorNotSupported;
   if (rc != 0) return (int)cudaErrorLaunchFailure;
   const long long n = (long long)Cout * 10 * Cin;
-  launch_wgrad_reduce(workspace, dw, n, slices, st);
+  launch_wgrad_reduce(workspace, dw, n, slices, st, dw1, dw1 ? (long long)Cout * 9 * Cin : -1, accumulate);
   HB_LAUNCH_CHECK();
   return 0;
+}
+
+int hb_repvgg_wgrad_bf16(const void* x, const void* dy3, const void* dy1, float* dw, float* workspace, size_t workspace_bytes,
+                         int N, int H, int W, int Cin, int Cout, int num_ctas, void* stream) {
+  return repvgg_wgrad_impl(x, dy3, dy1, dw, nullptr, workspace, workspace_bytes, N, H, W, Cin, Cout, num_ctas, stream, 0);
+}
+
+// dW3 [Cout,3,3,Cin] += ..., dW1 [Cout,Cin] += ...: the two gradients ADDED to separate destination buffers (the .grad
+// storage of the two branch filters), one pass over x, one reduction launch.
+int hb_repvgg_wgrad_acc_bf16(const void* x, const void* dy3, const void* dy1, float* dw3, float* dw1, float* workspace,
+                             size_t workspace_bytes, int N, int H, int W, int Cin, int Cout, int num_ctas, void* stream) {
+  if (!dw1) return (int)cudaErrorInvalidValue;
+  return repvgg_wgrad_impl(x, dy3, dy1, dw3, dw1, workspace, workspace_bytes, N, H, W, Cin, Cout, num_ctas, stream, 1);
 }
 
 }  // extern "C"

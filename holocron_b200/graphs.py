@@ -28,7 +28,11 @@ class GraphedTrainStep:
     Args:
         step_fn: runs one full training step on the given tensors and returns the (device) loss tensor
         example_inputs: tensors with the shapes / dtypes / device of every later call
-        warmup: eager executions on a side stream before the capture (allocator, lazy initialisation, autotuning)
+        warmup: eager executions on a side stream before the capture (allocator, lazy initialisation, autotuning).
+            At least TWO are always run: the first builds the lazily-created device tables (multi-tensor filter packing,
+            optimizer tensor tables - pageable host-to-device copies, illegal during capture), the second exercises the
+            steady-state path that is then captured. NOTE: warm-up executions are REAL training steps - they update the
+            parameters, the optimizer state and the BatchNorm running statistics.
     """
 
     def __init__(self, step_fn: Callable[..., Tensor], example_inputs: Sequence[Tensor], warmup: int = 3) -> None:
@@ -36,7 +40,7 @@ class GraphedTrainStep:
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for _ in range(max(1, warmup)):
+            for _ in range(max(2, warmup)):
                 step_fn(*self.static_inputs)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()

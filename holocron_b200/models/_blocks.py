@@ -42,7 +42,10 @@ def conv_bn_act(x: Tensor, conv: nn.Conv2d, bn: Optional[nn.BatchNorm2d], act: O
         if bn is None and residual is None:
             code, slope = K.act_code(act)
             return K.conv2d_bias_act(x, conv.weight, conv.bias, conv.stride[0], conv.padding[0], code, slope)
-        y = K.conv2d(x, conv.weight, conv.bias, conv.stride[0], conv.padding[0], keep_padded=keep_padded or bn is not None)
+        # training-mode BatchNorm next: the convolution's epilogue also produces the per-channel statistics of its output
+        stats = bn is not None and (bn.training or bn.running_mean is None)
+        y = K.conv2d(x, conv.weight, conv.bias, conv.stride[0], conv.padding[0], keep_padded=keep_padded or bn is not None,
+                     want_stats=stats)
     elif _depthwise_ok(conv):
         from ..nn._dwconv import dwconv2d
         y = dwconv2d(x, conv.weight, conv.bias, conv.stride[0], conv.padding[0])

@@ -111,7 +111,7 @@ class ReXBlock(nn.Module):
         else:
             u = K.act_only(tdw, *K.act_code(mods[i]))                        # ReLU6
         proj, bn_proj = mods[i + 1], mods[i + 2]                             # 1x1 projection -> BN (+ shortcut)
-        out = K.conv2d(u, proj.weight, proj.bias, 1, 0, keep_padded=True)
+        out = K.conv2d(u, proj.weight, proj.bias, 1, 0, keep_padded=True, want_stats=bn_proj.training)
         res = _pad_channels(xin, out.shape[1]) if self.use_shortcut else None
         out = K.bn_act([out], [bn_proj], K.ACT_NONE, residual=res)
         return out if keep_padded else out[:, :self.out_channels]

@@ -1,7 +1,7 @@
 """``DropBlock2d`` on the fused mask / apply kernels (csrc/dropblock.cu).
 
 Public surface of holocron/nn/modules/dropblock.py:14-41: constructor ``(p=0.1, block_size=7, inplace=False)``, attributes
-``p`` / ``block_size`` / ``inplace``, the ``repr`` string, identity in eval mode.
+``p`` / ``block_size`` / ``inplace``, the ``drop_prob`` property, the ``repr`` string, identity in eval mode.
 """
 from torch import Tensor, nn
 
@@ -26,6 +26,10 @@ class DropBlock2d(nn.Module):
     def extra_repr(self) -> str:
         return ", ".join(f"{name}={getattr(self, name)}" for name in _REPR_FIELDS)
 
+    @property
+    def drop_prob(self) -> float:
+        """Public attribute of the reference (dropblock.py:33-35): ``p`` divided by the block area."""
+        return self.p / self.block_size**2
+
     def forward(self, x: Tensor) -> Tensor:
-        seed_prob = self.p / (self.block_size * self.block_size)
-        return dropblock2d(x, seed_prob, self.block_size, self.inplace, self.training)
+        return dropblock2d(x, self.drop_prob, self.block_size, self.inplace, self.training)

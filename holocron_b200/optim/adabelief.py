@@ -4,7 +4,7 @@ from typing import Callable, Iterable, List, Optional, Tuple
 
 import torch
 from torch import Tensor
-from torch.optim import Optimizer
+from torch.optim import Adam
 
 from .._lib import check, lib, ptr, stream_ptr
 from ._multi_tensor import TensorTable, bump_versions, effective_strides
@@ -21,7 +21,7 @@ def _launch(table: TensorTable, step: int, amsgrad: bool, beta1: float, beta2: f
           "hb_adabelief_step")
 
 
-class AdaBelief(Optimizer):
+class AdaBelief(Adam):
     """AdaBelief (https://arxiv.org/abs/2010.07468) with the reference's exact update (adabelief.py:121-167):
     L2 weight decay folded into the gradient, no ``+eps`` inside the belief EMA, bias-corrected step.
 
@@ -37,20 +37,25 @@ class AdaBelief(Optimizer):
 
     def __init__(self, params: Iterable, lr: float = 1e-3, betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 0, amsgrad: bool = False, **kwargs) -> None:
-        if lr < 0.0:
-            raise ValueError(f"Invalid learning rate: {lr}")
-        if eps < 0.0:
-            raise ValueError(f"Invalid epsilon value: {eps}")
-        if not 0.0 <= betas[0] < 1.0:
-            raise ValueError(f"Invalid beta parameter at index 0: {betas[0]}")
-        if not 0.0 <= betas[1] < 1.0:
-            raise ValueError(f"Invalid beta parameter at index 1: {betas[1]}")
-        if weight_decay < 0.0:
-            raise ValueError(f"Invalid weight_decay value: {weight_decay}")
-        defaults = {"lr": lr, "betas": betas, "eps": eps, "weight_decay": weight_decay, "amsgrad": amsgrad}
-        defaults.update({k: v for k, v in kwargs.items() if k in ("foreach", "maximize", "capturable", "differentiable",
-                                                                 "fused")})
-        super().__init__(params, defaults)
+        # the reference inherits torch.optim.Adam.__init__ (adabelief.py:16): same validation, same defaults keys.
+        # Adam's implementation switches are accepted; `foreach` / `fused` select torch code paths that do not exist
+        # here (always ONE fused multi-tensor launch per group) and are only recorded, while flags that would change
+        # the arithmetic of the kernel are refused instead of being silently ignored.
+        if kwargs.get("maximize"):
+            raise NotImplementedError("AdaBelief(maximize=True): the fused kernel implements gradient descent only")
+        if kwargs.get("differentiable"):
+            raise NotImplementedError("AdaBelief(differentiable=True) is not supported by the fused kernel")
+        unknown = set(kwargs) - {"foreach", "maximize", "capturable", "differentiable", "fused", "decoupled_weight_decay"}
+        if unknown:
+            raise TypeError(f"unexpected keyword arguments {sorted(unknown)}")
+        if kwargs.get("decoupled_weight_decay"):
+            raise NotImplementedError("AdaBelief folds weight decay into the gradient (reference adabelief.py:149-150)")
+        switches = {k: kwargs[k] for k in ("foreach", "fused") if k in kwargs}
+        super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=amsgrad,
+                         capturable=bool(kwargs.get("capturable", False)))
+        for group in self.param_groups:
+            group.update(switches)
+        self.defaults.update(switches)
         self._tables = {}
         self._step_dev = {}
 

@@ -38,6 +38,26 @@ int hb_nl_relu_bwd_from_out(const void* y, const void* dy, void* dx, size_t n, f
 int hb_conv2d_fprop_bf16(const void* x, const void* w, void* y, const float* bias, const void* residual, int N, int H,
                          int W, int Cin, int Cout, int R, int S, int stride, int pad, int dil, int act, int num_ctas,
                          void* stream);
+/* General form of the above (one kernel launch), used by the fused RepVGG block (repvgg.py:71-73) and by every
+ * conv -> BatchNorm2d unit of conv_sequence (utils.py:71-76) in training mode:
+ *   K extension   xe != NULL: y += conv1x1(xe [N,Ho,Wo,Ce], we [Cout,1,1,Ce]) in the SAME accumulator (stride-1 layers:
+ *                 the input gradient of both RepVGG branches, dX = dgrad3x3(dY3) + dgrad1x1(dY1) (+ residual));
+ *   dual output   w2 != NULL: y2 [N,Ho,Wo,Cout] = conv1x1(x, w2 [Cout,1,1,Cin]; same stride, pad 0) from the centre-tap
+ *                 loads of the RxS convolution (pad must be (R/2)*dil): x is read once for both RepVGG branches;
+ *   statistics    stats / stats2 != NULL: per-channel (sum, sum of squares) partials of the bf16 outputs y / y2 as
+ *                 float [*stat_slots][Cout][2]; the caller allocates hb_conv_stat_slots_max() slots, the launch writes
+ *                 the first *stat_slots (host int) completely; summing the slots in order is deterministic. This replaces
+ *                 the separate statistics pass of training-mode BatchNorm2d.
+ * bias / residual / act apply to y only. Fields not used must be zero. */
+typedef struct hb_conv_args {
+  const void* x; const void* w; void* y; const float* bias; const void* residual;
+  int N, H, W, Cin, Cout, R, S, stride, pad, dil, act, num_ctas;
+  const void* xe; const void* we; int Ce;
+  const void* w2; void* y2;
+  float* stats; float* stats2;
+} hb_conv_args;
+int hb_conv2d_fused_bf16(const hb_conv_args* args, int* stat_slots, void* stream);
+int hb_conv_stat_slots_max(void);
 /* y = conv3x3(x, w; stride 1, pad 1) + sum_{e<nextra} conv1x1(xe_e, we_e), one accumulator (nextra <= 2; all inputs
  * [N,H,W,Cin] bf16, w [Cout,3,3,Cin], we_e [Cout,1,1,Cin]). Input gradient of a RepVGG block in one kernel
  * (holocron/models/classification/repvgg.py:71-73). Returns cudaErrorNotSupported (801) when the filter does not fit the
@@ -58,6 +78,15 @@ int hb_conv2d_wgrad_bf16(const void* x, const void* dy, float* dw, float* worksp
 size_t hb_repvgg_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout, int num_ctas);
 int hb_repvgg_wgrad_bf16(const void* x, const void* dy3, const void* dy1, float* dw, float* workspace, size_t workspace_bytes,
                          int N, int H, int W, int Cin, int Cout, int num_ctas, void* stream);
+/* Accumulating forms: the fixed-order reduction ADDS onto dw / dw3 / dw1 (the parameters' .grad storage, e.g. views of
+ * the flat data-parallel gradient bucket) instead of overwriting - what autograd's AccumulateGrad does with one more
+ * element-wise kernel per parameter and step. hb_conv2d_wgrad_acc_bf16 returns cudaErrorNotSupported (801), dw untouched,
+ * for shapes that run as a single pixel range. */
+int hb_conv2d_wgrad_acc_bf16(const void* x, const void* dy, float* dw, float* workspace, size_t workspace_bytes, int N, int H,
+                             int W, int Cin, int Cout, int R, int S, int stride, int pad, int dil, int num_ctas,
+                             void* stream);
+int hb_repvgg_wgrad_acc_bf16(const void* x, const void* dy3, const void* dy1, float* dw3, float* dw1, float* workspace,
+                             size_t workspace_bytes, int N, int H, int W, int Cin, int Cout, int num_ctas, void* stream);
 /* fp32 KRSC master filter -> bf16 KRSC [CoutF][R][S][CinP] (zero-padded rows / channels) and, if wd != NULL, the
  * flipped + transposed bf16 filter [CinD][R][S][CoutP] used by the data-gradient pass */
 int hb_pack_conv_weights(const float* w, void* wf, void* wd, int Cout, int Cin, int R, int S, int CinP, int CinD,
@@ -90,15 +119,20 @@ int hb_im2col_smallc_bf16(const void* x, void* col, int N, int C, int H, int W, 
 
 /* ---- BatchNorm2d + branch sum + activation, fused: BatchNorm2d/act emitted by conv_sequence
  *      (holocron/models/utils.py:73-78) and the branch sum of RepBlock.forward (repvgg.py:71-73) ------------- */
-/* per-channel sum / sum of squares of up to 3 tensors [M,C] bf16 into sums (double [B][2][C], pre-zeroed) */
-int hb_bn_stats_bf16(const void* u0, const void* u1, const void* u2, int B, int M, int C, double* sums, void* stream);
-/* gamma, beta, running_mean/var, num_batches_tracked: HOST arrays of B device pointers (entries may be NULL). Outputs fp32
- * [B][C]. Updates the running statistics with `momentum` (unbiased variance) and increments the int64
- * num_batches_tracked counters, like nn.BatchNorm2d in training mode. */
-int hb_bn_finalize(const double* sums, const float* const* gamma, const float* const* beta, float* const* running_mean,
-                   float* const* running_var, long long* const* num_batches_tracked, float* mean, float* rstd,
-                   float* scale, float* shift, int B, int C, int C_logical, int M, float eps, float momentum,
-                   void* stream);
+/* Training-mode statistics are carried as PARTIALS: float [slots][C][2] = per-channel (sum, sum of squares) of a
+ * subset of the rows, written by the producer of the tensor (hb_conv2d_fused_bf16's stats/stats2, hb_bn_act_fwd_bf16's
+ * out_stats) or by this stand-alone pass over u [M,C] bf16 (capacity hb_bn_stat_slots_max() slots, *slots = host int
+ * out). hb_bn_finalize adds the slots of each branch in a fixed order in fp64: no floating-point atomics anywhere, two
+ * runs give bit-identical statistics. */
+int hb_bn_stats_partials_bf16(const void* u, int M, int C, float* parts, int* slots, void* stream);
+int hb_bn_stat_slots_max(void);
+/* parts, slots, gamma, beta, running_mean/var, num_batches_tracked: HOST arrays of B entries (device pointers / ints;
+ * pointer entries other than parts may be NULL). Outputs fp32 [B][C]. Updates the running statistics with `momentum`
+ * (unbiased variance) and increments the int64 num_batches_tracked counters, like nn.BatchNorm2d in training mode. */
+int hb_bn_finalize(const float* const* parts, const int* slots, const float* const* gamma, const float* const* beta,
+                   float* const* running_mean, float* const* running_var, long long* const* num_batches_tracked,
+                   float* mean, float* rstd, float* scale, float* shift, int B, int C, int C_logical, int M, float eps,
+                   float momentum, void* stream);
 /* channels in [C_logical, C) are zero padding (the parameter arrays hold C_logical entries): scale = shift = 0 */
 int hb_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                       float eps, int C, int C_logical, float* scale, float* shift, float* mean, float* rstd,
@@ -106,13 +140,20 @@ int hb_bn_eval_affine(const float* gamma, const float* beta, const float* runnin
 /* out = act(sum_b (scale_b * u_b + shift_b) + residual)  [res_after = 1: act(sum_b ...) + residual, the shortcut of
  * holocron/models/classification/resnet.py:75-87 (_ResBlock.forward) used by the Darknet ResBlocks]; act: 0 none 1 relu 2 relu6 3 silu 4 leaky(slope) 5 mish
  * 6 hard_mish, 7 funnel: out = max(sum_b(...), residual) (FReLU, holocron/nn/modules/activation.py:58-82) */
+/* out_stats (optional): (sum, sum of squares) partials of the bf16 OUTPUT, float [*out_stat_slots][C][2] (capacity
+ * hb_bn_stat_slots_max()): the statistics of the identity-branch BatchNorm of the next RepVGG block, for free. */
 int hb_bn_act_fwd_bf16(const void* u0, const void* u1, const void* u2, int B, const float* scale, const float* shift,
                        const void* residual, void* out, int M, int C, int act, float slope, int res_after,
-                       void* stream);
-/* backward of the above; sums: double [1+B][C] pre-zeroed scratch; du_b/dres/dgamma/dbeta may be NULL */
+                       float* out_stats, int* out_stat_slots, void* stream);
+/* backward of the above; scratch: double [hb_bn_bwd_scratch_doubles(M, C, B)] (uninitialised); du_b/dres/dgamma/dbeta may
+ * be NULL; gamma_grad_acc / beta_grad_acc: optional HOST arrays of B device pointers (entries may be NULL) to the fp32
+ * [C_logical] gradient buffers of the BatchNorm weight / bias, which dgamma_b / dbeta_b are ADDED to (deterministic
+ * fixed-order reductions, no atomics). */
+size_t hb_bn_bwd_scratch_doubles(int M, int C, int B);
 int hb_bn_act_bwd_bf16(const void* dout, const void* u0, const void* u1, const void* u2, int B, const float* scale,
-                       const float* shift, const float* mean, const float* rstd, const void* residual, double* sums,
-                       void* du0, void* du1, void* du2, void* dres, float* dgamma, float* dbeta, int M, int C, int act,
+                       const float* shift, const float* mean, const float* rstd, const void* residual, double* scratch,
+                       void* du0, void* du1, void* du2, void* dres, float* dgamma, float* dbeta,
+                       float* const* gamma_grad_acc, float* const* beta_grad_acc, int C_logical, int M, int C, int act,
                        float slope, int train, int res_after, void* stream);
 
 /* ---- depth-wise k x k convolution (NHWC bf16; weights fp32 [C,K,K]): FReLU's conv (activation.py:71-73) and the

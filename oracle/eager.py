@@ -42,7 +42,7 @@ def _narrow(t: Tensor, c: int) -> Tensor:
 
 
 def _conv2d(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, stride: int = 1, padding: int = 0, dilation: int = 1,
-            keep_padded: bool = False) -> Tensor:
+            keep_padded: bool = False, want_stats: bool = False) -> Tensor:
     return TF.conv2d(_narrow(x, weight.shape[1]).float(), weight, bias, stride, padding, dilation)
 
 
@@ -51,7 +51,8 @@ def _conv2d_bias_act(x, weight, bias, stride, padding, act=0, slope=0.0):
 
 
 def _bn_act(us: Sequence[Tensor], bns: Sequence[nn.BatchNorm2d], act: int = 0, slope: float = 0.0,
-            residual: Optional[Tensor] = None, training: Optional[bool] = None, res_after_act: bool = False) -> Tensor:
+            residual: Optional[Tensor] = None, training: Optional[bool] = None, res_after_act: bool = False,
+            emit_stats: bool = False) -> Tensor:
     z = None
     for u, bn in zip(us, bns):
         t = bn(_narrow(u, bn.num_features).float())

@@ -72,20 +72,35 @@ def teacher_forcing():
     rep = Report()
     orig_conv, orig_bn, orig_unit = _fused.conv2d_forward_raw, _fused.bn_act, _blocks.conv_bn_act
 
-    def conv(x, wf, cout, r, s, stride, pad, dil, bias=None, residual=None, act=0):
-        y = orig_conv(x, wf, cout, r, s, stride, pad, dil, bias=bias, residual=residual, act=act)
+    def conv(x, wf, cout, r, s, stride, pad, dil, bias=None, residual=None, act=0, **kw):
+        out = orig_conv(x, wf, cout, r, s, stride, pad, dil, bias=bias, residual=residual, act=act, **kw)
+        y, y2 = out if isinstance(out, tuple) else (out, None)
         with torch.no_grad():
             ref = TF.conv2d(x.float(), wf[:cout].permute(0, 3, 1, 2).float(), None if bias is None else bias[:cout].float(),
                             stride, pad, dil)
+            if kw.get("xe") is not None:      # K extension: a second 1x1 source in the same accumulator
+                ref = ref + TF.conv2d(kw["xe"].float(), kw["we"][:cout].permute(0, 3, 1, 2).float())
             if residual is not None:
                 ref = ref + residual.float()
             if act == 1:
                 ref = ref.relu()
             rep.convs.append(((tuple(x.shape), tuple(wf.shape), stride, pad), _rel(y.float(), ref)))
-        return y
+            if y2 is not None:               # dual output: the 1x1 branch from the centre-tap loads
+                ref2 = TF.conv2d(x.float(), kw["w2"][:cout].permute(0, 3, 1, 2).float(), None, stride, 0, dil)
+                rep.convs.append(((tuple(x.shape), tuple(kw["w2"].shape), stride, 0), _rel(y2.float(), ref2)))
+            if kw.get("want_stats"):         # epilogue statistics vs the stored bf16 output
+                for t in (y, y2):
+                    if t is None:
+                        continue
+                    parts, slots = _fused.get_stats(t)
+                    tot = parts[:slots].double().sum(0)
+                    tf = t.double()
+                    ref_s = torch.stack([tf.sum((0, 2, 3)), (tf * tf).sum((0, 2, 3))], 1)
+                    rep.convs.append((("stats", tuple(t.shape)), _rel(tot, ref_s)))
+        return out
 
-    def bn_act(us, bns, act=0, slope=0.0, residual=None, training=None, res_after_act=False):
-        out = orig_bn(us, bns, act, slope, residual, training, res_after_act)
+    def bn_act(us, bns, act=0, slope=0.0, residual=None, training=None, res_after_act=False, emit_stats=False):
+        out = orig_bn(us, bns, act, slope, residual, training, res_after_act, emit_stats)
         with torch.no_grad():
             tr = bns[0].training if training is None else training
             z = sum(_bn_ref(u, bn, tr) for u, bn in zip(us, bns))

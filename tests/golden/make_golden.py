@@ -373,6 +373,20 @@ def gen_api():
         for name in names:
             d[f"{mod_path}.{name}"] = describe_signature(getattr(mod, name))
     (OUT / "api_signatures.json").write_text(json.dumps(d, indent=1, sort_keys=True))
+    # classes: public base classes (isinstance contract, e.g. AdaBelief is a torch.optim.Adam) and public properties
+    # (e.g. DropBlock2d.drop_prob) of the reference's classes -> tests/golden/api_classes.json
+    import inspect
+    c = {}
+    for mod_path, names in API_SURFACE.items():
+        mod = functools.reduce(getattr, mod_path.split("."), holocron)
+        for name in names:
+            obj = getattr(mod, name)
+            if not inspect.isclass(obj):
+                continue
+            bases = [f"{b.__module__}.{b.__qualname__}" for b in obj.__mro__[1:] if b.__module__.startswith("torch")]
+            props = sorted(k for k, v in vars(obj).items() if isinstance(v, property) and not k.startswith("_"))
+            c[f"{mod_path}.{name}"] = {"torch_bases": bases, "properties": props}
+    (OUT / "api_classes.json").write_text(json.dumps(c, indent=1, sort_keys=True))
 
 
 if __name__ == "__main__" and "--api" in sys.argv:

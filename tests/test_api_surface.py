@@ -48,6 +48,26 @@ def test_public_signatures_match_reference():
     assert not problems, "\n".join(problems)
 
 
+def test_public_classes_keep_reference_bases_and_properties():
+    """isinstance contract and public properties of the reference's classes (recorded by make_golden.py --api), e.g.
+    ``isinstance(AdaBelief(...), torch.optim.Adam)`` (reference optim/adabelief.py:16) and ``DropBlock2d.drop_prob``
+    (nn/modules/dropblock.py:33-35)."""
+    ref = json.loads((GOLDEN / "api_classes.json").read_text())
+    assert "optim.AdaBelief" in ref and "nn.DropBlock2d" in ref
+    problems = []
+    for path, want in ref.items():
+        *mods, name = path.split(".")
+        cls = getattr(functools.reduce(getattr, mods, hb), name)
+        ours = {f"{b.__module__}.{b.__qualname__}" for b in cls.__mro__[1:]}
+        missing = [b for b in want["torch_bases"] if b not in ours]
+        if missing:
+            problems.append(f"{path}: not a subclass of {missing}")
+        for prop in want["properties"]:
+            if not isinstance(inspect.getattr_static(cls, prop, None), property):
+                problems.append(f"{path}: property {prop} missing")
+    assert not problems, "\n".join(problems)
+
+
 def _describe_state_dict(model):
     import hashlib
     sd = model.state_dict()

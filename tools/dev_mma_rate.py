@@ -1,7 +1,7 @@
 import sys, ctypes, torch
 sys.path.insert(0, ".")
 from holocron_b200._lib import lib_path, stream_ptr
-L = ctypes.CDLL(str(lib_path()))
+L = ctypes.CDLL(str(__import__("pathlib").Path(__file__).resolve().parent / "probes" / "libhb_probes.so"))  # python tools/probes/build.py
 L.hb_dev_mma_rate_probe.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p]
 torch.zeros(1, device="cuda")
 for ctas in (1, 148):

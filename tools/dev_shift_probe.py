@@ -1,7 +1,7 @@
 import sys, ctypes, torch
 sys.path.insert(0, ".")
 from holocron_b200._lib import lib_path, ptr, stream_ptr
-L = ctypes.CDLL(str(lib_path()))
+L = ctypes.CDLL(str(__import__("pathlib").Path(__file__).resolve().parent / "probes" / "libhb_probes.so"))  # python tools/probes/build.py
 L.hb_dev_umma_shift_probe.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 3 + [ctypes.c_void_p]
 torch.manual_seed(0)
 rows = 384
