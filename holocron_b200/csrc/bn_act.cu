@@ -206,14 +206,18 @@ __device__ __forceinline__ void unpack8(const RawVec& v, float* f) {
   for (int j = 0; j < 8; ++j) f[j] = __bfloat162float(v.v[j]);
 }
 
+__device__ __forceinline__ void lds8(const float* p, float* f);
+
 // ---- per-thread cp.async ring ---------------------------------------------------------------------
 // Every thread streams ITS OWN 16-byte vectors (one per input tensor and row) global -> shared with cp.async, kDepth rows
 // ahead of the row it is computing on; nothing else reads those slots, so the ring needs no barrier at all. This puts
 // kDepth * (#inputs) * 16 B per thread in flight without holding them in registers: the register-staged version of these
 // kernels had ~36 KB per SM in flight and sat at 2.2 - 3.4 TB/s with long-scoreboard stalls (profiles/r01_bn_ncu.md);
 // HBM needs ~60 KB per SM (44 GB/s per SM x ~1.3 us loaded latency).
-constexpr int kDepth = 3;            // rows in flight per thread
-constexpr int kSlots = kDepth + 1;   // the slot refilled at step k is the one consumed at step k-1
+// rows in flight per thread as a function of the number of streamed tensors NT: what matters is BYTES in flight per SM
+// (depth * NT * 16 B * 256 threads * resident blocks). With depth 3 the single-branch units (ReXNet / Darknet / UNet3+ /
+// YOLOv4: one input tensor) had only ~49 KB per SM in flight and ran at 1.6 TB/s; deeper rings for fewer tensors.
+__host__ __device__ constexpr int ring_depth(int nt) { return nt <= 1 ? 8 : (nt == 2 ? 6 : 3); }
 
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
@@ -231,6 +235,8 @@ __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)
 // Walks the rows m = m0, m0 + stride, ... < M of one thread. NT input tensors; `src(t)` gives tensor t's base pointer.
 template <int NT>
 struct RowRing {
+  static constexpr int kDepth = ring_depth(NT);
+  static constexpr int kSlots = kDepth + 1;   // the slot refilled at step k is the one consumed at step k-1
   uint32_t base;       // shared address of this thread's slot 0 / tensor 0
   size_t m0, stride, M;
   size_t col_off;      // element offset of the thread's 8 channels inside a row
@@ -259,30 +265,39 @@ struct RowRing {
 };
 
 // forward: out = act(sum_b scale_b*u_b + shift_b (+ residual))
-template <int NB>
-__global__ void __launch_bounds__(kThreads) bn_act_fwd_kernel(FwdParams p, Geo g) {
+// kStats: also accumulate the output statistics (separate instantiation: the plain kernel keeps its register budget; with
+// the 16 extra accumulators the 3-branch kernel would drop from 3 to 2 resident blocks per SM, so the statistics variant is
+// compiled for 3 blocks explicitly)
+template <int NB, bool kStats>
+__global__ void __launch_bounds__(kThreads, 3) bn_act_fwd_kernel(FwdParams p, Geo g) {
   extern __shared__ __align__(16) uint8_t ring_smem[];
   const int tx = threadIdx.x % g.cg_t, ty = threadIdx.x / g.cg_t;
   const int cg = blockIdx.y * g.cg_t + tx;
   const bool active = ty < g.rows_t && cg < g.cg_total;
-  if (!active && !p.out_stats) return;
   float os[8], oq[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { os[j] = 0.f; oq[j] = 0.f; }
-  if (active) {
-    float sc[NB > 0 ? NB : 1][8], sh[8];
+  // folded per-channel constants of this block's channel slab live in shared memory (read as float4 pairs per row): with
+  // them in registers the statistics variant of the 3-branch kernel spilled inside the streaming loop
+  __shared__ __align__(16) float k_sc[kMaxBranches][256];
+  __shared__ __align__(16) float k_sh[256];
+  {
+    const int nch = g.cg_t * 8;
+    for (int ch = threadIdx.x; ch < nch; ch += kThreads) {
+      const int c = blockIdx.y * nch + ch;
+      float shv = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) sh[j] = 0.f;
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        sc[b][j] = p.scale[(size_t)b * p.C + cg * 8 + j];
-        sh[j] += p.shift[(size_t)b * p.C + cg * 8 + j];
+      for (int b = 0; b < NB; ++b) {
+        k_sc[b][ch] = c < p.C ? p.scale[(size_t)b * p.C + c] : 0.f;
+        shv += c < p.C ? p.shift[(size_t)b * p.C + c] : 0.f;
       }
+      k_sh[ch] = shv;
     }
+    __syncthreads();
+  }
+  if (!active && !kStats) return;
+  if (active) {
     const bool has_res = p.residual != nullptr;
-    const bool want_stats = p.out_stats != nullptr;
     RowRing<NB + 1> ring;
     ring.base = smem_addr(ring_smem) + threadIdx.x * 16;
     ring.m0 = (size_t)blockIdx.x * g.rows_t + ty;
@@ -296,21 +311,21 @@ __global__ void __launch_bounds__(kThreads) bn_act_fwd_kernel(FwdParams p, Geo g
     ring.prologue();
     for (size_t k = 0; ring.valid(k); ++k) {
       ring.wait();
-      const int s = (int)(k % kSlots);
+      const int s = (int)(k % RowRing<NB + 1>::kSlots);
       RawVec u[NB > 0 ? NB : 1], r;
 #pragma unroll
       for (int b = 0; b < NB; ++b) u[b] = lds16(ring.addr(s, b));
       if (has_res) r = lds16(ring.addr(s, NB));
-      ring.issue(k + kDepth);
+      ring.issue(k + RowRing<NB + 1>::kDepth);
       float z[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) z[j] = sh[j];
+      lds8(&k_sh[tx * 8], z);
 #pragma unroll
       for (int b = 0; b < NB; ++b) {
-        float f[8];
+        float f[8], sc[8];
+        lds8(&k_sc[b][tx * 8], sc);
         unpack8(u[b], f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) z[j] = fmaf(sc[b][j], f[j], z[j]);
+        for (int j = 0; j < 8; ++j) z[j] = fmaf(sc[j], f[j], z[j]);
       }
       float rr[8];
       if (has_res) unpack8(r, rr);
@@ -333,7 +348,7 @@ __global__ void __launch_bounds__(kThreads) bn_act_fwd_kernel(FwdParams p, Geo g
 #pragma unroll
       for (int j = 0; j < 8; ++j) ov.v[j] = __float2bfloat16_rn(z[j]);
       st16(p.out + ring.off(k), ov);
-      if (want_stats) {
+      if (kStats) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float f = __bfloat162float(ov.v[j]);   // statistics of what the consumer will read
@@ -342,7 +357,7 @@ __global__ void __launch_bounds__(kThreads) bn_act_fwd_kernel(FwdParams p, Geo g
       }
     }
   }
-  if (!p.out_stats) return;
+  if (!kStats) return;
   // block partial of the output statistics: the ring memory is free now (every cp.async group has been waited for)
   cp_async_wait<0>();
   __syncthreads();
@@ -514,13 +529,13 @@ __global__ void __launch_bounds__(kThreads, 2) bn_act_bwd_reduce_kernel(BwdParam
     ring.prologue();
     for (size_t kk = 0; ring.valid(kk); ++kk) {
       ring.wait();
-      const int s = (int)(kk % kSlots);
+      const int s = (int)(kk % RowRing<NB + 2>::kSlots);
       RawVec uv[NB > 0 ? NB : 1], rv, dv;
 #pragma unroll
       for (int b = 0; b < NB; ++b) uv[b] = lds16(ring.addr(s, b));
       if (ring.src[NB]) rv = lds16(ring.addr(s, NB));
       dv = lds16(ring.addr(s, NB + 1));
-      ring.issue(kk + kDepth);
+      ring.issue(kk + RowRing<NB + 2>::kDepth);
       float u[NB > 0 ? NB : 1][8], dz[8], dr[8];
       recompute_dz<NB>(p, k, tx * 8, uv, rv, dv, u, dz, dr);
 #pragma unroll
@@ -565,13 +580,13 @@ __global__ void __launch_bounds__(kThreads, 2) bn_act_bwd_apply_kernel(BwdParams
   ring.prologue();
   for (size_t kk = 0; ring.valid(kk); ++kk) {
     ring.wait();
-    const int s = (int)(kk % kSlots);
+    const int s = (int)(kk % RowRing<NB + 2>::kSlots);
     RawVec uv[NB > 0 ? NB : 1], rv, dv;
 #pragma unroll
     for (int b = 0; b < NB; ++b) uv[b] = lds16(ring.addr(s, b));
     if (ring.src[NB]) rv = lds16(ring.addr(s, NB));
     dv = lds16(ring.addr(s, NB + 1));
-    ring.issue(kk + kDepth);
+    ring.issue(kk + RowRing<NB + 2>::kDepth);
     const size_t off = ring.off(kk);
     float u[NB > 0 ? NB : 1][8], dz[8], dr[8];
     recompute_dz<NB>(p, k, tx * 8, uv, rv, dv, u, dz, dr);
@@ -665,7 +680,7 @@ inline cudaError_t allow_smem(K kernel, size_t bytes) {
     default: HB_BN_LAUNCH(KERNEL, 3, GRID, SMEM, ST, __VA_ARGS__) break;                     \
   }
 
-inline size_t ring_bytes(int tensors) { return (size_t)kSlots * tensors * kThreads * 16; }
+inline size_t ring_bytes(int tensors) { return (size_t)(ring_depth(tensors) + 1) * tensors * kThreads * 16; }
 
 }  // namespace
 
@@ -735,7 +750,26 @@ int hb_bn_act_fwd_bf16(const void* u0, const void* u1, const void* u2, int B, co
   if (out_stat_slots) *out_stat_slots = (int)grid.x;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = ring_bytes(B + 1);
-  HB_BN_DISPATCH(bn_act_fwd_kernel, B, grid, smem, st, p, g)
+#define HB_FWD_CASE(NBV)                                                                                   \
+  case NBV:                                                                                                \
+    if (out_stats) {                                                                                       \
+      static bool r1 = false;                                                                              \
+      if (!r1) { if (allow_smem(bn_act_fwd_kernel<NBV, true>, 200 * 1024) != cudaSuccess) return (int)cudaErrorInvalidValue; r1 = true; } \
+      bn_act_fwd_kernel<NBV, true><<<grid, kThreads, smem, st>>>(p, g);                                    \
+    } else {                                                                                               \
+      static bool r0 = false;                                                                              \
+      if (!r0) { if (allow_smem(bn_act_fwd_kernel<NBV, false>, 200 * 1024) != cudaSuccess) return (int)cudaErrorInvalidValue; r0 = true; } \
+      bn_act_fwd_kernel<NBV, false><<<grid, kThreads, smem, st>>>(p, g);                                   \
+    }                                                                                                      \
+    break;
+  switch (B) {
+    HB_FWD_CASE(0)
+    HB_FWD_CASE(1)
+    HB_FWD_CASE(2)
+    default:
+    HB_FWD_CASE(3)
+  }
+#undef HB_FWD_CASE
   HB_LAUNCH_CHECK();
   return 0;
 }

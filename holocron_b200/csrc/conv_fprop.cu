@@ -179,8 +179,11 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const bool last_cb = ++cb == p.cblocks;
           const int ks = last_cb ? p.ksteps_last : kBK / kUmmaK;
           if (last_cb) cb = 0;
-          for (int k = 0; k < ks; ++k)
-            umma_f16_lh(d_tmem, a_lo + 2 * k, dhi, b_lo + 2 * k, dhi, idesc, (uint32_t)(kb | k));
+          // fully unrolled with a predicate per step: the single issuing thread must not pay loop overhead per MMA (a
+          // runtime-trip-count loop here cost ~20 % on every layer: the kernel is issue-rate sensitive)
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k)
+            if (k < ks) umma_f16_lh(d_tmem, a_lo + 2 * k, dhi, b_lo + 2 * k, dhi, idesc, (uint32_t)(kb | k));
           umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs have read it
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
@@ -192,8 +195,10 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint32_t a_lo = a_lo0 + (uint32_t)stage * stage_lo;
           const uint32_t b_lo = a_lo + (kABytes >> 4);
           const int ks = (ecb == p.e_cblocks - 1) ? p.e_ksteps_last : kBK / kUmmaK;
-          for (int k = 0; k < ks; ++k)
-            umma_f16_lh(d_extra, a_lo + 2 * k, dhi, b_lo + 2 * k, dhi, idesc, p.e_mode == 2 ? (uint32_t)(ecb | k) : 1u);
+          const uint32_t acc_first = p.e_mode == 2 ? (uint32_t)ecb : 1u;
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k)
+            if (k < ks) umma_f16_lh(d_extra, a_lo + 2 * k, dhi, b_lo + 2 * k, dhi, idesc, acc_first | (uint32_t)k);
           umma_commit(&empty_bar[stage]);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }

@@ -55,6 +55,19 @@ CONV_STAT_SLOTS = 2 * 148      # conv epilogues: 2 epilogue groups x (<= one CTA
 BN_STAT_SLOTS = 4 * 148        # streaming kernels: <= 4 blocks per SM
 
 
+def epilogue_stats_pay_off(k_total: int) -> bool:
+    """Whether the convolution epilogue should also produce the BatchNorm statistics of its output. The epilogue
+    warps have slack only on layers whose tile time is set by the tensor pipe (K = R*S*Cin large); on the narrow layers
+    (48 .. 96 channels) the epilogue IS the critical path and the extra shared-memory pass costs more than the stand-alone
+    statistics kernel it replaces (measured on RepVGG-A0, batch 256: +1.7 ms vs -0.5 ms per step when applied to every
+    layer). HB_FORCE_CONV_STATS / HB_DISABLE_CONV_STATS override."""
+    if os.environ.get("HB_DISABLE_CONV_STATS"):
+        return False
+    if os.environ.get("HB_FORCE_CONV_STATS"):
+        return True
+    return k_total >= 1024
+
+
 def attach_stats(t: Tensor, parts: Tensor, slots: int) -> None:
     """Marks ``t`` ([N, C, H, W] bf16 NHWC) as carrying per-channel (sum, sum of squares) partials ``parts`` [cap, C, 2]."""
     t._hb_stats = (parts, int(slots), t._version)
@@ -378,7 +391,7 @@ class _Conv2dFn(torch.autograd.Function):
         pk = pack_filter(weight, need_dx, round_up(x.shape[1], 8))
         xb = to_channels_last_bf16(x, pk.cin_p)
         y = conv2d_forward_raw(xb, pk.wf, pk.cout_p, r, s, stride, pad, dil, _pad_vec(bias, pk.cout_p),
-                               want_stats=want_stats)
+                               want_stats=want_stats and epilogue_stats_pay_off(r * s * pk.cin_p))
         ctx.save_for_backward(xb, weight)
         ctx.cfg = (stride, pad, dil, pk.wd, bias is not None, x.shape[1], pk.cout_p, pk.cin_d)
         return y if (keep_padded or pk.cout_p == cout) else y[:, :cout]
@@ -541,6 +554,8 @@ def _bn_forward_pass(us: Sequence[Tensor], stats: Tensor, res: Optional[Tensor],
     n, _, h, w = shape
     nb = len(us)
     dev = us[0].device if nb else res.device
+    if emit_stats and os.environ.get("HB_DISABLE_BN_OUT_STATS"):    # A/B switch
+        emit_stats = False
     out = _empty_cl(n, c, h, w, dev)
     ost = torch.empty((BN_STAT_SLOTS, c, 2), device=dev, dtype=torch.float32) if emit_stats else None
     sl = ctypes.c_int(0)
@@ -705,25 +720,33 @@ class _RepBlockFn(torch.autograd.Function):
         if cout % 16 != 0:
             raise NotImplementedError("fused RepBlock needs out_channels % 16 == 0")
         stem = cin <= 4 and x.shape[1] == cin and not need_dx and x.is_contiguous() and x.dtype in DTYPE_CODE
-        fused_fwd = not os.environ.get("HB_DISABLE_FUSED_FPROP")
+        # Dual-output launch (x read once, 1x1 branch from the centre-tap loads): correct and tested, but on B200 it loses to
+        # two launches - the second accumulator halves the Cout tile of the wide layers (N = 96 MMAs cost as much as N = 128)
+        # and doubles the per-tile epilogue work of the narrow ones, whose epilogue is the critical path. Opt-in (A/B).
+        fused_fwd = bool(os.environ.get("HB_FUSED_FPROP"))
         if stem:
             # network stem: explicit im2col once (27 -> 32 columns), both branches become dense GEMMs over it
             xb, w3p, w1p = _stem_im2col(x, w3, w1, stride)
             if fused_fwd:
-                y3, y1 = conv2d_forward_raw(xb, w3p, cout, 1, 1, 1, 0, 1, w2=w1p, want_stats=training)
+                y3, y1 = conv2d_forward_raw(xb, w3p, cout, 1, 1, 1, 0, 1, w2=w1p,
+                                            want_stats=training and epilogue_stats_pay_off(xb.shape[1]))
             else:
-                y3 = conv2d_forward_raw(xb, w3p, cout, 1, 1, 1, 0, 1, want_stats=training)
-                y1 = conv2d_forward_raw(xb, w1p, cout, 1, 1, 1, 0, 1, want_stats=training)
+                st = training and epilogue_stats_pay_off(xb.shape[1])
+                y3 = conv2d_forward_raw(xb, w3p, cout, 1, 1, 1, 0, 1, want_stats=st)
+                y1 = conv2d_forward_raw(xb, w1p, cout, 1, 1, 1, 0, 1, want_stats=st)
             pk3 = pk1 = None
         else:
             pk3 = pack_filter(w3, need_dx, round_up(x.shape[1], 8))
             pk1 = pack_filter(w1, need_dx, round_up(x.shape[1], 8))
             xb = to_channels_last_bf16(x, pk3.cin_p)
             if fused_fwd:
-                y3, y1 = conv2d_forward_raw(xb, pk3.wf, cout, 3, 3, stride, 1, 1, w2=pk1.wf, want_stats=training)
+                y3, y1 = conv2d_forward_raw(xb, pk3.wf, cout, 3, 3, stride, 1, 1, w2=pk1.wf,
+                                            want_stats=training and epilogue_stats_pay_off(9 * pk3.cin_p))
             else:
-                y3 = conv2d_forward_raw(xb, pk3.wf, cout, 3, 3, stride, 1, 1, want_stats=training)
-                y1 = conv2d_forward_raw(xb, pk1.wf, cout, 1, 1, stride, 0, 1, want_stats=training)
+                y3 = conv2d_forward_raw(xb, pk3.wf, cout, 3, 3, stride, 1, 1,
+                                        want_stats=training and epilogue_stats_pay_off(9 * pk3.cin_p))
+                y1 = conv2d_forward_raw(xb, pk1.wf, cout, 1, 1, stride, 0, 1,
+                                        want_stats=training and epilogue_stats_pay_off(pk3.cin_p))
         us = [y3, y1] + ([xb] if nb == 3 else [])
         n, c, h, w = y3.shape
         m = n * h * w
