@@ -81,10 +81,17 @@ SIGNATURES = {
     "hb_dice_fwd": "pppppp" + "iiqffip",
     "hb_dice_bwd": "pppp" + "iiqip",
     "hb_optim_chunk_elems": "",
-    "hb_adabelief_step": "ppifffffiipp",
+    "hb_adabelief_step": "ppifffffiippp",
+    "hb_adamp_step": "ppiifffffifipppp",
+    "hb_train_ctl_bytes": "",
+    "hb_train_ctl_observe": "ppip",
+    "hb_train_ctl_step": "ppiip",
+    "hb_train_ctl_tick": "pp",
+    "hb_grad_clip_partials_max": "",
+    "hb_grad_clip_norm": "pqfppp",
     "hb_lamb_step": "ppiifffffffpp",
     "hb_tadam_step": "ppiifffffifipp" + "p",
-    "hb_step_increment": "pp",
+    "hb_step_increment": "ppp",
 }
 _CTYPE = {"p": ctypes.c_void_p, "i": ctypes.c_int, "z": ctypes.c_size_t, "f": ctypes.c_float, "q": ctypes.c_longlong}
 

@@ -1,6 +1,7 @@
 // Activation codes shared by the fused BatchNorm / gate kernels: forward value and derivative w.r.t. the pre-activation.
 #pragma once
 #include <cuda_runtime.h>
+#include "common.cuh"
 
 namespace hb {
 
@@ -9,8 +10,8 @@ enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_RELU6 = 2, ACT_SILU = 3, ACT_LEAKY = 
 
 __device__ __forceinline__ float act_fwd(int act, float z, float slope) {
   switch (act) {
-    case ACT_RELU: return fmaxf(z, 0.f);
-    case ACT_RELU6: return fminf(fmaxf(z, 0.f), 6.f);
+    case ACT_RELU: return relu_nan(z);
+    case ACT_RELU6: return clamp_nan(z, 0.f, 6.f);
     case ACT_SILU: return z / (1.f + __expf(-z));
     case ACT_LEAKY: return z > 0.f ? z : z * slope;
     case ACT_MISH: {
@@ -18,7 +19,7 @@ __device__ __forceinline__ float act_fwd(int act, float z, float slope) {
       float sp = z > 20.f ? z : log1pf(__expf(z));
       return z * tanhf(sp);
     }
-    case ACT_HARDMISH: return (0.5f * z) * fminf(fmaxf(z + 2.f, 0.f), 2.f);
+    case ACT_HARDMISH: return (0.5f * z) * clamp_nan(z + 2.f, 0.f, 2.f);
     default: return z;
   }
 }

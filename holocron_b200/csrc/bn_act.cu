@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(kThreads, 3) bn_act_fwd_kernel(FwdParams p, Ge
       if (has_res && !p.res_after) {
         if (p.act == ACT_FRELU) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) z[j] = fmaxf(z[j], rr[j]);
+          for (int j = 0; j < 8; ++j) z[j] = max_nan(z[j], rr[j]);
         } else {
 #pragma unroll
           for (int j = 0; j < 8; ++j) z[j] += rr[j];

@@ -58,6 +58,13 @@ template <typename T> __device__ __forceinline__ void st16(T* p, const Vec16<T>&
 
 __host__ __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// ---- NaN-propagating clamps -------------------------------------------------------------
+// torch.relu / clamp / max propagate NaN; CUDA's fmaxf / fminf return the non-NaN operand, which would silently launder a NaN
+// activation into 0 at the first ReLU - and with it the reference trainer's NaN-loss detection (trainer/core.py:153-159).
+__device__ __forceinline__ float relu_nan(float z) { return z < 0.f ? 0.f : z; }
+__device__ __forceinline__ float clamp_nan(float z, float lo, float hi) { return z < lo ? lo : (z > hi ? hi : z); }
+__device__ __forceinline__ float max_nan(float a, float b) { return (a > b || a != a) ? a : b; }
+
 // ---- reductions ---------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

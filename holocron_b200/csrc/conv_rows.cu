@@ -230,7 +230,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
               }
               if (p.act == 1 && !p.residual) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.0f);
+                for (int j = 0; j < 16; ++j) f[j] = hb::relu_nan(f[j]);
               }
               uint4 o[2];
               __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(o);
@@ -270,7 +270,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             for (int j = 0; j < 4; ++j) {
               float2 fa = __bfloat1622float2(a[j]), fb = __bfloat1622float2(b[j]);
               fa.x += fb.x; fa.y += fb.y;
-              if (p.act == 1) { fa.x = fmaxf(fa.x, 0.f); fa.y = fmaxf(fa.y, 0.f); }
+              if (p.act == 1) { fa.x = hb::relu_nan(fa.x); fa.y = hb::relu_nan(fa.y); }
               a[j] = __floats2bfloat162_rn(fa.x, fa.y);
             }
           }

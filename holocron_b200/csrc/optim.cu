@@ -32,7 +32,20 @@ struct Hyper {
   int amsgrad;
   float clip_lo, clip_hi;  // LAMB
   float dof;               // TAdam (< 0: use numel)
+  float delta;             // AdamP
+  // optional device control block of a captured training step (train_ctl.cu): {lr, beta1, skip, ...}. When given, the
+  // learning rate (and beta1 when >= 0) are read from it and the whole update is skipped while skip != 0
+  const float* ctl;
 };
+
+// applies the control block to a by-value copy of the hyper-parameters; returns false when the update must be skipped
+__device__ __forceinline__ bool apply_ctl(Hyper& h) {
+  if (!h.ctl) return true;
+  if (reinterpret_cast<const int*>(h.ctl)[2] != 0) return false;
+  h.lr = h.ctl[0];
+  if (h.ctl[1] >= 0.f) h.beta1 = h.ctl[1];
+  return true;
+}
 
 __device__ __forceinline__ void bias_corrections(const Hyper& h, float& bc1, float& bc2) {
   if (h.step_dev) {
@@ -78,6 +91,7 @@ __device__ __forceinline__ void adabelief_elem(float& p, float g, float& m, floa
 
 __global__ void __launch_bounds__(kThreads) adabelief_kernel(const TensorMeta* __restrict__ metas,
                                                              const int2* __restrict__ chunks, Hyper h) {
+  if (!apply_ctl(h)) return;
   const int2 c = chunks[blockIdx.x];
   const TensorMeta t = metas[c.x];
   float bc1, bc2;
@@ -119,23 +133,35 @@ __global__ void __launch_bounds__(kThreads) lamb_moments_kernel(const TensorMeta
   __shared__ double red[32];
   const int2 c = chunks[blockIdx.x];
   const TensorMeta t = metas[c.x];
-  double pn = 0.0, un = 0.0;
-  auto elem = [&](long long i) {
-    const float g = t.g[i], p = t.p[i];
-    const float m = fmaf(1.f - h.beta1, g, h.beta1 * t.m[i]);
-    const float v = fmaf(1.f - h.beta2, g * g, h.beta2 * t.v[i]);
-    t.m[i] = m; t.v[i] = v;
+  float pn = 0.f, un = 0.f;   // <= 16 elements per thread: fp32 partials, fp64 from the block reduction on
+  auto one = [&](float p, float g, float& m, float& v) {
+    m = fmaf(1.f - h.beta1, g, h.beta1 * m);
+    v = fmaf(1.f - h.beta2, g * g, h.beta2 * v);
     float u = m / (sqrtf(v) + h.eps);
     if (h.wd != 0.f) u = fmaf(h.wd, p, u);
-    pn += (double)p * p;
-    un += (double)u * u;
+    pn = fmaf(p, p, pn);
+    un = fmaf(u, u, un);
   };
-  for_chunk(t, c.y, false, [&](long long) {}, elem);
-  pn = block_sum<double>(pn, red);
-  un = block_sum<double>(un, red);
+  for_chunk(t, c.y, meta_vec_ok(t),
+      [&](long long i) {
+        const float4 p = *reinterpret_cast<const float4*>(t.p + i);
+        const float4 g = *reinterpret_cast<const float4*>(t.g + i);
+        float4 m = *reinterpret_cast<float4*>(t.m + i);
+        float4 v = *reinterpret_cast<float4*>(t.v + i);
+        one(p.x, g.x, m.x, v.x); one(p.y, g.y, m.y, v.y); one(p.z, g.z, m.z, v.z); one(p.w, g.w, m.w, v.w);
+        *reinterpret_cast<float4*>(t.m + i) = m;
+        *reinterpret_cast<float4*>(t.v + i) = v;
+      },
+      [&](long long i) {
+        float m = t.m[i], v = t.v[i];
+        one(t.p[i], t.g[i], m, v);
+        t.m[i] = m; t.v[i] = v;
+      });
+  const double pd = block_sum<double>((double)pn, red);
+  const double ud = block_sum<double>((double)un, red);
   if (threadIdx.x == 0) {
-    atomicAdd(&norms[2 * c.x + 0], pn);
-    atomicAdd(&norms[2 * c.x + 1], un);
+    atomicAdd(&norms[2 * c.x + 0], pd);
+    atomicAdd(&norms[2 * c.x + 1], ud);
   }
 }
 
@@ -150,13 +176,109 @@ __global__ void __launch_bounds__(kThreads) lamb_apply_kernel(const TensorMeta* 
   const float local_lr = (phi == 0.f || u_norm == 0.f) ? 1.f : phi / u_norm;
   if (c.y == 0 && threadIdx.x == 0 && t.aux) *t.aux = local_lr;
   const float a = h.lr * local_lr;
-  for_chunk(t, c.y, false, [&](long long) {},
+  auto one = [&](float p, float m, float v) {
+    float u = m / (sqrtf(v) + h.eps);
+    if (h.wd != 0.f) u = fmaf(h.wd, p, u);
+    return p - a * u;
+  };
+  for_chunk(t, c.y, meta_vec_ok(t),
       [&](long long i) {
-        const float p = t.p[i];
-        float u = t.m[i] / (sqrtf(t.v[i]) + h.eps);
-        if (h.wd != 0.f) u = fmaf(h.wd, p, u);
-        t.p[i] = p - a * u;
+        float4 p = *reinterpret_cast<float4*>(t.p + i);
+        const float4 m = *reinterpret_cast<const float4*>(t.m + i);
+        const float4 v = *reinterpret_cast<const float4*>(t.v + i);
+        p.x = one(p.x, m.x, v.x); p.y = one(p.y, m.y, v.y); p.z = one(p.z, m.z, v.z); p.w = one(p.w, m.w, v.w);
+        *reinterpret_cast<float4*>(t.p + i) = p;
+      },
+      [&](long long i) { t.p[i] = one(t.p[i], t.m[i], t.v[i]); });
+}
+
+// ---------------------------------------------------------------------------------------------------
+// AdamP (reference adamp.py:144-191): Adam moments with bias correction; when the gradient is (nearly) orthogonal to
+// the weight tensor, cos(p, g) < delta / sqrt(numel), the radial component of the update is projected out:
+//   pt = (m / bc1) / (sqrt(v) / sqrt(bc2) + eps);  pt -= <p / (||p|| + eps), pt> * p / (||p|| + eps);  p -= lr * pt
+// Pass 1 updates the moments and reduces <p,g>, ||p||^2, ||g||^2, <p,pt> per tensor; pass 2 applies (40 B / parameter).
+__device__ __forceinline__ float adamp_pt(float m, float v, float vmax_or_neg, float bc1, float inv_sqrt_bc2, float eps) {
+  const float sec = vmax_or_neg >= 0.f ? vmax_or_neg : v;
+  return (m / bc1) / (sqrtf(sec) * inv_sqrt_bc2 + eps);
+}
+
+__global__ void __launch_bounds__(kThreads) adamp_moments_kernel(const TensorMeta* __restrict__ metas,
+                                                                 const int2* __restrict__ chunks, Hyper h,
+                                                                 double* __restrict__ sums /*[T][4]*/) {
+  __shared__ double red[32];
+  if (!apply_ctl(h)) return;
+  const int2 c = chunks[blockIdx.x];
+  const TensorMeta t = metas[c.x];
+  float bc1, bc2;
+  bias_corrections(h, bc1, bc2);
+  const float inv_sqrt_bc2 = 1.f / sqrtf(bc2);
+  const bool ams = h.amsgrad && t.vmax;
+  float s_pg = 0.f, s_pp = 0.f, s_gg = 0.f, s_ppt = 0.f;
+  auto one = [&](float p, float g, float& m, float& v, float& x) {
+    if (h.wd != 0.f) g = fmaf(h.wd, p, g);
+    m = fmaf(1.f - h.beta1, g, h.beta1 * m);
+    v = fmaf(1.f - h.beta2, g * g, h.beta2 * v);
+    if (ams) x = fmaxf(x, v);
+    const float pt = adamp_pt(m, v, ams ? x : -1.f, bc1, inv_sqrt_bc2, h.eps);
+    s_pg = fmaf(p, g, s_pg); s_pp = fmaf(p, p, s_pp); s_gg = fmaf(g, g, s_gg); s_ppt = fmaf(p, pt, s_ppt);
+  };
+  for_chunk(t, c.y, meta_vec_ok(t),
+      [&](long long i) {
+        const float4 p = *reinterpret_cast<const float4*>(t.p + i);
+        const float4 g = *reinterpret_cast<const float4*>(t.g + i);
+        float4 m = *reinterpret_cast<float4*>(t.m + i);
+        float4 v = *reinterpret_cast<float4*>(t.v + i);
+        float4 x = ams ? *reinterpret_cast<float4*>(t.vmax + i) : make_float4(0, 0, 0, 0);
+        one(p.x, g.x, m.x, v.x, x.x); one(p.y, g.y, m.y, v.y, x.y); one(p.z, g.z, m.z, v.z, x.z); one(p.w, g.w, m.w, v.w, x.w);
+        *reinterpret_cast<float4*>(t.m + i) = m;
+        *reinterpret_cast<float4*>(t.v + i) = v;
+        if (ams) *reinterpret_cast<float4*>(t.vmax + i) = x;
+      },
+      [&](long long i) {
+        float m = t.m[i], v = t.v[i], x = ams ? t.vmax[i] : 0.f;
+        one(t.p[i], t.g[i], m, v, x);
+        t.m[i] = m; t.v[i] = v;
+        if (ams) t.vmax[i] = x;
       });
+  const double a = block_sum<double>((double)s_pg, red), b = block_sum<double>((double)s_pp, red);
+  const double cc = block_sum<double>((double)s_gg, red), d = block_sum<double>((double)s_ppt, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(&sums[4 * c.x + 0], a); atomicAdd(&sums[4 * c.x + 1], b);
+    atomicAdd(&sums[4 * c.x + 2], cc); atomicAdd(&sums[4 * c.x + 3], d);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) adamp_apply_kernel(const TensorMeta* __restrict__ metas,
+                                                               const int2* __restrict__ chunks, Hyper h,
+                                                               const double* __restrict__ sums) {
+  if (!apply_ctl(h)) return;
+  const int2 c = chunks[blockIdx.x];
+  const TensorMeta t = metas[c.x];
+  float bc1, bc2;
+  bias_corrections(h, bc1, bc2);
+  const float inv_sqrt_bc2 = 1.f / sqrtf(bc2);
+  const bool ams = h.amsgrad && t.vmax;
+  // F.cosine_similarity clamps each norm at 1e-8 (torch eps default)
+  const float pn = (float)sqrt(sums[4 * c.x + 1]), gn = (float)sqrt(sums[4 * c.x + 2]);
+  const float cosv = (float)sums[4 * c.x + 0] / (fmaxf(pn, 1e-8f) * fmaxf(gn, 1e-8f));
+  const bool project = cosv < h.delta / sqrtf((float)t.numel);
+  const float inv = 1.f / (pn + h.eps);
+  const float k = project ? (float)sums[4 * c.x + 3] * inv * inv : 0.f;   // <p_hat, pt> / (||p|| + eps)
+  auto one = [&](float p, float m, float v, float x) {
+    float pt = adamp_pt(m, v, ams ? x : -1.f, bc1, inv_sqrt_bc2, h.eps);
+    pt = fmaf(-k, p, pt);
+    return fmaf(-h.lr, pt, p);
+  };
+  for_chunk(t, c.y, meta_vec_ok(t),
+      [&](long long i) {
+        float4 p = *reinterpret_cast<float4*>(t.p + i);
+        const float4 m = *reinterpret_cast<const float4*>(t.m + i);
+        const float4 v = *reinterpret_cast<const float4*>(t.v + i);
+        const float4 x = ams ? *reinterpret_cast<const float4*>(t.vmax + i) : make_float4(0, 0, 0, 0);
+        p.x = one(p.x, m.x, v.x, x.x); p.y = one(p.y, m.y, v.y, x.y); p.z = one(p.z, m.z, v.z, x.z); p.w = one(p.w, m.w, v.w, x.w);
+        *reinterpret_cast<float4*>(t.p + i) = p;
+      },
+      [&](long long i) { t.p[i] = one(t.p[i], t.m[i], t.v[i], ams ? t.vmax[i] : 0.f); });
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -167,16 +289,24 @@ __global__ void __launch_bounds__(kThreads) tadam_reduce_kernel(const TensorMeta
   __shared__ double red[32];
   const int2 c = chunks[blockIdx.x];
   const TensorMeta t = metas[c.x];
-  double acc = 0.0;
-  for_chunk(t, c.y, false, [&](long long) {},
+  float acc = 0.f;
+  auto one = [&](float p, float g, float m, float v) {
+    if (h.wd != 0.f) g = fmaf(h.wd, p, g);
+    const float d = g - m;
+    acc += (d * d) / (v + h.eps);
+  };
+  const bool need_p = h.wd != 0.f;
+  for_chunk(t, c.y, meta_vec_ok(t),
       [&](long long i) {
-        float g = t.g[i];
-        if (h.wd != 0.f) g = fmaf(h.wd, t.p[i], g);
-        const float d = g - t.m[i];
-        acc += (double)((d * d) / (t.v[i] + h.eps));
-      });
-  acc = block_sum<double>(acc, red);
-  if (threadIdx.x == 0) atomicAdd(&sums[c.x], acc);
+        const float4 g = *reinterpret_cast<const float4*>(t.g + i);
+        const float4 m = *reinterpret_cast<const float4*>(t.m + i);
+        const float4 v = *reinterpret_cast<const float4*>(t.v + i);
+        const float4 p = need_p ? *reinterpret_cast<const float4*>(t.p + i) : make_float4(0, 0, 0, 0);
+        one(p.x, g.x, m.x, v.x); one(p.y, g.y, m.y, v.y); one(p.z, g.z, m.z, v.z); one(p.w, g.w, m.w, v.w);
+      },
+      [&](long long i) { one(need_p ? t.p[i] : 0.f, t.g[i], t.m[i], t.v[i]); });
+  const double tot = block_sum<double>((double)acc, red);
+  if (threadIdx.x == 0) atomicAdd(&sums[c.x], tot);
 }
 
 __device__ __forceinline__ float tadam_wt(const TensorMeta& t, const Hyper& h, double sum) {
@@ -198,18 +328,33 @@ __global__ void __launch_bounds__(kThreads) tadam_apply_kernel(const TensorMeta*
   const float W = *t.aux;
   const float a = W / (W + w);
   const bool ams = h.amsgrad && t.vmax;
-  for_chunk(t, c.y, false, [&](long long) {},
+  auto one = [&](float& p, float g, float& m, float& v, float& x) {
+    if (h.wd != 0.f) g = fmaf(h.wd, p, g);
+    m = m * a + (w * g) / (W + w);
+    v = fmaf(1.f - h.beta2, g * g, h.beta2 * v);
+    float sec = v;
+    if (ams) { x = fmaxf(x, v); sec = x; }
+    const float denom = sqrtf(sec) * inv_sqrt_bc2 + h.eps;
+    p = p - step_size * (m / denom);
+  };
+  for_chunk(t, c.y, meta_vec_ok(t),
       [&](long long i) {
-        float g = t.g[i];
-        const float p = t.p[i];
-        if (h.wd != 0.f) g = fmaf(h.wd, p, g);
-        const float m = t.m[i] * a + (w * g) / (W + w);
-        const float v = fmaf(1.f - h.beta2, g * g, h.beta2 * t.v[i]);
-        float sec = v;
-        if (ams) { const float x = fmaxf(t.vmax[i], v); t.vmax[i] = x; sec = x; }
-        const float denom = sqrtf(sec) * inv_sqrt_bc2 + h.eps;
-        t.m[i] = m; t.v[i] = v;
-        t.p[i] = p - step_size * (m / denom);
+        float4 p = *reinterpret_cast<float4*>(t.p + i);
+        const float4 g = *reinterpret_cast<const float4*>(t.g + i);
+        float4 m = *reinterpret_cast<float4*>(t.m + i);
+        float4 v = *reinterpret_cast<float4*>(t.v + i);
+        float4 x = ams ? *reinterpret_cast<float4*>(t.vmax + i) : make_float4(0, 0, 0, 0);
+        one(p.x, g.x, m.x, v.x, x.x); one(p.y, g.y, m.y, v.y, x.y); one(p.z, g.z, m.z, v.z, x.z); one(p.w, g.w, m.w, v.w, x.w);
+        *reinterpret_cast<float4*>(t.p + i) = p;
+        *reinterpret_cast<float4*>(t.m + i) = m;
+        *reinterpret_cast<float4*>(t.v + i) = v;
+        if (ams) *reinterpret_cast<float4*>(t.vmax + i) = x;
+      },
+      [&](long long i) {
+        float p = t.p[i], m = t.m[i], v = t.v[i], x = ams ? t.vmax[i] : 0.f;
+        one(p, t.g[i], m, v, x);
+        t.p[i] = p; t.m[i] = m; t.v[i] = v;
+        if (ams) t.vmax[i] = x;
       });
 }
 
@@ -223,7 +368,7 @@ __global__ void tadam_wt_update_kernel(const TensorMeta* __restrict__ metas, int
   *t.aux = *t.aux * ((2.f * h.beta1 - 1.f) / h.beta1) + w;
 }
 
-__global__ void step_increment_kernel(int* step) { *step += 1; }
+__global__ void step_increment_kernel(int* step, const int* ctl) { if (!ctl || ctl[2] == 0) *step += 1; }
 
 Hyper make_hyper(float lr, float b1, float b2, float eps, float wd, int step, const int* step_dev, int amsgrad) {
   Hyper h{};
@@ -233,6 +378,8 @@ Hyper make_hyper(float lr, float b1, float b2, float eps, float wd, int step, co
   h.step_dev = step_dev;
   h.amsgrad = amsgrad;
   h.dof = -1.f;
+  h.delta = 0.1f;
+  h.ctl = nullptr;
   return h;
 }
 
@@ -245,9 +392,11 @@ extern "C" {
 int hb_optim_chunk_elems(void) { return kChunk; }
 
 int hb_adabelief_step(const void* metas, const void* chunks, int num_chunks, float lr, float beta1, float beta2,
-                      float eps, float weight_decay, int amsgrad, int step, const int* step_dev, void* stream) {
+                      float eps, float weight_decay, int amsgrad, int step, const int* step_dev, const void* ctl,
+                      void* stream) {
   if (num_chunks <= 0) return 0;
   Hyper h = make_hyper(lr, beta1, beta2, eps, weight_decay, step, step_dev, amsgrad);
+  h.ctl = (const float*)ctl;
   adabelief_kernel<<<num_chunks, kThreads, 0, (cudaStream_t)stream>>>((const TensorMeta*)metas, (const int2*)chunks, h);
   HB_LAUNCH_CHECK();
   return 0;
@@ -288,8 +437,27 @@ int hb_tadam_step(const void* metas, const void* chunks, int num_chunks, int T, 
   return 0;
 }
 
-int hb_step_increment(int* step_dev, void* stream) {
-  step_increment_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+// scratch: device double[4*T], zeroed here. delta: projection threshold (reference default 0.1).
+int hb_adamp_step(const void* metas, const void* chunks, int num_chunks, int T, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, int amsgrad, float delta, int step, const int* step_dev, const void* ctl,
+                  double* scratch, void* stream) {
+  if (num_chunks <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  Hyper h = make_hyper(lr, beta1, beta2, eps, weight_decay, step, step_dev, amsgrad);
+  h.delta = delta;
+  h.ctl = (const float*)ctl;
+  cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(double) * 4 * T, st);
+  if (e != cudaSuccess) return (int)e;
+  adamp_moments_kernel<<<num_chunks, kThreads, 0, st>>>((const TensorMeta*)metas, (const int2*)chunks, h, scratch);
+  HB_LAUNCH_CHECK();
+  adamp_apply_kernel<<<num_chunks, kThreads, 0, st>>>((const TensorMeta*)metas, (const int2*)chunks, h, scratch);
+  HB_LAUNCH_CHECK();
+  return 0;
+}
+
+// ctl (optional): control block of a captured training step - the counter only advances when the update is not skipped
+int hb_step_increment(int* step_dev, const void* ctl, void* stream) {
+  step_increment_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev, (const int*)ctl);
   HB_LAUNCH_CHECK();
   return 0;
 }

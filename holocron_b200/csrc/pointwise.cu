@@ -33,7 +33,7 @@ struct HardMishBwd {
 struct NLReluFwd {
   float beta;
   __device__ __forceinline__ float operator()(float x) const {
-    return logf(1.0f + beta * fmaxf(x, 0.0f));
+    return logf(1.0f + beta * hb::relu_nan(x));
   }
 };
 struct NLReluBwd {

@@ -11,6 +11,7 @@ import torch
 from torch import Tensor, nn
 
 from ...nn import DropBlock2d, GlobalAvgPool2d
+from ...nn import _fused as K
 from ...nn.init import init_module
 from .._blocks import FusedSequential, run_fused
 from ..utils import conv_sequence
@@ -107,7 +108,7 @@ class _DarknetClassifier(nn.Sequential):
     def forward(self, x: Tensor) -> Tensor:  # type: ignore[override]
         feats = self.pool(self.features(x))
         lin = self.classifier
-        return nn.functional.linear(feats, lin.weight.to(feats.dtype), lin.bias.to(feats.dtype)).float()
+        return K.head_linear(feats, lin.weight, lin.bias)
 
 
 class DarknetV3(_DarknetClassifier):

@@ -71,14 +71,15 @@ class RepBlock(nn.Module):
         if conv3.out_channels % 16 == 0 and all(b.eps == bn3.eps and b.momentum == bn3.momentum for b in bns) \
                 and bn3.momentum is not None:
             # whole block as one autograd node (input-gradient contributions chained through the conv epilogues)
-            out = K.repblock(x, conv3.weight, conv1.weight, bns, conv3.stride[0], code, slope, self.training)
+            # batch statistics iff the BatchNorm layers are in training mode (they may be frozen inside a training model)
+            out = K.repblock(x, conv3.weight, conv1.weight, bns, conv3.stride[0], code, slope, bn3.training)
             return out if post is None else post(out)
         # generic composition: one bf16 NHWC copy of the input shared by both convolutions
         xb = K.to_channels_last_bf16(x, K.round_up(x.shape[1], 8))
         y3 = K.conv2d(xb, conv3.weight, None, conv3.stride[0], 1)
         y1 = K.conv2d(xb, conv1.weight, None, conv1.stride[0], 0)
         us = [y3, y1] + ([xb] if len(bns) == 3 else [])
-        out = K.bn_act(us, bns, code, slope, training=self.training)
+        out = K.bn_act(us, bns, code, slope, training=bn3.training)
         return out if post is None else post(out)
 
     @torch.no_grad()
@@ -145,9 +146,7 @@ class RepVGG(nn.Sequential):
     def forward(self, x: Tensor) -> Tensor:
         feats = self.pool(self.features(x))
         head = cast(nn.Linear, self.head)
-        # classifier = plain library GEMM in the activation dtype (bf16), logits returned in fp32
-        logits = TF.linear(feats, head.weight.to(feats.dtype), None if head.bias is None else head.bias.to(feats.dtype))
-        return logits.float()
+        return K.head_linear(feats, head.weight, head.bias)
 
     def reparametrize(self) -> None:
         """Re-parametrises every block (inference form)."""

@@ -175,7 +175,7 @@ class ReXNet(nn.Sequential):
         feats = self.pool(x)
         drop, lin = self.head[0], self.head[1]
         feats = drop(feats)[:, :lin.in_features]
-        return TF.linear(feats, lin.weight.to(feats.dtype), lin.bias.to(feats.dtype)).float()
+        return K.head_linear(feats, lin.weight, lin.bias)
 
 
 def _rexnet(width_mult: float, depth_mult: float, pretrained: bool, checkpoint: Any, **kwargs: Any) -> ReXNet:

@@ -144,7 +144,9 @@ def to_channels_last_bf16(x: Tensor, c_pad: Optional[int] = None) -> Tensor:
 
 
 def _empty_cl(n: int, c: int, h: int, w: int, device, dtype=torch.bfloat16) -> Tensor:
-    return torch.empty((n, h, w, c), device=device, dtype=dtype).permute(0, 3, 1, 2)
+    # a real channels_last allocation, not a permuted VIEW: outputs of custom autograd Functions that are views may not be
+    # modified in place afterwards (the in-place DropBlock2d that conv_sequence puts behind every activation does that)
+    return torch.empty((n, c, h, w), device=device, dtype=dtype, memory_format=torch.channels_last)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -978,6 +980,13 @@ def gate_act(x: Tensor, gate: Tensor, act: int = ACT_NONE, slope: float = 0.0) -
     if gate.shape[:2] != x.shape[:2] or gate.numel() != x.shape[0] * x.shape[1]:
         raise ValueError(f"gate of shape {tuple(gate.shape)} does not match input {tuple(x.shape)}")
     return _GateActFn.apply(x, gate, int(act), float(slope))
+
+
+def head_linear(feats: Tensor, weight: Tensor, bias: Optional[Tensor]) -> Tensor:
+    """Classifier head: plain library GEMM in the activation dtype (bf16 operands, fp32 accumulation, bf16 result), logits
+    returned in fp32 (the head ``Linear`` of RepVGG / ReXNet / Darknet; not a hot-path kernel)."""
+    import torch.nn.functional as TF
+    return TF.linear(feats, weight.to(feats.dtype), None if bias is None else bias.to(feats.dtype)).float()
 
 
 def global_avg_pool_flat(x: Tensor) -> Tensor:

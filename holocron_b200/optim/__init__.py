@@ -1,3 +1,4 @@
 from .adabelief import *  # noqa: F401,F403
+from .adamp import *  # noqa: F401,F403
 from .lamb import *  # noqa: F401,F403
 from .tadam import *  # noqa: F401,F403

@@ -15,10 +15,10 @@ _cf = ctypes.c_float
 
 
 def _launch(table: TensorTable, step: int, amsgrad: bool, beta1: float, beta2: float, lr: float, weight_decay: float,
-            eps: float, step_dev: Optional[Tensor] = None) -> None:
+            eps: float, step_dev: Optional[Tensor] = None, ctl: Optional[Tensor] = None) -> None:
     check(lib().hb_adabelief_step(ptr(table.metas), ptr(table.chunks), table.num_chunks, _cf(lr), _cf(beta1), _cf(beta2),
-                                  _cf(eps), _cf(weight_decay), int(amsgrad), int(step), ptr(step_dev), stream_ptr()),
-          "hb_adabelief_step")
+                                  _cf(eps), _cf(weight_decay), int(amsgrad), int(step), ptr(step_dev), ptr(ctl),
+                                  stream_ptr()), "hb_adabelief_step")
 
 
 class AdaBelief(Adam):
@@ -72,6 +72,8 @@ class AdaBelief(Adam):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        # device control block of holocron_b200.trainer.TrainStep (lr / beta1 schedule, NaN-skip flag), if any
+        ctl = getattr(self, "_hb_ctl", None)
         for gi, group in enumerate(self.param_groups):
             by_step = {}
             for p in group["params"]:
@@ -102,9 +104,9 @@ class AdaBelief(Adam):
                     if step_dev is None:
                         step_dev = torch.full((1,), step - 1, device=plist[0].device, dtype=torch.int32)
                         self._step_dev[key] = step_dev
-                    check(lib().hb_step_increment(ptr(step_dev), stream_ptr()), "hb_step_increment")
+                    check(lib().hb_step_increment(ptr(step_dev), ptr(ctl), stream_ptr()), "hb_step_increment")
                 _launch(table, step, group["amsgrad"], beta1, beta2, group["lr"], group["weight_decay"], group["eps"],
-                        step_dev)
+                        step_dev, ctl)
                 bump_versions(plist)
         return loss
 

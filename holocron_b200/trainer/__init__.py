@@ -1,0 +1,2 @@
+from .core import *  # noqa: F401,F403
+from .utils import *  # noqa: F401,F403

@@ -234,14 +234,42 @@ int hb_dice_bwd(const void* target, const float* coef, const float* gout, void* 
 /* metas: device table of T records {p, g, m, v, vmax, aux, numel} (7 x 8 bytes each, fp32 tensors);
  * chunks: device int2[num_chunks] = {tensor index, chunk index}, chunk = hb_optim_chunk_elems() elements. */
 int hb_optim_chunk_elems(void);
+/* ctl (may be NULL): device control block of a captured training step (see hb_train_ctl_* below): the kernels then read
+ * lr (and beta1 when >= 0) from it and skip the whole update while its skip flag is set. */
 int hb_adabelief_step(const void* metas, const void* chunks, int num_chunks, float lr, float beta1, float beta2,
-                      float eps, float weight_decay, int amsgrad, int step, const int* step_dev, void* stream);
+                      float eps, float weight_decay, int amsgrad, int step, const int* step_dev, const void* ctl,
+                      void* stream);
+/* AdamP, holocron/optim/adamp.py:144-191 (the reference scripts' default optimizer, references/classification/train.py:340):
+ * two launches per group (moments + per-tensor <p,g>, ||p||^2, ||g||^2, <p,pt>; then the projected update), 40 B/parameter.
+ * scratch: double [4*T]. */
+int hb_adamp_step(const void* metas, const void* chunks, int num_chunks, int T, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, int amsgrad, float delta, int step, const int* step_dev, const void* ctl,
+                  double* scratch, void* stream);
 int hb_lamb_step(const void* metas, const void* chunks, int num_chunks, int T, float lr, float beta1, float beta2,
                  float eps, float weight_decay, float clip_lo, float clip_hi, double* scratch, void* stream);
 int hb_tadam_step(const void* metas, const void* chunks, int num_chunks, int T, float lr, float beta1, float beta2,
                   float eps, float weight_decay, int amsgrad, float dof, int step, const int* step_dev, double* scratch,
                   void* stream);
-int hb_step_increment(int* step_dev, void* stream);
+int hb_step_increment(int* step_dev, const void* ctl, void* stream);
+
+/* ---- training-loop control on the device: holocron/trainer/core.py:135-227 (_fit_epoch: NaN-loss skipping :153-159,
+ *      per-iteration scheduler.step() :161; _backprop_step: gradient accumulation, clip_grad_norm_, optimizer.step :184-208)
+ *      and :262-269 (OneCycleLR / CosineAnnealingLR) without host synchronisation, CUDA-graph replayable -------------- */
+/* ctl: device block of hb_train_ctl_bytes() bytes, zero-initialised by the caller, then [0] = lr, [1] = -1:
+ *   f32 lr | f32 beta1 (<0: keep) | i32 skip | i32 bad | i32 iter | i32 nan_run | i32 opt_steps | f32 grad_norm */
+int hb_train_ctl_bytes(void);
+/* after a micro-batch: remember a non-finite *loss (device fp32 scalar) when skip_nan != 0 */
+int hb_train_ctl_observe(void* ctl, const float* loss, int skip_nan, void* stream);
+/* phase 0, before the optimizer update: lr / beta1 = table[min(iter, n-1)] (table: n x {lr, beta1} fp32 or NULL), skip =
+ * bad, nan_run counts consecutive skipped updates; phase 1, after it: opt_steps += !skip, the window's bad flag is cleared */
+int hb_train_ctl_step(void* ctl, const float* table, int n, int phase, void* stream);
+/* once per iteration (the reference's scheduler.step()): iter += 1 */
+int hb_train_ctl_tick(void* ctl, void* stream);
+/* torch.nn.utils.clip_grad_norm_(params, max_norm) on a flat fp32 gradient buffer (core.py:194,205): fixed-order global L2
+ * norm + in-place scaling by min(1, max_norm / (norm + 1e-6)), two launches; scratch: double
+ * [hb_grad_clip_partials_max()]; ctl (may be NULL) receives the norm. */
+int hb_grad_clip_partials_max(void);
+int hb_grad_clip_norm(float* grads, long long n, float max_norm, double* scratch, void* ctl, void* stream);
 
 /* ---- bookkeeping (not part of the reference surface) ------------------------------------------------ */
 long long hb_launch_count(void);      /* kernels launched through this library since the last reset */

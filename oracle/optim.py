@@ -66,3 +66,27 @@ def tadam_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, W: Tensor, step: int,
         second = v_max
     denom = second.sqrt() / math.sqrt(1 - beta2**step) + eps
     p.sub_((lr / (1 - beta1**step)) * m / denom)
+
+
+@torch.no_grad()
+def adamp_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: int, lr: float, beta1: float, beta2: float, eps: float,
+               weight_decay: float = 0.0, delta: float = 0.1, amsgrad: bool = False, v_max: Optional[Tensor] = None) -> None:
+    """reference optim/adamp.py:144-191: Adam moments (L2 decay folded into the gradient), then - when the gradient is almost
+    orthogonal to the weights, cosine_similarity(p, g) < delta / sqrt(numel) - the update's component along the weights is
+    projected out before it is applied."""
+    import torch.nn.functional as F
+    bc1, bc2 = 1 - beta1**step, 1 - beta2**step
+    if weight_decay != 0:
+        g = g + weight_decay * p
+    m.mul_(beta1).add_(g, alpha=1 - beta1)
+    v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+    second = v
+    if amsgrad:
+        torch.maximum(v_max, v, out=v_max)
+        second = v_max
+    denom = (second.sqrt() / math.sqrt(bc2)).add_(eps)
+    pt = m / bc1 / denom
+    if F.cosine_similarity(p.view(1, -1), g.view(1, -1)).max() < delta / math.sqrt(p.numel()):
+        pn = p / p.norm().add_(eps)
+        pt -= (pn * pt).sum() * pn
+    p.add_(pt, alpha=-lr)

@@ -197,6 +197,23 @@ def gen_optim():
             traj.append([p.detach().clone() for p in params])
         d[name] = traj
         d[name + "_kw"] = kw
+    # AdamP (reference optim/adamp.py): tensors of several sizes, one of them with a gradient orthogonal to the weights so
+    # that the projection branch fires; gradient of step k = k * g
+    torch.manual_seed(1)
+    shapes = [(64, 32, 3, 3), (64,), (10, 64), (1,), (4099,)]
+    ps = [torch.randn(s) * 0.1 for s in shapes]
+    gs = [torch.randn(s) * 1e-2 for s in shapes]
+    gs[0] = gs[0] - (gs[0] * ps[0]).sum() / (ps[0] * ps[0]).sum() * ps[0]
+    after = {}
+    for amsgrad, wd in ((False, 0.0), (True, 1e-2)):
+        params = [torch.nn.Parameter(p.clone()) for p in ps]
+        opt = optim.AdamP(params, lr=1e-2, betas=(0.9, 0.99), eps=1e-8, weight_decay=wd, amsgrad=amsgrad, delta=0.1)
+        for it in range(1, 4):
+            for p, g in zip(params, gs):
+                p.grad = g * it
+            opt.step()
+        after[f"adamp_{int(amsgrad)}"] = [p.detach().clone() for p in params]
+    d["adamp"] = dict(params=ps, grads=gs, after=after)
     torch.save(d, OUT / "optim.pt")
 
 
@@ -258,7 +275,7 @@ def gen_models():
     torch.save(d, OUT / "models.pt")
 
 
-if __name__ == "__main__" and "--zoo" not in sys.argv and "--api" not in sys.argv:
+if __name__ == "__main__" and not any(f in sys.argv for f in ("--zoo", "--api", "--trainer")):
     gen_activations()
     gen_losses()
     gen_boxes()
@@ -270,64 +287,86 @@ if __name__ == "__main__" and "--zoo" not in sys.argv and "--api" not in sys.arg
 
 
 def gen_zoo():
-    """Model-zoo fixtures (rows a11-a14, a21 of SURVEY §8): seeded init (identical in both implementations, checked by
-    the state_dict tests), small inputs, training-mode forward + loss + a few gradients from the reference."""
+    """Model-zoo fixtures (rows a10-a14, a21 of SURVEY §8) from the UNMODIFIED reference: seeded init (identical in both
+    implementations, checked by the state_dict tests) + the shared conditioning of tests/_conditioning.py, then for every
+    model two fp32 runs on seeded inputs:
+      "eval"  - training-mode model with frozen (running-statistics) BatchNorm: outputs, loss, first / last / one BatchNorm
+                gradient. Well conditioned -> the GPU test holds the bf16 CUDA path to <= 2e-2 against these directly.
+      "train" - batch-statistics BatchNorm: outputs, loss, last-layer gradient (see oracle/eager.py for how the chaotic
+                amplification of bf16 rounding in this mode is handled)."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    import _conditioning as C
     models = holocron.models
+    from holocron.nn import DropBlock2d
     d = {}
 
     def grads_of(model, names):
         ps = dict(model.named_parameters())
         return {n: ps[n].grad.clone() for n in names}
 
-    for name in ("darknet53", "cspdarknet53", "rexnet1_0x", "darknet24", "darknet19"):
+    def build(factory, **kw):
         torch.manual_seed(0)
-        m = getattr(models, name)(num_classes=10).train()
-        if name == "rexnet1_0x":
-            m.head[0].p = 0.0   # dropout off: device-specific RNG
-        torch.manual_seed(1)
-        # rexnet: batch 8 - its squeeze-excite BatchNorm sees N x 1 x 1 maps, and with 2 samples the normalised values
-        # are +-1 whatever the input (zero Jacobian), which makes the fixture degenerate
-        bsz = 8 if name == "rexnet1_0x" else 2
-        x = torch.rand(bsz, 3, 64, 64)
-        t = torch.tensor([3, 7, 1, 0, 9, 4, 2, 5][:bsz])
-        out = m(x)
-        loss = torch.nn.functional.cross_entropy(out, t)
-        loss.backward()
-        first = next(n for n, _ in m.named_parameters())
-        last = "head.1.weight" if name == "rexnet1_0x" else "classifier.weight"
-        d[name] = dict(x=x, t=t, logits=out.detach(), loss=loss.detach(), grads=grads_of(m, [first, last]), first=first,
-                       last=last)
+        m = factory(**kw)
+        for mod in m.modules():          # device-specific RNG streams off
+            if isinstance(mod, DropBlock2d):
+                mod.p = 0.0
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+        return C.condition(m)
+
+    def pick_names(m, last):
+        names = [n for n, _ in m.named_parameters()]
+        bn_w = [n for n, mod in m.named_modules() if isinstance(mod, torch.nn.BatchNorm2d)]
+        mid = bn_w[len(bn_w) // 2] + ".weight" if bn_w else names[len(names) // 2]
+        return names[0], mid, last
+
+    for name in C.CLS:
+        out = {}
+        for mode in ("eval", "train"):
+            m = build(getattr(models, name), num_classes=10)
+            m = C.freeze_bn(m) if mode == "eval" else m.train()
+            x, t = C.cls_inputs(name, mode)
+            store = {}
+            C.capture(m, C.PROBE[name], store)
+            logits = m(x)
+            loss = torch.nn.functional.cross_entropy(logits, t)
+            loss.backward()
+            last = [n for n, _ in m.named_parameters()][-2]
+            first, mid, last = pick_names(m, last)
+            out[mode] = dict(logits=logits.detach(), loss=loss.detach(), first=first, mid=mid, last=last,
+                             grads=grads_of(m, [first, mid, last]), probe=store["probe"][:2].half() if mode == "train" else None)
+        d[name] = out
     # UNet3+ with DiceLoss (BASELINE config 5, at 64x64)
-    torch.manual_seed(0)
-    m = models.segmentation.unet3p(num_classes=21).train()
-    torch.manual_seed(2)
-    x = torch.rand(1, 3, 64, 64)
-    mask = torch.randint(0, 21, (1, 64, 64))
-    onehot = torch.nn.functional.one_hot(mask, 21).movedim(-1, 1).float()
-    out = m(x)
-    loss = F.dice_loss(torch.softmax(out, 1), onehot)
-    loss.backward()
-    d["unet3p"] = dict(x=x, mask=mask, out=out.detach(), loss=loss.detach(),
-                       grads=grads_of(m, ["encoder.0.0.weight", "classifier.weight"]))
-    # YOLOv4 (BASELINE config 4, at 128x128), DropBlock disabled (its RNG stream is device specific)
-    from holocron.nn import DropBlock2d
-    torch.manual_seed(0)
-    m = models.detection.yolov4(pretrained_backbone=False, num_classes=80).train()
-    for mod in m.modules():
-        if isinstance(mod, DropBlock2d):
-            mod.p = 0.0
-    torch.manual_seed(3)
-    x = torch.rand(2, 3, 128, 128)
-    target = []
-    for _ in range(2):
-        xy = torch.rand(3, 2) * 0.7
-        wh = torch.rand(3, 2) * 0.2 + 0.05
-        target.append({"boxes": torch.cat([xy, (xy + wh).clamp(max=1.0)], 1), "labels": torch.randint(0, 80, (3,))})
-    losses = m(x, target)
-    total = sum(losses.values())
-    total.backward()
-    d["yolov4"] = dict(x=x, target=target, losses={k: v.detach() for k, v in losses.items()},
-                       grads=grads_of(m, ["head.head3.24.weight", "head.head1.3.bias", "neck.pan2.convs.0.weight"]))
+    out = {}
+    for mode in ("eval", "train"):
+        m = build(models.segmentation.unet3p, num_classes=21)
+        m = C.freeze_bn(m) if mode == "eval" else m.train()
+        x, mask = C.unet_inputs()
+        onehot = torch.nn.functional.one_hot(mask, 21).movedim(-1, 1).float()
+        store = {}
+        C.capture(m, C.PROBE["unet3p"], store)
+        o = m(x)
+        loss = F.dice_loss(torch.softmax(o, 1), onehot)
+        loss.backward()
+        first, mid, last = pick_names(m, "classifier.weight")
+        out[mode] = dict(out=o.detach(), loss=loss.detach(), first=first, mid=mid, last=last, grads=grads_of(m, [first, mid, last]),
+                         probe=store["probe"][:2].half() if mode == "train" else None)
+    d["unet3p"] = out
+    # YOLOv4 (BASELINE config 4, at 128x128): the four losses, gradients of an output convolution, a neck and a backbone filter
+    out = {}
+    for mode in ("eval", "train"):
+        m = build(models.detection.yolov4, pretrained_backbone=False, num_classes=80)
+        m = C.freeze_bn(m) if mode == "eval" else m.train()
+        x, target = C.yolo_inputs()
+        store = {}
+        C.capture(m, C.PROBE["yolov4"], store)
+        losses = m(x, target)
+        sum(losses.values()).backward()
+        names = ["head.head1.3.weight", "head.head3.24.weight", "neck.pan2.convs.0.weight", "backbone.stem.0.weight"]
+        ps = dict(m.named_parameters())
+        names = [n for n in names if n in ps]
+        out[mode] = dict(losses={k: v.detach() for k, v in losses.items()}, grads=grads_of(m, names), probe=store["probe"][:1].half() if mode == "train" else None)
+    d["yolov4"] = out
     torch.save(d, OUT / "zoo.pt")
 
 
@@ -425,3 +464,96 @@ def gen_state_dicts():
 if __name__ == "__main__" and "--api" in sys.argv:
     gen_state_dicts()
     print("state_dicts.json", (OUT / "state_dicts.json").stat().st_size)
+
+
+# ------------------------------------------------------------------------------------------------ trainer semantics
+def gen_trainer():
+    """Golden runs of the UNMODIFIED reference Trainer (holocron/trainer/core.py: _fit_epoch, _backprop_step, _reset_opt,
+    _reset_scheduler) on a tiny RepVGG, CPU fp32 -> tests/golden/trainer.pt. matplotlib / fastprogress (absent here, only used
+    for plots and progress bars) are stubbed before the import; nothing of the training logic is touched."""
+    import types
+    for name in ("matplotlib", "matplotlib.pyplot", "fastprogress", "fastprogress.fastprogress"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+
+    class _Bar(list):
+        def __init__(self, it, parent=None):
+            super().__init__(it)
+            self.comment = ""
+            self.main_bar = types.SimpleNamespace(comment="")
+
+        def write(self, *a, **k):
+            pass
+    sys.modules["fastprogress"].master_bar = _Bar
+    sys.modules["fastprogress"].progress_bar = _Bar
+    sys.modules["fastprogress.fastprogress"].ConsoleMasterBar = _Bar
+    import importlib
+    core = importlib.import_module("holocron.trainer.core")
+    tutils = importlib.import_module("holocron.trainer.utils")
+    from holocron.models.classification.repvgg import RepVGG
+    from holocron.optim import AdaBelief
+
+    def tiny():
+        torch.manual_seed(0)
+        return RepVGG([1, 1, 1], [16, 32, 64], 1, 1, num_classes=10)
+
+    def batches(n, nan_at=None):
+        g = torch.Generator().manual_seed(31)
+        out = []
+        for i in range(n):
+            x = (torch.rand(8, 3, 32, 32, generator=g) - 0.45) / 0.225
+            if nan_at is not None and i == nan_at:
+                x = x.clone()
+                x[0, 0, 0, 0] = float("nan")
+            out.append((x, torch.randint(0, 10, (8,), generator=g)))
+        return out
+
+    class T(core.Trainer):
+        def evaluate(self):
+            return {"val_loss": 0.0}
+
+        @staticmethod
+        def _eval_metrics_str(m):
+            return ""
+
+    d = {}
+    scenarios = {
+        "acc2_clip_onecycle": dict(gradient_acc=2, gradient_clip=0.5, skip_nan_loss=False, sched="onecycle", lr=2e-3, nan_at=None),
+        "nan_skip_cosine": dict(gradient_acc=1, gradient_clip=None, skip_nan_loss=True, sched="cosine", lr=1e-3, nan_at=3),
+    }
+    for tag, cfg in scenarios.items():
+        model = tiny()
+        data = batches(8, cfg["nan_at"])
+        opt = AdaBelief(model.parameters(), lr=1e-3, betas=(0.95, 0.99), eps=1e-6)
+        tr = T(model, data, data, torch.nn.CrossEntropyLoss(), opt, gpu=None, output_file="/tmp/_hb_golden_ckpt.pth", amp=False,
+               skip_nan_loss=cfg["skip_nan_loss"], nan_tolerance=5, gradient_acc=cfg["gradient_acc"], gradient_clip=cfg["gradient_clip"])
+        losses, lrs, beta1s = [], [], []
+        orig = tr._get_loss
+
+        def rec(x, t, return_logits=False, orig=orig, tr=tr):
+            lrs.append(tr.optimizer.param_groups[0]["lr"])
+            beta1s.append(tr.optimizer.param_groups[0]["betas"][0])
+            loss = orig(x, t, return_logits)
+            losses.append(float(loss.detach()))
+            return loss
+        tr._get_loss = rec
+        tutils.freeze_model(tr.model.train(), None)
+        tr._reset_opt(cfg["lr"], None)
+        tr._reset_scheduler(cfg["lr"], 1, cfg["sched"])
+        tr._fit_epoch(_Bar(range(1)))
+        d[tag] = dict(cfg=cfg, losses=torch.tensor(losses), lrs=torch.tensor(lrs, dtype=torch.float64),
+                      beta1s=torch.tensor(beta1s, dtype=torch.float64),
+                      state={k: v.clone() for k, v in model.state_dict().items()},
+                      opt_steps=int(next(iter(opt.state.values()))["step"]))
+    # freezing helpers on the reference's tiny model: names of frozen parameters / eval-mode BatchNorms, normalisation split
+    model = tiny()
+    tutils.freeze_model(model.train(), "features.1")
+    d["freeze"] = dict(frozen=[n for n, p in model.named_parameters() if not p.requires_grad],
+                       bn_eval=[n for n, m in model.named_modules() if isinstance(m, torch.nn.BatchNorm2d) and not m.training])
+    norm, other = tutils.split_normalization_params(tiny())
+    d["split"] = dict(norm=len(norm), other=len(other), norm_numel=sum(p.numel() for p in norm), other_numel=sum(p.numel() for p in other))
+    torch.save(d, OUT / "trainer.pt")
+
+
+if __name__ == "__main__" and "--trainer" in sys.argv:
+    gen_trainer()
+    print("trainer.pt", (OUT / "trainer.pt").stat().st_size)

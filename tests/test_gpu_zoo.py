@@ -1,16 +1,21 @@
-"""GPU parity tests for the model-zoo rows of SURVEY §8 (a11 ReXNet, a12 Darknet, a13/a14 YOLOv4, a21 UNet3+):
-training-mode forward, loss and selected gradients of the CUDA path vs fixtures produced by the unmodified reference
-(tests/golden/make_golden.py --zoo) with identical seeded parameters.
+"""GPU parity tests for the model-zoo rows of SURVEY §8 (a10 RepVGG, a11 ReXNet, a12 Darknet v1-v4 incl. the Mish variant,
+a13/a14 YOLOv4, a21 UNet3+) against fixtures produced by the UNMODIFIED reference (tests/golden/make_golden.py --zoo) with
+identical seeded + conditioned parameters (tests/_conditioning.py) and identical seeded inputs.
 
-Two layers of checks:
-  1. teacher forcing (tests/_teacher.py): every fused launch of the forward pass is compared with fp32 torch library
-     ops on the very same input tensor - conv launches, BN/activation passes and conv-BN-act units (from the
-     fp32 master weights) all rel-L2 < 5e-3 (measured: 1.7e-3 = the bf16 output rounding). This is the kernel-correctness bar and it is the same for every model.
-  2. end to end against the fp32 fixture with a PER-MODEL tolerance. Deep random-init nets in training mode amplify
-     bf16 rounding (batch statistics over 8 samples in the last stages); the tolerance of each model is ~1.5x the
-     distance at which torch's own bf16 autocast lands from the same fixture (profiles/r01_bf16_conditioning.log:
-     darknet53 0.046, cspdarknet53 0.47, darknet19 0.155, darknet24 0.003), i.e. "as close as any bf16 execution".
-"""
+Three layers of checks, no tolerance above 5e-2 anywhere:
+
+  1. frozen-BatchNorm fixtures ("eval": training-mode model, BatchNorm on its conditioned running statistics, gradients
+     through every layer): FULL-DEPTH outputs <= 2e-2 rel-L2, loss <= 1e-2, last-layer gradient <= 5e-2 against the
+     reference's fp32 run. This is the well-conditioned end-to-end comparison. Gradients of the middle (a BatchNorm
+     weight) and FIRST layer have passed through 20-100 bf16 layers of ReLU-type masks backwards; their bar is
+     max(5e-2, 1.25 x the distance at which torch's own bf16 autocast lands on the very same fixture) - the "autocast twin"
+     is the same module tree run with stock torch ops under torch.autocast (oracle/eager.py), measured inside the test.
+  2. batch-statistics fixtures ("train"): an early probe activation (4-7 layers deep) <= 2e-2 and the full-depth loss
+     <= 5e-2 against the reference, BatchNorm running statistics of the first layers <= 1e-2. Full-depth logits of a
+     random-init network in this mode are chaotic for ANY bf16 execution (tests/_conditioning.py explains and measures
+     it); they are printed, not asserted.
+  3. teacher forcing (tests/_teacher.py) in both modes: every fused launch at every depth against fp32 torch ops on the
+     very same input tensors, rel-L2 < 5e-3 (measured 1.7e-3 = the bf16 output rounding)."""
 import pytest
 import torch
 import torch.nn.functional as TF
@@ -18,19 +23,13 @@ import torch.nn.functional as TF
 import holocron_b200 as hb
 from holocron_b200.nn import functional as F
 
+import _conditioning as C
 from _teacher import teacher_forcing
 from conftest import load_golden
 
 pytestmark = pytest.mark.gpu
 
-# model -> (logits rel-L2, loss rel, last-layer gradient rel-L2) against the fp32 fixture
-E2E_TOL = {
-    "darknet53": (8e-2, 2e-2, 0.15),
-    "cspdarknet53": (0.6, 5e-2, 0.6),
-    "rexnet1_0x": (0.35, 2e-2, 0.35),
-    "darknet24": (2e-2, 1e-2, 5e-2),
-    "darknet19": (0.25, 0.25, 0.5),
-}
+ZOO = load_golden("zoo")
 
 
 def rel_l2(a, b):
@@ -38,103 +37,238 @@ def rel_l2(a, b):
     return ((a - b).norm() / (b.norm() + 1e-20)).item()
 
 
-@pytest.mark.parametrize("name", ["darknet53", "cspdarknet53", "rexnet1_0x", "darknet24", "darknet19"])
-def test_classification_backbones(name):
-    g = load_golden("zoo")[name]
+def build(factory, **kw):
     torch.manual_seed(0)
-    m = getattr(hb.models, name)(num_classes=10)
-    if name == "rexnet1_0x":
-        m.head[0].p = 0.0
-    m = m.cuda().train()
+    m = factory(**kw)
+    for mod in m.modules():
+        if isinstance(mod, (hb.nn.DropBlock2d, torch.nn.Dropout)):
+            mod.p = 0.0
+    return C.condition(m).cuda()
+
+
+def narrow_like(t, ref):
+    return t[: ref.shape[0], : ref.shape[1]].float()
+
+
+def autocast_twin(make_model, run):
+    """Same module tree, stock torch ops under bf16 autocast on the GPU (no kernel of this package): what a library bf16
+    execution of this network achieves on the fixture. ``run(model)`` does forward + backward and returns a dict."""
+    from oracle.eager import reference_execution
+    m = make_model()
+    with reference_execution(), torch.autocast("cuda", dtype=torch.bfloat16):
+        out = run(m)
+    return m, out
+
+
+def check_grads(m, g, twin):
+    """last-layer gradient <= 5e-2; middle / first <= max(5e-2, 1.25 x the autocast twin's own distance)."""
+    ps, pt = dict(m.named_parameters()), dict(twin.named_parameters())
+    assert all(p.grad is None or torch.isfinite(p.grad).all() for p in ps.values())
+    errs = {}
+    for i, key in enumerate((g["last"], g["mid"], g["first"])):
+        e = rel_l2(ps[key].grad, g["grads"][key])
+        e_twin = rel_l2(pt[key].grad, g["grads"][key])
+        tol = 5e-2 if i == 0 else max(5e-2, 1.25 * e_twin)
+        errs[key] = (round(e, 4), round(e_twin, 4))
+        assert e < tol, (key, e, e_twin)
+    return errs
+
+
+@pytest.mark.parametrize("name", list(C.CLS))
+def test_classification_frozen_bn_full_depth(name):
+    g = ZOO[name]["eval"]
+    m = C.freeze_bn(build(getattr(hb.models, name), num_classes=10))
+    x, t = C.cls_inputs(name, "eval")
     with teacher_forcing() as rep:
-        out = m(g["x"].cuda())
+        out = m(x.cuda())
     assert out.shape == g["logits"].shape and out.dtype == torch.float32
-    loss = TF.cross_entropy(out, g["t"].cuda())
+    loss = TF.cross_entropy(out, t.cuda())
     loss.backward()
-    ps = dict(m.named_parameters())
-    tol_logits, tol_loss, tol_grad = E2E_TOL[name]
     e_logits = rel_l2(out, g["logits"])
     e_loss = abs(loss.item() - g["loss"].item()) / abs(g["loss"].item())
-    e_grad = rel_l2(ps[g["last"]].grad, g["grads"][g["last"]])
-    ratio = (ps[g["first"]].grad.float().norm().cpu() / g["grads"][g["first"]].norm()).item()
-    print(f"\n[zoo] {name}: launches {rep.worst()} logits {e_logits:.4f} loss {e_loss:.4f} last-grad {e_grad:.4f} "
-          f"first-grad norm ratio {ratio:.3f}")
-    assert len(rep.convs) > 10
+    assert len(rep.convs) + len(rep.units) > 10
     rep.assert_ok()
-    assert e_logits < tol_logits, e_logits
-    assert e_loss < tol_loss, e_loss
+    assert e_logits < 2e-2, e_logits
+    assert e_loss < 1e-2, e_loss
+
+    def run(mm):
+        o = mm(x.cuda())
+        TF.cross_entropy(o.float(), t.cuda()).backward()
+        return o
+    twin, out_twin = autocast_twin(lambda: C.freeze_bn(build(getattr(hb.models, name), num_classes=10)), run)
+    errs = check_grads(m, g, twin)
+    print(f"\n[zoo eval] {name}: launches {rep.worst()} logits {e_logits:.4f} (autocast twin {rel_l2(out_twin, g['logits']):.4f}) "
+          f"loss {e_loss:.5f} grads (ours, twin) {errs}")
+    # argmax parity wherever the reference's own decision is not a near-tie
+    top2 = g["logits"].topk(2, 1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 0.05 * g["logits"].abs().max()
+    assert torch.equal(out.argmax(1).cpu()[clear], g["logits"].argmax(1)[clear])
+
+
+@pytest.mark.parametrize("name", list(C.CLS))
+def test_classification_batch_statistics(name):
+    g = ZOO[name]["train"]
+    m = build(getattr(hb.models, name), num_classes=10).train()
+    x, t = C.cls_inputs(name, "train")
+    store = {}
+    C.capture(m, C.PROBE[name], store)
+    with teacher_forcing() as rep:
+        out = m(x.cuda())
+    loss = TF.cross_entropy(out, t.cuda())
+    loss.backward()
+    rep.assert_ok()
+    e_probe = rel_l2(narrow_like(store["probe"], g["probe"]), g["probe"].float())
+    e_loss = abs(loss.item() - g["loss"].item()) / abs(g["loss"].item())
+    e_logits = rel_l2(out, g["logits"])
+    print(f"\n[zoo train] {name}: launches {rep.worst()} probe {e_probe:.4f} loss {e_loss:.5f} (full-depth logits {e_logits:.3f}, "
+          f"chaotic - not asserted)")
+    assert e_probe < 2e-2, e_probe
+    assert e_loss < 5e-2, e_loss
+    ps = dict(m.named_parameters())
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in ps.values())
-    assert e_grad < tol_grad, e_grad
-    # first-layer gradient after 50+ bf16 layers at batch 2: element-wise agreement with an fp32 run is not defined
-    # (torch's own bf16 autocast differs from its fp32 self by rel-L2 ~0.9 here, tools/dev_gradcheck.py); check scale
-    assert 0.3 < ratio < 3.0, ratio
     m.eval()
     with torch.no_grad():
-        assert m(g["x"].cuda()).shape == g["logits"].shape
+        assert m(x.cuda()).shape == g["logits"].shape
 
 
-def test_unet3p_with_dice_loss():
-    g = load_golden("zoo")["unet3p"]
-    torch.manual_seed(0)
-    m = hb.models.unet3p(num_classes=21).cuda().train()
+@pytest.mark.parametrize("mode", ["eval", "train"])
+def test_unet3p_with_dice_loss(mode):
+    g = ZOO["unet3p"][mode]
+    m = build(hb.models.unet3p, num_classes=21)
+    m = C.freeze_bn(m) if mode == "eval" else m.train()
+    x, mask = C.unet_inputs()
+    store = {}
+    C.capture(m, C.PROBE["unet3p"], store)
     with teacher_forcing() as rep:
-        out = m(g["x"].cuda())
-    assert out.shape == (1, 21, 64, 64)
-    onehot = TF.one_hot(g["mask"].cuda(), 21).movedim(-1, 1).float()
+        out = m(x.cuda())
+    assert out.shape == (2, 21, 64, 64)
+    onehot = TF.one_hot(mask.cuda(), 21).movedim(-1, 1).float()
     loss = F.dice_loss(torch.softmax(out, 1), onehot)
     loss.backward()
-    ps = dict(m.named_parameters())
+    rep.assert_ok()
     e_out = rel_l2(out, g["out"])
     e_loss = abs(loss.item() - g["loss"].item()) / abs(g["loss"].item())
-    e_grad = rel_l2(ps["classifier.weight"].grad, g["grads"]["classifier.weight"])
-    ratio = (ps["encoder.0.0.weight"].grad.float().norm().cpu() / g["grads"]["encoder.0.0.weight"].norm()).item()
-    print(f"\n[zoo] unet3p: launches {rep.worst()} out {e_out:.4f} loss {e_loss:.4f} last-grad {e_grad:.4f} ratio {ratio:.3f}")
-    rep.assert_ok()
-    # batch 1 at 64x64: the deepest encoder stage normalises over 16 samples; bf16 autocast of the same net lands at ~0.05
-    assert e_out < 0.1, e_out
-    assert e_loss < 2e-2, e_loss
-    assert e_grad < 0.15, e_grad
-    assert 0.3 < ratio < 3.0, ratio
+    if mode == "eval":
+        def run(mm):
+            o = mm(x.cuda())
+            F_ref = __import__("oracle.functional", fromlist=["dice_loss"])
+            F_ref.dice_loss(torch.softmax(o.float(), 1), onehot).backward()
+            return o
+        twin, _ = autocast_twin(lambda: C.freeze_bn(build(hb.models.unet3p, num_classes=21)), run)
+        errs = check_grads(m, g, twin)
+        print(f"\n[zoo eval] unet3p: launches {rep.worst()} out {e_out:.4f} loss {e_loss:.5f} grads (ours, twin) {errs}")
+        assert e_out < 2e-2, e_out
+        assert e_loss < 1e-2, e_loss
+    else:
+        e_probe = rel_l2(narrow_like(store["probe"], g["probe"]), g["probe"].float())
+        print(f"\n[zoo train] unet3p: launches {rep.worst()} probe {e_probe:.4f} loss {e_loss:.5f} (full-depth out {e_out:.3f})")
+        assert e_probe < 2e-2, e_probe
+        assert e_loss < 5e-2, e_loss
 
 
-YOLO_TOL = {"obj_loss": 0.8, "noobj_loss": 0.8, "bbox_loss": 0.8, "clf_loss": 0.8}
-
-
-def test_yolov4_losses_and_inference():
-    g = load_golden("zoo")["yolov4"]
-    torch.manual_seed(0)
-    m = hb.models.yolov4(num_classes=80)
-    for mod in m.modules():
-        if isinstance(mod, hb.nn.DropBlock2d):
-            mod.p = 0.0
-    m = m.cuda().train()
-    target = [{k: v.cuda() for k, v in t.items()} for t in g["target"]]
+@pytest.mark.parametrize("mode", ["eval", "train"])
+def test_yolov4_losses(mode):
+    g = ZOO["yolov4"][mode]
+    m = build(hb.models.yolov4, num_classes=80)
+    m = C.freeze_bn(m) if mode == "eval" else m.train()
+    x, target = C.yolo_inputs()
+    target = [{k: v.cuda() for k, v in t.items()} for t in target]
+    store = {}
+    C.capture(m, C.PROBE["yolov4"], store)
     with teacher_forcing() as rep:
-        losses = m(g["x"].cuda(), target)
+        losses = m(x.cuda(), target)
     assert set(losses) == set(g["losses"])
-    print("\n[zoo] yolov4: launches", rep.worst(), {k: (round(v.item(), 4), round(g["losses"][k].item(), 4))
-                                                    for k, v in losses.items()})
     rep.assert_ok()
-    # The objectness / box terms depend on which anchors clear the IoU thresholds against the (random-init) predictions:
-    # a discrete assignment that bf16 noise in a 100+-layer net flips for a few anchors. The per-launch checks above are
-    # the parity bar; end to end the losses must stay in the fixture's neighbourhood.
-    for k, v in losses.items():
-        assert v.requires_grad and torch.isfinite(v).all()
-        ref = g["losses"][k].item()
-        assert abs(v.item() - ref) <= YOLO_TOL[k] * abs(ref) + 1e-3, (k, v.item(), ref)
+    errs = {k: abs(v.item() - g["losses"][k].item()) / abs(g["losses"][k].item()) for k, v in losses.items()}
+    print(f"\n[zoo {mode}] yolov4: launches {rep.worst()} loss errors {errs}")
     sum(losses.values()).backward()
     ps = dict(m.named_parameters())
-    e_grad = rel_l2(ps["head.head1.3.bias"].grad, g["grads"]["head.head1.3.bias"])
-    print("[zoo] yolov4 head bias grad rel", e_grad)
-    assert e_grad < 1.0, e_grad
     assert all(p.grad is None or torch.isfinite(p.grad).all() for p in ps.values())
+    tol = {k: (2e-2 if mode == "eval" else 5e-2) for k in losses}
+    if mode == "train":
+        # obj_loss = squared error of SIX assigned anchors' objectness against the IoU of their feature-dependent boxes: with
+        # batch-statistics BatchNorm over 2 images it inherits the full-depth chaos of the 100+-layer network (this path
+        # lands 0.31 away, torch's bf16 autocast twin 0.14, two runs of either differ as much). It is held to 2e-2 in the
+        # frozen-BatchNorm fixture above; here the three terms that average over many cells / classes are asserted.
+        del tol["obj_loss"]
+    for k, v in losses.items():
+        assert v.requires_grad and torch.isfinite(v).all()
+        if k in tol:
+            assert errs[k] < tol[k], (k, v.item(), g["losses"][k].item())
+    if mode == "eval":
+        gerr = {k: rel_l2(ps[k].grad, ref) for k, ref in g["grads"].items()}
+        print("[zoo eval] yolov4 gradients", gerr)
+        assert all(e < 5e-2 for e in gerr.values()), gerr
+    else:
+        e_probe = rel_l2(narrow_like(store["probe"], g["probe"]), g["probe"].float())
+        assert e_probe < 2e-2, e_probe
+
+
+def test_yolov4_empty_targets_and_inference():
+    m = build(hb.models.yolov4, num_classes=80).train()
+    x, _ = C.yolo_inputs()
     # empty ground truth (reference tests/test_models_detection.py:60-64) and eval-mode detections
     empty = [{"boxes": torch.zeros((0, 4), device="cuda"), "labels": torch.zeros(0, dtype=torch.long, device="cuda")}] * 2
-    out = m(g["x"].cuda(), empty)
+    out = m(x.cuda(), empty)
     assert all(torch.isfinite(v).all() for v in out.values())
     m.eval()
     with torch.no_grad():
-        dets = m(g["x"].cuda())
+        dets = m(x.cuda())
     assert len(dets) == 2 and all(set(d) == {"boxes", "scores", "labels"} for d in dets)
     with pytest.raises(ValueError):
-        m.train()(g["x"].cuda())
+        m.train()(x.cuda())
+
+
+def test_yolov4_with_dropblock_trains():
+    """The default YOLOv4 (in-place DropBlock2d behind every activation, reference yolov4.py:665-666) runs forward + backward."""
+    torch.manual_seed(0)
+    m = hb.models.yolov4(num_classes=80).cuda().train()
+    x, target = C.yolo_inputs()
+    target = [{k: v.cuda() for k, v in t.items()} for t in target]
+    losses = m(x.cuda(), target)
+    sum(losses.values()).backward()
+    assert all(torch.isfinite(v).all() for v in losses.values())
+    assert all(p.grad is None or torch.isfinite(p.grad).all() for p in m.parameters())
+
+
+def test_repvgg_a0_adabelief_loss_trajectory():
+    """Five AdaBelief steps (the bench's hyper-parameters) of the full RepVGG-A0 on a fixed batch against the fp32 oracle
+    (reference RepVGG + reference AdaBelief update, oracle/models.py + oracle/optim.py).
+
+    At random init the per-parameter gradients of this 28-layer network carry ~70 % relative bf16 noise for ANY bf16
+    execution, torch's own autocast included (profiles/r02_bf16_gradient_conditioning.log: every weight gradient is a
+    small difference of large sums), and AdaBelief's first updates are sign-like (lr / (beta1 + eps/|g|)), so trajectories
+    separate after two steps whatever the kernel. Asserted here: the first loss (1e-2) and the same qualitative fit of the
+    batch. The tight multi-step comparison (8 iterations, losses to 1e-3, against the reference's own Trainer) runs on a
+    3-stage RepVGG in tests/test_gpu_trainer.py, where the gradient signal-to-noise ratio is sane."""
+    from oracle.models import RepVGGOracle
+    from oracle.optim import adabelief_step
+    torch.manual_seed(0)
+    ours = hb.models.repvgg_a0(num_classes=10)
+    ref = RepVGGOracle("repvgg_a0", num_classes=10)
+    ref.load_state_dict(ours.state_dict())
+    g = torch.Generator().manual_seed(21)
+    x = (torch.rand(16, 3, 64, 64, generator=g) - 0.45) / 0.225
+    t = torch.randint(0, 10, (16,), generator=g)
+    ref.train()
+    state = [(torch.zeros_like(p), torch.zeros_like(p)) for p in ref.parameters()]
+    ref_losses = []
+    for i in range(1, 6):
+        loss = TF.cross_entropy(ref(x), t)
+        loss.backward()
+        for p, (mm, ss) in zip(ref.parameters(), state):
+            adabelief_step(p.data, p.grad, mm, ss, i, 1e-3, 0.95, 0.99, 1e-6)
+            p.grad = None
+        ref_losses.append(loss.item())
+    ours = ours.cuda().train()
+    opt = hb.optim.AdaBelief(ours.parameters(), lr=1e-3, betas=(0.95, 0.99), eps=1e-6)
+    our_losses = []
+    for _ in range(5):
+        loss = TF.cross_entropy(ours(x.cuda()), t.cuda())
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+        our_losses.append(loss.item())
+    print("\n[trajectory] oracle", [round(v, 4) for v in ref_losses], "cuda", [round(v, 4) for v in our_losses])
+    assert abs(our_losses[0] - ref_losses[0]) / abs(ref_losses[0]) < 1e-2
+    assert ref_losses[-1] < 0.6 * ref_losses[0] and our_losses[-1] < 0.6 * our_losses[0]
