@@ -71,7 +71,16 @@ def test_train_step_reproduces_reference_trainer(tag, graph):
     p0 = torch.cat([init[k].flatten() for k in keys])
     e_all = rel_l2(ours, ref_p)
     cos = torch.nn.functional.cosine_similarity(ours - p0, ref_p - p0, dim=0).item()
-    stats = max(rel_l2(sd[k], v) for k, v in d["state"].items() if "running" in k)
+    # running statistics: the NaN batch poisons them in the reference as well (its forward pass is not skipped) - the NaN
+    # pattern must be identical, the finite entries close
+    stats = 0.0
+    for k, v in d["state"].items():
+        if "running" in k:
+            mine = sd[k].detach().float().cpu()
+            assert torch.equal(torch.isnan(mine), torch.isnan(v)), k
+            ok = ~torch.isnan(v)
+            if ok.any():
+                stats = max(stats, rel_l2(mine[ok], v[ok]))
     print(f"[trainer {tag}] parameters rel-L2 {e_all:.5f}, update cosine {cos:.4f}, running statistics {stats:.4f}")
     assert e_all < 2e-2 and cos > 0.9 and stats < 5e-2
     step.check()   # nan_run never exceeded the tolerance
