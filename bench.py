@@ -429,7 +429,7 @@ def measure(args, wl: Workload, rank: int, local_rank: int, world: int, full: bo
     import holocron_b200 as hb
     from holocron_b200.nn import _fused as K
     from holocron_b200.nn import functional as hbF
-    from holocron_b200.distributed import GradBucket, broadcast_parameters
+    from holocron_b200.distributed import GradBucket, OverlappedReducer, broadcast_parameters
     from holocron_b200._lib import lib
     from holocron_b200.graphs import GraphedTrainStep
 
@@ -446,10 +446,22 @@ def measure(args, wl: Workload, rank: int, local_rank: int, world: int, full: bo
     if devb[0].ndim == 4:
         devb[0] = devb[0].contiguous()
 
+    # N > 1: the gradient all-reduce leaves in chunks on a side stream while backward is still running (stage boundaries of
+    # model.features); the un-overlapped tail is the first stages' few MB
+    reducer = None
+    if world > 1 and not args.no_overlap and not args.no_direct_grads:
+        bounds = OverlappedReducer.stage_boundaries(model)
+        if bounds:
+            reducer = OverlappedReducer(bucket, bounds)
+
     def eager_step(*b, collective=True, optimizer=True):
+        if reducer is not None:
+            reducer.enabled = collective
         loss = wl.loss(model, hbF, *b)
         loss.backward()
-        if collective:
+        if collective and reducer is not None:
+            reducer.finish()
+        elif collective:
             bucket.all_reduce_mean()
         if optimizer:
             opt.step()
@@ -536,6 +548,8 @@ def measure(args, wl: Workload, rank: int, local_rank: int, world: int, full: bo
         "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": wl.desc, "batch_per_gpu": batch, "global_batch": images, "parallelism": f"dp{world}",
+                   "allreduce": ("none" if world == 1 else ("overlapped chunks on a side stream" if reducer is not None
+                                                            else "single all-reduce after backward")),
                    "l2": "per-step working set (GBs of activations) exceeds the 126 MB L2; no explicit flush",
                    "launch": "cuda_graph" if graphed is not None else "eager"},
         "e2e": {"value": images / ms_e2e * 1e3, "unit": "images/s", "ms_per_step": ms_e2e,
@@ -576,6 +590,7 @@ def main():
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the torch-eager (cuDNN) baseline leg on the GPU")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel of the step eagerly (no CUDA graph)")
     ap.add_argument("--no-direct-grads", action="store_true", help="let autograd accumulate parameter gradients (A/B switch)")
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: one all-reduce after backward instead of overlapped chunks")
     ap.add_argument("--no-secondary", action="store_true", help="skip the ReXNet-1.0x leg (BASELINE configs[1]) at N=1")
     args = ap.parse_args()
     if args.config:

@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from holocron_b200.distributed import GradBucket, broadcast_parameters, shard_batch
+from holocron_b200.distributed import GradBucket, OverlappedReducer, broadcast_parameters, shard_batch
 
 
 def _free_port() -> int:
@@ -85,3 +85,74 @@ def test_shard_batch_covers_everything():
     for n, w in ((256, 8), (10, 3), (5, 8)):
         seen = [i for r in range(w) for i in shard_batch(n, r, w)]
         assert seen == list(range(n))
+
+
+class _Staged(torch.nn.Module):
+    """Toy model with a `features` Sequential of four parameterised stages + head (the shape stage_boundaries expects)."""
+
+    def __init__(self) -> None:
+        super().__init__()
+        def stage(cin, cout):
+            return torch.nn.Sequential(torch.nn.Conv2d(cin, cout, 3, padding=1), torch.nn.BatchNorm2d(cout), torch.nn.ReLU())
+        self.features = torch.nn.Sequential(stage(3, 8), stage(8, 8), stage(8, 16), stage(16, 16))
+        self.head = torch.nn.Linear(16, 5)
+
+    def forward(self, x):
+        return self.head(self.features(x).mean((2, 3)))
+
+
+def _worker_overlap(rank: int, world: int, port: int, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(3)
+    model = _Staged()
+    bucket = GradBucket(model.parameters())
+    bounds = OverlappedReducer.stage_boundaries(model)
+    assert len(bounds) == 2                                   # stages 1 and 2: chunks {head, stage 3}, {stage 2}, {stages 1, 0}
+    reducer = OverlappedReducer(bucket, bounds)
+    assert reducer.ends == sorted(reducer.ends, reverse=True) and reducer.ends[-1] > 0
+    torch.manual_seed(50 + rank)
+    x, t = torch.randn(4, 3, 6, 6), torch.randint(0, 5, (4,))
+    grads = []
+    for _ in range(2):                                        # two steps: the per-step state of the reducer resets
+        torch.nn.functional.cross_entropy(model(x), t).backward()
+        reducer.finish()
+        grads.append(bucket.flat.clone())
+        bucket.zero_()
+    # reference: plain single all-reduce of the locally computed gradient
+    torch.nn.functional.cross_entropy(model(x), t).backward()
+    # (the hooks fired again during this backward and reduced their prefixes; finish() completes the tail)
+    reducer.finish()
+    local = bucket.flat.clone()
+    torch.save((grads, local), os.path.join(out, f"ovl{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_overlapped_reducer_equals_mean_allreduce(tmp_path):
+    world = 2
+    ctx = mp.get_context("spawn")
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_overlap, args=(r, world, port, str(tmp_path))) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    (g0, l0), (g1, l1) = [torch.load(tmp_path / f"ovl{r}.pt") for r in range(world)]
+    # chunked reduction gives every rank the same averaged bucket, step after step
+    for a, b in zip(g0, g1):
+        assert torch.equal(a, b)
+    assert torch.allclose(g0[0], g0[1], atol=1e-7) and torch.equal(l0, l1) and torch.allclose(l0, g0[0], atol=1e-7)
+    # ... equal to the mean of the two ranks' local gradients (recomputed in this process)
+    ref = None
+    for rank in range(world):
+        torch.manual_seed(3)
+        model = _Staged()
+        torch.manual_seed(50 + rank)
+        x, t = torch.randn(4, 3, 6, 6), torch.randint(0, 5, (4,))
+        bucket = GradBucket(model.parameters())
+        torch.nn.functional.cross_entropy(model(x), t).backward()
+        ref = bucket.flat.clone() / world if ref is None else ref + bucket.flat / world
+    assert torch.allclose(g0[0], ref, atol=1e-6)
