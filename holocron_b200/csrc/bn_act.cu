@@ -127,25 +127,33 @@ struct FinalizeParams {
   int C_logical;  // channels >= C_logical are padding: scale = shift = 0, no parameter / running-stat access
   float eps, momentum;
 };
-// one warp per (branch, channel): lanes stride over the slots, fixed-shape shuffle tree -> run-to-run identical result
+// block = 32 channels (threadIdx.x, coalesced reads of the [slot][C][2] partials) x 8 slot lanes (threadIdx.y): each lane
+// adds its slots in order, the 8 lane sums are combined in lane order -> fixed summation order, run-to-run identical.
+// (One warp per channel with lanes striding over the slots read one 8-byte element per 32-byte sector: 10 us per launch.)
 __global__ void __launch_bounds__(256) bn_finalize_kernel(FinalizeParams p) {
-  const int lane = threadIdx.x & 31;
-  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  __shared__ double red[2][8][32];
+  const int c = blockIdx.x * 32 + threadIdx.x;
   const int b = blockIdx.y;
-  if (c >= p.C) return;
+  double s = 0.0, q = 0.0;
+  if (c < p.C_logical) {
+    const float* pp = p.parts[b] + (size_t)c * 2;
+    for (int k = threadIdx.y; k < p.slots[b]; k += 8) {
+      const float2 v = *reinterpret_cast<const float2*>(pp + (size_t)k * p.C * 2);
+      s += (double)v.x; q += (double)v.y;
+    }
+  }
+  red[0][threadIdx.y][threadIdx.x] = s;
+  red[1][threadIdx.y][threadIdx.x] = q;
+  __syncthreads();
+  if (threadIdx.y != 0 || c >= p.C) return;
   const size_t o = (size_t)b * p.C + c;
   if (c >= p.C_logical) {
-    if (lane == 0) { p.mean[o] = 0.f; p.rstd[o] = 0.f; p.scale[o] = 0.f; p.shift[o] = 0.f; }
+    p.mean[o] = 0.f; p.rstd[o] = 0.f; p.scale[o] = 0.f; p.shift[o] = 0.f;
     return;
   }
-  double s = 0.0, q = 0.0;
-  const float* pp = p.parts[b] + (size_t)c * 2;
-  for (int k = lane; k < p.slots[b]; k += 32) {
-    const float2 v = *reinterpret_cast<const float2*>(pp + (size_t)k * p.C * 2);
-    s += (double)v.x; q += (double)v.y;
-  }
-  s = warp_sum(s); q = warp_sum(q);
-  if (lane != 0) return;
+  s = 0.0; q = 0.0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s += red[0][j][threadIdx.x]; q += red[1][j][threadIdx.x]; }
   const double mean = s / p.M;
   double var = q / p.M - mean * mean;
   if (var < 0) var = 0;
@@ -217,7 +225,8 @@ __device__ __forceinline__ void lds8(const float* p, float* f);
 // rows in flight per thread as a function of the number of streamed tensors NT: what matters is BYTES in flight per SM
 // (depth * NT * 16 B * 256 threads * resident blocks). With depth 3 the single-branch units (ReXNet / Darknet / UNet3+ /
 // YOLOv4: one input tensor) had only ~49 KB per SM in flight and ran at 1.6 TB/s; deeper rings for fewer tensors.
-__host__ __device__ constexpr int ring_depth(int nt) { return nt <= 1 ? 8 : (nt == 2 ? 6 : 3); }
+// depth + 1 slots: keep the slot count a power of two (the slot index is k % slots on a 64-bit row counter)
+__host__ __device__ constexpr int ring_depth(int nt) { return nt <= 2 ? 7 : 3; }
 
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
@@ -616,17 +625,33 @@ struct BwdFinalizeParams {
   float* gacc[kMaxBranches]; float* bacc[kMaxBranches];
   int nblocks, B, C, C_logical;
 };
+// same block shape as bn_finalize_kernel: 32 channels (coalesced) x 8 block lanes, fixed order
 __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(BwdFinalizeParams p) {
-  const int lane = threadIdx.x & 31;
-  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (c >= p.C) return;
-  double tot[1 + kMaxBranches];
-  for (int i = 0; i <= p.B; ++i) {
-    double a = 0.0;
-    for (int k = lane; k < p.nblocks; k += 32) a += p.part[((size_t)k * (1 + p.B) + i) * p.C + c];
-    tot[i] = warp_sum(a);
+  __shared__ double red[1 + kMaxBranches][8][32];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double acc[1 + kMaxBranches];
+#pragma unroll
+  for (int i = 0; i <= kMaxBranches; ++i) acc[i] = 0.0;
+  if (c < p.C) {
+    for (int k = threadIdx.y; k < p.nblocks; k += 8) {
+      const double* row = p.part + (size_t)k * (1 + p.B) * p.C + c;
+#pragma unroll
+      for (int i = 0; i <= kMaxBranches; ++i)
+        if (i <= p.B) acc[i] += row[(size_t)i * p.C];
+    }
   }
-  if (lane != 0) return;
+#pragma unroll
+  for (int i = 0; i <= kMaxBranches; ++i) red[i][threadIdx.y][threadIdx.x] = acc[i];
+  __syncthreads();
+  if (threadIdx.y != 0 || c >= p.C) return;
+  double tot[1 + kMaxBranches];
+#pragma unroll
+  for (int i = 0; i <= kMaxBranches; ++i) {
+    double t = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += red[i][j][threadIdx.x];
+    tot[i] = t;
+  }
   for (int i = 0; i <= p.B; ++i) p.sums[(size_t)i * p.C + c] = tot[i];
   for (int b = 0; b < p.B; ++b) {
     const size_t o = (size_t)b * p.C + c;
@@ -718,7 +743,7 @@ int hb_bn_finalize(const float* const* parts, const int* slots, const float* con
   }
   p.mean = mean; p.rstd = rstd; p.scale = scale; p.shift = shift;
   p.B = B; p.C = C; p.M = M; p.C_logical = C_logical; p.eps = eps; p.momentum = momentum;
-  bn_finalize_kernel<<<dim3((C + 7) / 8, B), 256, 0, (cudaStream_t)stream>>>(p);
+  bn_finalize_kernel<<<dim3((C + 31) / 32, B), dim3(32, 8), 0, (cudaStream_t)stream>>>(p);
   HB_LAUNCH_CHECK();
   return 0;
 }
@@ -818,7 +843,7 @@ int hb_bn_act_bwd_bf16(const void* dout, const void* u0, const void* u1, const v
       f.bacc[b] = beta_grad_acc ? beta_grad_acc[b] : nullptr;
     }
     f.nblocks = (int)grid.x; f.B = B; f.C = C; f.C_logical = C_logical > 0 ? C_logical : C;
-    bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(f);
+    bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(f);
     HB_LAUNCH_CHECK();
   }
   {

@@ -9,8 +9,10 @@ import holocron_b200 as hb
 
 name = sys.argv[1] if len(sys.argv) > 1 else "rexnet1_0x"
 batch = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+from holocron_b200.distributed import GradBucket
 m = getattr(hb.models, name)(num_classes=1000).cuda().to(memory_format=torch.channels_last).train()
-opt = hb.optim.AdaBelief(m.parameters(), lr=1e-3)
+bucket = GradBucket(m.parameters())      # gradients added straight into the flat bucket, like bench.py's step
+opt = hb.optim.AdaBelief(m.parameters(), lr=1e-3, betas=(0.95, 0.99), eps=1e-6)
 x = torch.randn(batch, 3, 224, 224, device="cuda")
 t = torch.randint(0, 1000, (batch,), device="cuda")
 
@@ -19,7 +21,7 @@ def step():
     loss = TF.cross_entropy(m(x), t)
     loss.backward()
     opt.step()
-    opt.zero_grad(set_to_none=True)
+    bucket.zero_()
 
 
 for _ in range(2):
