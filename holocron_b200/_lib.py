@@ -51,6 +51,7 @@ SIGNATURES = {
     "hb_im2col_smallc_bf16": "pp" + "i" * 10 + "p",
     "hb_conv2d_fused_bf16": "ppp",
     "hb_conv_stat_slots_max": "",
+    "hb_patch_stats_bf16": "pppp" + "i" * 10 + "fp",
     "hb_bn_stats_partials_bf16": "piippp",
     "hb_bn_stat_slots_max": "",
     "hb_bn_finalize": "ppppppp" + "pppp" + "iiiiffp",
@@ -125,7 +126,8 @@ class ConvArgs(ctypes.Structure):
     _fields_ = ([(n, ctypes.c_void_p) for n in ("x", "w", "y", "bias", "residual")]
                 + [(n, ctypes.c_int) for n in ("N", "H", "W", "Cin", "Cout", "R", "S", "stride", "pad", "dil", "act", "num_ctas")]
                 + [("xe", ctypes.c_void_p), ("we", ctypes.c_void_p), ("Ce", ctypes.c_int), ("w2", ctypes.c_void_p),
-                   ("y2", ctypes.c_void_p), ("stats", ctypes.c_void_p), ("stats2", ctypes.c_void_p)])
+                   ("y2", ctypes.c_void_p), ("stats", ctypes.c_void_p), ("stats2", ctypes.c_void_p),
+                   ("norm_mean", ctypes.c_void_p), ("norm_rstd", ctypes.c_void_p), ("norm_wsum", ctypes.c_void_p)])
 
 
 def check(rc: int, what: str) -> None:

@@ -68,6 +68,11 @@ struct FpropParams {
   float* stats2;
   const float* bias;              // [Cout] or null
   const __nv_bfloat16* residual;  // [M, Cout] or null (same addressing as y)
+  // patch normalisation in the epilogue (NormConv2d, reference nn/functional.py:322-413): with the per-patch statistics of
+  // the im2col rows, y = rstd[m] * (acc - mean[m] * wsum[co]) (+ bias) == sum_k ((patch_k - mean) * rstd) * w[co, k]
+  const float* norm_mean;         // [M] or null
+  const float* norm_rstd;         // [M]
+  const float* norm_wsum;         // [Cout] = sum over (r, s, ci) of the bf16 filter
   // output addressing: dense rows (scatter == 0) or output pixel (n, i, j) of the Ho x Wo grid written to pixel
   // (i*o_step + o_a, j*o_step + o_b) of an OH x OW image (the parity classes of a strided data gradient)
   int scatter, OH, OW, o_step, o_a, o_b;
@@ -234,6 +239,11 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t taddr0 = tmem_base + acc * 256 + ((uint32_t)(quarter * 32) << 16);
       const int rows_valid = min(kBM, p.m_total - m_tile * kBM);
       uint8_t* srow = sout + (size_t)row_in_tile * p.out_pitch;
+      float nm = 0.f, nr = 1.f;
+      if (p.norm_mean) {
+        const int m_row = m_tile * kBM + row_in_tile;
+        if (m_row < p.m_total) { nm = __ldg(p.norm_mean + m_row); nr = __ldg(p.norm_rstd + m_row); }
+      }
 #pragma unroll
       for (int gi = 0; gi < 4; ++gi) {
         if (gi >= ngroups) break;
@@ -268,6 +278,10 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
               for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[h * 16 + j]);
               const int col = col_base + g0 + c + h * 16;
+              if (first && p.norm_mean && col < p.Cout) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = nr * (f[j] - nm * __ldg(p.norm_wsum + col + j));
+              }
               if (first && p.bias && col < p.Cout) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) f[j] += __ldg(p.bias + col + j);
@@ -417,6 +431,7 @@ struct FpropArgs {
   // dual output: w2 [Cout,1,1,Cin] applied to the centre tap of x -> y2
   const void* w2; void* y2;
   float* stats; float* stats2; int* stat_slots;
+  const float* norm_mean; const float* norm_rstd; const float* norm_wsum;
   cudaStream_t stream;
 };
 
@@ -470,6 +485,8 @@ int fprop_launch(const FpropArgs& a) {
   p.stats = a.stats; p.stats2 = dual ? a.stats2 : nullptr;
   p.bias = a.bias;
   p.residual = (const __nv_bfloat16*)a.residual;
+  p.norm_mean = a.norm_mean; p.norm_rstd = a.norm_rstd; p.norm_wsum = a.norm_wsum;
+  if (p.norm_mean && (!p.norm_rstd || !p.norm_wsum || a.scatter)) return (int)cudaErrorInvalidValue;
 
   CUtensorMap tmA, tmB, tmA2, tmB2;
   int rc;
@@ -559,7 +576,7 @@ int hb_conv2d_fused_bf16(const hb_conv_args* c, int* stat_slots, void* stream) {
   if (c->w2 && pad != (R / 2) * dil) return (int)cudaErrorInvalidValue;   // centre tap == the 1x1 pad-0 conv's input
   if ((c->stats || c->stats2) && !stat_slots) return (int)cudaErrorInvalidValue;
 
-  if (R == 3 && S == 3 && stride == 1 && pad == 1 && dil == 1 && !c->xe && !c->w2) {
+  if (R == 3 && S == 3 && stride == 1 && pad == 1 && dil == 1 && !c->xe && !c->w2 && !c->norm_mean) {
     static const bool rows_enabled = getenv("HB_DISABLE_CONV_ROWS") == nullptr;
     if (rows_enabled) {
       const int rc = hb_conv_rows_try(c->x, c->w, c->y, c->bias, c->residual, N, H, W, Cin, Cout, c->act, c->num_ctas,
@@ -575,6 +592,7 @@ int hb_conv2d_fused_bf16(const hb_conv_args* c, int* stat_slots, void* stream) {
   a.Ho = Ho; a.Wo = Wo; a.stream = (cudaStream_t)stream;
   a.xe = c->xe; a.we = c->we; a.Ce = c->Ce; a.w2 = c->w2; a.y2 = c->y2;
   a.stats = c->stats; a.stats2 = c->stats2; a.stat_slots = stat_slots;
+  a.norm_mean = c->norm_mean; a.norm_rstd = c->norm_rstd; a.norm_wsum = c->norm_wsum;
   return fprop_launch(a);
 }
 

@@ -319,7 +319,7 @@ def conv_out_size(h: int, k: int, stride: int, pad: int, dil: int) -> int:
 def conv2d_forward_raw(x: Tensor, wf: Tensor, cout: int, r: int, s: int, stride: int, pad: int, dil: int,
                        bias: Optional[Tensor] = None, residual: Optional[Tensor] = None, act: int = ACT_NONE, *,
                        w2: Optional[Tensor] = None, xe: Optional[Tensor] = None, we: Optional[Tensor] = None,
-                       want_stats: bool = False, kind: str = "fprop"):
+                       want_stats: bool = False, kind: str = "fprop", norm: Optional[Tuple[Tensor, Tensor, Tensor]] = None):
     """x: bf16 channels_last [N, Cin_p, H, W]; wf: bf16 [Cout, R, S, Cin_p] -> bf16 channels_last [N, Cout, Ho, Wo].
 
     One launch of ``hb_conv2d_fused_bf16``. ``w2`` ([Cout, 1, 1, Cin_p]): dual output, returns ``(y, y2)`` with
@@ -354,6 +354,8 @@ def conv2d_forward_raw(x: Tensor, wf: Tensor, cout: int, r: int, s: int, stride:
         w_elems += cout * cin_p
     if residual is not None:
         in_elems += m_out * cout
+    if norm is not None:           # (mean [M], rstd [M], wsum [Cout]) fp32: NormConv2d's patch standardisation in the epilogue
+        a.norm_mean, a.norm_rstd, a.norm_wsum = norm[0].data_ptr(), norm[1].data_ptr(), norm[2].data_ptr()
     st = st2 = None
     if want_stats:
         st = torch.empty((CONV_STAT_SLOTS, cout, 2), device=x.device, dtype=torch.float32)

@@ -102,7 +102,8 @@ class TrainStep:
         self._clip_scratch = torch.empty(L.hb_grad_clip_partials_max(), device=dev, dtype=torch.float64)
         optimizer._hb_ctl = self.ctl           # the fused optimizers read lr / beta1 / skip from the control block
         self._count = 0                        # iterations inside the current accumulation window (host bookkeeping)
-        self.iterations = 0
+        self.iterations = 0                    # the reference Trainer's `step`
+        self.epoch, self.start_epoch, self.min_loss = 0, 0, float("inf")
         self._graphs: Dict[bool, Any] = {}
         self._use_graph = bool(graph)
 
@@ -181,6 +182,23 @@ class TrainStep:
                 if k not in st["steps"]:
                     v.zero_()
         torch.autograd.graph.increment_version(list(self.model.parameters()))
+
+    # ---- checkpoints: the reference's on-disk layout (holocron/trainer/core.py:106-133) --------------------------
+    def save(self, output_file: str) -> None:
+        """``{"epoch", "step", "min_loss", "model": state_dict}`` written with the legacy (non-zipfile) serialisation,
+        exactly what the reference ``Trainer.save`` writes (optimizer / scheduler state is not part of it there either), so
+        that ``references/clean_checkpoint.py`` and the reference ``Trainer.load`` read it unchanged."""
+        torch.save({"epoch": self.epoch, "step": self.iterations, "min_loss": self.min_loss,
+                    "model": self.model.state_dict()}, output_file, _use_new_zipfile_serialization=False)
+
+    def load(self, state: Dict[str, Any]) -> None:
+        """Resumes from a checkpoint dict of the reference layout (reference ``Trainer.load``, core.py:123-133)."""
+        self.start_epoch = state["epoch"]
+        self.epoch = self.start_epoch
+        self.iterations = state["step"]
+        self.min_loss = state["min_loss"]
+        self.model.load_state_dict(state["model"])
+        torch.autograd.graph.increment_version(list(self.model.parameters()))   # packed bf16 filters are stale now
 
     # ---- host-visible state (each property synchronises) --------------------------------------------------------
     def state(self) -> Dict[str, float]:

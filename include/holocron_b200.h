@@ -48,6 +48,9 @@ int hb_conv2d_fprop_bf16(const void* x, const void* w, void* y, const float* bia
  *                 float [*stat_slots][Cout][2]; the caller allocates hb_conv_stat_slots_max() slots, the launch writes
  *                 the first *stat_slots (host int) completely; summing the slots in order is deterministic. This replaces
  *                 the separate statistics pass of training-mode BatchNorm2d.
+ *   patch norm    norm_mean != NULL (NormConv2d, holocron/nn/functional.py:322-413): y = norm_rstd[m] * (acc - norm_mean[m] *
+ *                 norm_wsum[co]) + bias, m = output pixel: the per-patch standardisation of the im2col rows folded
+ *                 algebraically into the epilogue (statistics from hb_patch_stats_bf16).
  * bias / residual / act apply to y only. Fields not used must be zero. */
 typedef struct hb_conv_args {
   const void* x; const void* w; void* y; const float* bias; const void* residual;
@@ -55,9 +58,15 @@ typedef struct hb_conv_args {
   const void* xe; const void* we; int Ce;
   const void* w2; void* y2;
   float* stats; float* stats2;
+  const float* norm_mean; const float* norm_rstd; const float* norm_wsum;
 } hb_conv_args;
 int hb_conv2d_fused_bf16(const hb_conv_args* args, int* stat_slots, void* stream);
 int hb_conv_stat_slots_max(void);
+/* Per-patch statistics of the im2col rows of x [N,H,W,C] bf16 (zero padding included, like F.unfold): for every output
+ * pixel m, mean[m] and rstd[m] = 1/sqrt(biased var + eps) over its K = k_logical = Cin*kh*kw patch values (channels
+ * beyond the logical ones are zero padding of the layout and do not count). scratch: float [2*N*H*W]. */
+int hb_patch_stats_bf16(const void* x, float* mean, float* rstd, float* scratch, int N, int H, int W, int C, int kh, int kw,
+                        int stride, int pad, int dil, int k_logical, float eps, void* stream);
 /* y = conv3x3(x, w; stride 1, pad 1) + sum_{e<nextra} conv1x1(xe_e, we_e), one accumulator (nextra <= 2; all inputs
  * [N,H,W,Cin] bf16, w [Cout,3,3,Cin], we_e [Cout,1,1,Cin]). Input gradient of a RepVGG block in one kernel
  * (holocron/models/classification/repvgg.py:71-73). Returns cudaErrorNotSupported (801) when the filter does not fit the

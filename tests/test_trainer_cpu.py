@@ -59,3 +59,26 @@ def test_tiny_model_state_matches_reference_init():
     sd = tiny().state_dict()
     assert list(sd) == list(g["acc2_clip_onecycle"]["state"])
     assert hb.optim.AdaBelief is not None
+
+
+def test_checkpoint_layout_is_the_reference_one(tmp_path):
+    """TrainStep.save writes the reference Trainer's checkpoint dict (core.py:106-121: epoch / step / min_loss / model,
+    legacy serialisation); TrainStep.load resumes from a dict of that layout, e.g. one written by the reference."""
+    from holocron_b200.trainer import TrainStep
+    g = load_golden("trainer")
+    m = tiny()
+    ts = TrainStep(m, torch.nn.CrossEntropyLoss(), torch.optim.SGD(m.parameters(), lr=0.1), graph=False)
+    ts.epoch, ts.iterations, ts.min_loss = 3, 17, 0.25
+    path = tmp_path / "ckpt.pth"
+    ts.save(str(path))
+    state = torch.load(path, weights_only=False)
+    assert list(state) == ["epoch", "step", "min_loss", "model"] and state["epoch"] == 3 and state["step"] == 17
+    assert list(state["model"]) == list(g["acc2_clip_onecycle"]["state"])       # the reference model's state_dict keys
+    # a checkpoint as the reference writes it (its final golden state) loads into this package's model
+    ref_state = {"epoch": 1, "step": 8, "min_loss": 1.5, "model": g["acc2_clip_onecycle"]["state"]}
+    m2 = tiny()
+    ts2 = TrainStep(m2, torch.nn.CrossEntropyLoss(), torch.optim.SGD(m2.parameters(), lr=0.1), graph=False)
+    ts2.load(ref_state)
+    assert ts2.epoch == 1 and ts2.iterations == 8 and ts2.min_loss == 1.5
+    for k, v in m2.state_dict().items():
+        assert torch.equal(v, g["acc2_clip_onecycle"]["state"][k])
