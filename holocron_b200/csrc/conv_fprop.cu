@@ -78,6 +78,9 @@ struct FpropParams {
   int scatter, OH, OW, o_step, o_a, o_b;
 };
 
+// kStats: the epilogue also accumulates the output-column statistics (separate instantiation: the plain kernel carries
+// neither the 16 accumulator registers nor the extra shared-memory pass in its instruction stream)
+template <bool kStats>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const FpropParams p) {
@@ -355,7 +358,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
           }
         }
-        if (o ? (p.stats2 != nullptr) : (p.stats != nullptr)) {
+        if (kStats && (o ? (p.stats2 != nullptr) : (p.stats != nullptr))) {
           // per-channel sum / sum of squares of the staged (bf16-rounded) tile: thread = (column pair, row subset)
           const int npairs = gw >> 1, rgs = 128 / npairs;
           const int rg = et / npairs, pr = et - rg * npairs;
@@ -373,7 +376,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     // ---- statistics: fold the row subsets in a fixed order and write this (CTA, group)'s partial (every slot is written,
     // zeros included, so the consumer can add all slots without a memset)
-    if (p.stats || p.stats2) {
+    if (kStats && (p.stats || p.stats2)) {
       const int slot = (blockIdx.x / p.num_n_tiles) * 2 + group;
 #pragma unroll
       for (int gi = 0; gi < 4; ++gi) {
@@ -525,7 +528,8 @@ int fprop_launch(const FpropArgs& a) {
   const size_t smem_bytes = (size_t)stages * stage_bytes + out_bytes + (2 * stages + 4) * sizeof(uint64_t) + 16 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_fprop_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_fprop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
@@ -537,7 +541,8 @@ int fprop_launch(const FpropArgs& a) {
   if (per_n > p.num_m_tiles) per_n = p.num_m_tiles;
   grid = per_n * p.num_n_tiles;
   if (a.stat_slots) *a.stat_slots = 2 * per_n;
-  conv_fprop_kernel<<<grid, kThreads, smem_bytes, a.stream>>>(tmA, tmB, tmA2, tmB2, p);
+  if (p.stats || p.stats2) conv_fprop_kernel<true><<<grid, kThreads, smem_bytes, a.stream>>>(tmA, tmB, tmA2, tmB2, p);
+  else conv_fprop_kernel<false><<<grid, kThreads, smem_bytes, a.stream>>>(tmA, tmB, tmA2, tmB2, p);
   HB_LAUNCH_CHECK();
   return 0;
 }
