@@ -169,9 +169,9 @@ class Workload:
             "repvgg_a1": ("repvgg_a1", {"num_classes": NUM_CLASSES}, 512, 224, True,
                           "repvgg_a1 224x224 bf16 train step (BASELINE configs[2]): fwd + CE(label_smoothing=0.1) + bwd + AdaBelief, "
                           "batch 512/GPU"),
-            "yolov4": ("yolov4", {"num_classes": 80}, 16, 512, False,
+            "yolov4": ("yolov4", {"num_classes": 80}, 16, 512, True,
                        "yolov4 (CSP-Darknet53) 512x512 detection train step (BASELINE configs[3]): fwd + CIoU/objectness/class "
-                       "losses + bwd + AdaBelief; synthetic COCO-like boxes (1-19 per image)"),
+                       "losses (sync-free per-box formulation) + bwd + AdaBelief; synthetic COCO-like boxes (1-19 per image)"),
             "unet3p": ("unet3p", {"num_classes": 21}, 16, 256, True,
                        "unet3p 256x256 segmentation train step (BASELINE configs[4]): fwd + DiceLoss(softmax, one-hot) + bwd + "
                        "AdaBelief; synthetic masks"),

@@ -139,54 +139,90 @@ class YoloLayer(nn.Module):
             detections.append({"boxes": coords, "scores": scores, "labels": labels})
         return detections
 
+    def _assignment(self, b: int, h: int, w: int, na: int, target: List[Dict[str, Tensor]], dev):
+        """Per ground-truth box: image index, cell, best-shape anchor, linear index of its (image, cell, anchor) slot and
+        the number of boxes sharing that slot (reference yolov4.py:338-388: cell = the one holding the box centre, anchor =
+        best IoU between the box's and the anchors' shapes). Everything is a static-shape device tensor - the only host
+        knowledge used is the number of boxes per image, which defines the shapes anyway."""
+        counts = tuple(int(t["boxes"].shape[0]) for t in target)
+        key = (counts, str(dev))
+        cache = self.__dict__.setdefault("_img_index_cache", {})
+        img = cache.get(key)
+        if img is None:     # built once per box-count pattern (a pageable host->device copy: not inside a graph capture)
+            img = torch.repeat_interleave(torch.arange(b), torch.tensor(counts)).to(dev)
+            cache[key] = img
+        boxes = torch.cat([t["boxes"] for t in target], dim=0).float()
+        labels = torch.cat([t["labels"] for t in target], dim=0)
+        cell_x = ((boxes[:, 0] + boxes[:, 2]) / 2 * w).to(torch.long)
+        cell_y = ((boxes[:, 1] + boxes[:, 3]) / 2 * h).to(torch.long)
+        gt_wh = boxes[:, 2:] - boxes[:, :2]
+        anchor_idx = box_iou(torch.cat((-gt_wh, gt_wh), dim=-1),
+                             torch.cat((-self.anchors, self.anchors), dim=-1)).argmax(dim=1)
+        lin = ((img * h + cell_y) * w + cell_x) * na + anchor_idx
+        cnt = torch.zeros(b * h * w * na, device=dev).index_put_((lin,), torch.ones_like(lin, dtype=torch.float32),
+                                                                    accumulate=True)
+        return img, cell_y, cell_x, anchor_idx, lin, cnt[lin], boxes, labels
+
     def _build_targets(self, pred_boxes: Tensor, b_o: Tensor, target: List[Dict[str, Tensor]]):
-        """Objectness / class targets and the (obj, noobj) masks: each GT box is assigned to the cell holding its centre
-        and to the anchor whose shape has the best IoU with it (reference yolov4.py:338-388)."""
+        """Dense objectness / class targets and the (obj, noobj) masks of reference yolov4.py:338-388, produced without any
+        boolean-mask gather (no host synchronisation). Kept for introspection; the losses use the per-box form below."""
         b, h, w, na = b_o.shape
         dev = b_o.device
         target_o = torch.zeros((b, h, w, na), device=dev)
         target_scores = torch.zeros((b, h, w, na, self.num_classes), device=dev)
         obj_mask = torch.zeros((b, h, w, na), dtype=torch.bool, device=dev)
         noobj_mask = torch.ones((b, h, w, na), dtype=torch.bool, device=dev)
-        gt_boxes = [t["boxes"] for t in target]
-        gt_labels = [t["labels"] for t in target]
-        counts = [bx.shape[0] for bx in gt_boxes]
-        if sum(counts) == 0:
+        if sum(t["boxes"].shape[0] for t in target) == 0:
             return target_o, target_scores, obj_mask, noobj_mask
-        boxes = torch.cat(gt_boxes, dim=0).float()
-        cell_x = ((boxes[:, 0] + boxes[:, 2]) / 2 * w).to(torch.long)
-        cell_y = ((boxes[:, 1] + boxes[:, 3]) / 2 * h).to(torch.long)
-        img = torch.repeat_interleave(torch.arange(b, device=dev), torch.tensor(counts, device=dev))
-        gt_wh = boxes[:, 2:] - boxes[:, :2]
-        anchor_idx = box_iou(torch.cat((-gt_wh, gt_wh), dim=-1),
-                             torch.cat((-self.anchors, self.anchors), dim=-1)).argmax(dim=1)
-        obj_mask[img, cell_y, cell_x, anchor_idx] = True
-        noobj_mask[img, cell_y, cell_x, :] = False
-        for idx in range(b):
-            if counts[idx] > 0:
-                # no detach: like the reference (yolov4.py:380-382) the objectness target stays attached to the predicted
-                # boxes, so obj_loss also back-propagates through the IoU
-                ious, gt_idx = box_iou(pred_boxes[idx][obj_mask[idx]], gt_boxes[idx].float()).max(dim=1)
-                target_o[idx][obj_mask[idx]] = ious
-                sel = obj_mask[idx].nonzero(as_tuple=True)
-                target_scores[idx][sel[0], sel[1], sel[2], gt_labels[idx][gt_idx]] = 1.0
+        img, cy, cx, a, lin, mult, boxes, labels = self._assignment(b, h, w, na, target, dev)
+        obj_mask[img, cy, cx, a] = True
+        noobj_mask[img, cy, cx, :] = False
+        ious, gt_idx = self._per_box_iou(pred_boxes[img, cy, cx, a], boxes, img)
+        target_o[img, cy, cx, a] = ious
+        target_scores[img, cy, cx, a, labels[gt_idx]] = 1.0
         return target_o, target_scores, obj_mask, noobj_mask
+
+    @staticmethod
+    def _per_box_iou(preds: Tensor, boxes: Tensor, img: Tensor) -> Tuple[Tensor, Tensor]:
+        """For the prediction assigned to every ground-truth box: the best IoU with the boxes of ITS image and that box's
+        index (reference: box_iou(pred_boxes[idx][obj_mask[idx]], gt_boxes[idx]).max(dim=1), one call per image)."""
+        same = img[:, None] == img[None, :]
+        iou = box_iou(preds, boxes)
+        return torch.where(same, iou, torch.full_like(iou, -1.0)).max(dim=1)
 
     def _compute_losses(self, pred_boxes: Tensor, b_o: Tensor, b_scores: Tensor,
                         target: List[Dict[str, Tensor]]) -> Dict[str, Tensor]:
-        target_o, target_scores, obj_mask, noobj_mask = self._build_targets(pred_boxes, b_o, target)
-        bbox_loss = torch.zeros(1, device=b_o.device)
-        for idx, _target in enumerate(target):
-            if _target["boxes"].shape[0] > 0 and bool(obj_mask[idx].any()):
-                bbox_loss = bbox_loss + ciou_loss(pred_boxes[idx][obj_mask[idx]], _target["boxes"].float()).min(dim=1).values.sum()
+        """The four YOLOv4 losses of reference yolov4.py:390-420. The reference gathers the predictions of the assigned
+        (cell, anchor) slots with boolean masks, image by image (data-dependent shapes, one host synchronisation per gather).
+        Here every ground-truth box carries the prediction of its slot (static shapes); a slot shared by m boxes would be
+        counted m times, so each row is weighted by 1/m - the rows of a shared slot are identical, hence the weighted sum
+        equals the reference's sum over DISTINCT slots exactly. All pairs of one G x G box-op launch replace the per-image
+        calls (pairs of different images masked out). No host synchronisation: the step can be CUDA-graph captured."""
+        b, h, w, na = b_o.shape
+        dev = b_o.device
+        n = b
         prob_o = torch.sigmoid(b_o)
-        n = b_o.shape[0]
+        if sum(t["boxes"].shape[0] for t in target) == 0:
+            zero = torch.zeros((), device=dev) * prob_o.sum() * 0
+            return {"obj_loss": zero, "noobj_loss": self.lambda_noobj * prob_o.pow(2).sum() / n,
+                    "bbox_loss": torch.zeros(1, device=dev) + zero, "clf_loss": zero * b_scores.sum() * 0}
+        img, cy, cx, a, lin, mult, boxes, labels = self._assignment(b, h, w, na, target, dev)
+        wgt = 1.0 / mult
+        preds = pred_boxes[img, cy, cx, a]                              # [G, 4], differentiable gather
+        same = img[:, None] == img[None, :]
+        ious, gt_idx = self._per_box_iou(preds, boxes, img)             # objectness target stays attached to the graph
+        ciou = ciou_loss(preds, boxes)
+        bbox = (torch.where(same, ciou, torch.full_like(ciou, float("inf"))).min(dim=1).values * wgt).sum()
+        obj = ((prob_o[img, cy, cx, a] - ious).pow(2) * wgt).sum()
+        noobj_w = torch.ones((b, h, w, na), device=dev)
+        noobj_w[img, cy, cx, :] = 0.0
+        onehot = F.one_hot(labels[gt_idx], self.num_classes).to(b_scores.dtype)
+        clf = (F.binary_cross_entropy_with_logits(b_scores[img, cy, cx, a], onehot, reduction="none").mean(1) * wgt).sum()
         return {
-            "obj_loss": self.lambda_obj * F.mse_loss(prob_o[obj_mask], target_o[obj_mask], reduction="sum") / n,
-            "noobj_loss": self.lambda_noobj * prob_o[noobj_mask].pow(2).sum() / n,
-            "bbox_loss": self.lambda_coords * bbox_loss / n,
-            "clf_loss": self.lambda_class * F.binary_cross_entropy_with_logits(
-                b_scores[obj_mask], target_scores[obj_mask], reduction="none").mean(1).sum(0) / n,
+            "obj_loss": self.lambda_obj * obj / n,
+            "noobj_loss": self.lambda_noobj * (prob_o.pow(2) * noobj_w).sum() / n,
+            "bbox_loss": (self.lambda_coords * bbox / n).reshape(1),
+            "clf_loss": self.lambda_class * clf / n,
         }
 
     def forward(self, x: Tensor, target: Optional[List[Dict[str, Tensor]]] = None):

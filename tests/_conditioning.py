@@ -64,6 +64,18 @@ def yolo_inputs():
     return x, target
 
 
+def yolo_dup_inputs():
+    """Like yolo_inputs, but in image 0 two boxes share their cell AND their best-shape anchor at every scale (same centre,
+    nearly the same shape): the reference's boolean masks collapse them into ONE assigned slot; and image 1 has a single box."""
+    x, _ = yolo_inputs()
+    c = torch.tensor([[0.30, 0.40], [0.30, 0.40], [0.70, 0.65]])
+    wh = torch.tensor([[0.20, 0.26], [0.21, 0.25], [0.10, 0.12]])
+    t0 = {"boxes": torch.cat([c - wh / 2, c + wh / 2], 1), "labels": torch.tensor([5, 9, 33])}
+    c1, wh1 = torch.tensor([[0.5, 0.5]]), torch.tensor([[0.4, 0.3]])
+    t1 = {"boxes": torch.cat([c1 - wh1 / 2, c1 + wh1 / 2], 1), "labels": torch.tensor([61])}
+    return x, [t0, t1]
+
+
 def unet_inputs():
     g = torch.Generator().manual_seed(14)
     x = torch.rand(2, 3, 64, 64, generator=g)

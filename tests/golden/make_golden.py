@@ -367,6 +367,14 @@ def gen_zoo():
         names = [n for n in names if n in ps]
         out[mode] = dict(losses={k: v.detach() for k, v in losses.items()}, grads=grads_of(m, names), probe=store["probe"][:1].half() if mode == "train" else None)
     d["yolov4"] = out
+    # shared (cell, anchor) slot: two boxes of one image collapse into one assigned prediction in the reference's masks
+    m = C.freeze_bn(build(models.detection.yolov4, pretrained_backbone=False, num_classes=80))
+    x, target = C.yolo_dup_inputs()
+    losses = m(x, target)
+    sum(losses.values()).backward()
+    ps = dict(m.named_parameters())
+    d["yolov4_dup"] = dict(losses={k: v.detach() for k, v in losses.items()},
+                           grads={"head.head1.3.weight": ps["head.head1.3.weight"].grad.clone()})
     torch.save(d, OUT / "zoo.pt")
 
 
