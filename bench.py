@@ -474,6 +474,8 @@ def measure(args, wl: Workload, rank: int, local_rank: int, world: int, full: bo
             graphed = GraphedTrainStep(eager_step, devb, warmup=3)
             train_step = graphed
         except Exception as e:  # noqa: BLE001 - capture is an optimisation: report and run the same CUDA path eagerly
+            import traceback
+            traceback.print_exc(file=sys.stderr)
             print(f"[bench] CUDA-graph capture failed ({e!r}); running the step eagerly", file=sys.stderr)
             torch.cuda.synchronize()
 

@@ -215,7 +215,7 @@ class YoloLayer(nn.Module):
         bbox = (torch.where(same, ciou, torch.full_like(ciou, float("inf"))).min(dim=1).values * wgt).sum()
         obj = ((prob_o[img, cy, cx, a] - ious).pow(2) * wgt).sum()
         noobj_w = torch.ones((b, h, w, na), device=dev)
-        noobj_w[img, cy, cx, :] = 0.0
+        noobj_w.index_put_((img, cy, cx), noobj_w.new_zeros(()))    # device-side value: graph-capturable (no CPU scalar copy)
         onehot = F.one_hot(labels[gt_idx], self.num_classes).to(b_scores.dtype)
         clf = (F.binary_cross_entropy_with_logits(b_scores[img, cy, cx, a], onehot, reduction="none").mean(1) * wgt).sum()
         return {
