@@ -3,6 +3,7 @@
 // (one 128-bit vector) of one output pixel; neighbouring threads share their taps through L1/L2.
 // Used by FReLU (reference holocron/nn/modules/activation.py:58-82: conv k x k, groups = C, bias) and by the ReXNet
 // blocks (reference holocron/models/classification/rexnet.py:112-125: dw 3x3, stride 1|2, no bias).
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
@@ -170,6 +171,104 @@ __global__ void __launch_bounds__(kThreads, 3) dw3x3_kernel(const __nv_bfloat16*
   }
 }
 
+// ---- four horizontally adjacent outputs per thread ------------------------------------------------------------------
+// The one-output-per-thread kernel above issues 9 vector loads, 72 converts, 18 shared-memory filter reads, two integer
+// divisions and 9 bounds predicates per 8 output values and sat at ~1 TB/s on the ReXNet expansions (instruction-bound,
+// profiles/r02_launches_rexnet1_0x_b256.md). With 4 outputs of one row per thread the 3 input rows are loaded once
+// (3 x (3*S+3) vectors for stride S instead of 36), the filter slab is read once per quad and the index arithmetic is
+// amortised over 32 output values.
+//   forward  (kFlip = 0): y[oh, ow]  = b + sum_{r,s} x[oh*S + r - pad, ow*S + s - pad] * w[r, s]
+//   backward (kFlip = 1, S = 1 only): dx[h, w] = sum_{r,s} dy[h + pad - r, w + pad - s] * w[r, s]
+//            = correlation of dy with the FLIPPED filter and padding 2 - pad
+template <int kStride, bool kFlip>
+__global__ void __launch_bounds__(kThreads, 2) dw3x3_quad_kernel(const __nv_bfloat16* __restrict__ src, const float* __restrict__ w,
+                                                              const float* __restrict__ bias, __nv_bfloat16* __restrict__ dst,
+                                                              int N, int IH, int IW, int OH, int OW, int C, int pad, int cg_t,
+                                                              int rows_t) {
+  __shared__ __align__(16) float ws[9][256];   // the block's channel slab of the filter, tap-major (flipped for kFlip)
+  const int cv = C / 8;
+  const int tx = threadIdx.x % cg_t, ty = threadIdx.x / cg_t;
+  const int cg = blockIdx.y * cg_t + tx;
+  for (int i = threadIdx.x; i < 9 * cg_t * 8; i += kThreads) {
+    const int k = i / (cg_t * 8), ch = i % (cg_t * 8);
+    const int c = blockIdx.y * cg_t * 8 + ch;
+    ws[k][ch] = c < C ? w[c * 9 + (kFlip ? 8 - k : k)] : 0.f;
+  }
+  __syncthreads();
+  if (ty >= rows_t || cg >= cv) return;
+  float b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) b[j] = (!kFlip && bias) ? bias[cg * 8 + j] : 0.f;
+  constexpr int kIn = 3 * kStride + 3;          // input columns feeding 4 outputs: (4 - 1) * S + 3
+  const int qw = (OW + 3) >> 2;                 // quads per output row
+  const unsigned total = (unsigned)N * OH * qw;
+  for (unsigned q = blockIdx.x * rows_t + ty; q < total; q += gridDim.x * rows_t) {
+    const unsigned t1 = q / (unsigned)qw;
+    const int ow0 = (int)(q - t1 * (unsigned)qw) * 4;
+    const unsigned n = t1 / (unsigned)OH;
+    const int oh = (int)(t1 - n * (unsigned)OH);
+    const int iw0 = ow0 * kStride - pad;
+    float acc[4][8];
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[o][j] = b[j];
+    const __nv_bfloat16* sn = src + (size_t)n * IH * IW * C + cg * 8;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int ih = oh * kStride + r - pad;
+      if (ih < 0 || ih >= IH) continue;
+      const __nv_bfloat16* row = sn + (size_t)ih * IW * C;
+      Vec16<__nv_bfloat16> v[kIn];
+#pragma unroll
+      for (int c = 0; c < kIn; ++c) {           // all loads of the row in flight before the first use
+        const int iw = iw0 + c;
+        if (iw >= 0 && iw < IW) v[c] = ld16(row + (size_t)iw * C);
+        else v[c].raw = make_uint4(0, 0, 0, 0);
+      }
+      float wk[3][8];
+#pragma unroll
+      for (int s2 = 0; s2 < 3; ++s2) {
+        const float4 w0 = *reinterpret_cast<const float4*>(&ws[r * 3 + s2][tx * 8]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&ws[r * 3 + s2][tx * 8 + 4]);
+        wk[s2][0] = w0.x; wk[s2][1] = w0.y; wk[s2][2] = w0.z; wk[s2][3] = w0.w;
+        wk[s2][4] = w1.x; wk[s2][5] = w1.y; wk[s2][6] = w1.z; wk[s2][7] = w1.w;
+      }
+#pragma unroll
+      for (int c = 0; c < kIn; ++c) {
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = __bfloat162float(v[c].v[j]);
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          const int s2 = c - o * kStride;        // compile-time after unrolling
+          if (s2 >= 0 && s2 < 3) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[o][j] = fmaf(f[j], wk[s2][j], acc[o][j]);
+          }
+        }
+      }
+    }
+    __nv_bfloat16* out = dst + (((size_t)n * OH + oh) * OW + ow0) * C + cg * 8;
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+      if (ow0 + o < OW) store8(out + (size_t)o * C, acc[o]);
+  }
+}
+
+inline dim3 dw_quad_grid(long long quads, int cv, int& cg_t, int& rows_t, int per_sm) {
+  const int nslab = (cv + 31) / 32;
+  cg_t = (cv + nslab - 1) / nslab;
+  rows_t = kThreads / cg_t;
+  const int slabs = (cv + cg_t - 1) / cg_t;
+  long long gx = (quads + rows_t * 2 - 1) / (rows_t * 2);
+  long long cap = (HB_NUM_SMS * per_sm) / slabs;
+  if (cap < 1) cap = 1;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  return dim3((unsigned)gx, (unsigned)slabs);
+}
+
 inline dim3 dw_grid(long long M, int cv, int& cg_t, int& rows_t, int per_sm) {
   const int nslab = (cv + 31) / 32;
   cg_t = (cv + nslab - 1) / nslab;      // balanced channel slabs (see bn_act.cu)
@@ -302,10 +401,19 @@ int hb_dwconv_fwd_bf16(const void* x, const float* w, const float* bias, void* y
   if (total <= 0) return 0;
   if (K == 3 && (long long)N * p.Ho * p.Wo < 0x7fffffffLL) {
     int cg_t, rows_t;
-    const dim3 grid = dw_grid((long long)N * p.Ho * p.Wo, C / 8, cg_t, rows_t, 3);
     const __nv_bfloat16* xb = (const __nv_bfloat16*)x;
     __nv_bfloat16* yb = (__nv_bfloat16*)y;
     cudaStream_t st = (cudaStream_t)stream;
+    static const bool quad_on = getenv("HB_DISABLE_DW_QUAD") == nullptr;
+    if (quad_on && (stride == 1 || stride == 2) && p.Wo >= 4) {
+      const long long quads = (long long)N * p.Ho * ((p.Wo + 3) / 4);
+      const dim3 qgrid = dw_quad_grid(quads, C / 8, cg_t, rows_t, 2);
+      if (stride == 1) dw3x3_quad_kernel<1, false><<<qgrid, kThreads, 0, st>>>(xb, w, bias, yb, N, H, W, p.Ho, p.Wo, C, pad, cg_t, rows_t);
+      else dw3x3_quad_kernel<2, false><<<qgrid, kThreads, 0, st>>>(xb, w, bias, yb, N, H, W, p.Ho, p.Wo, C, pad, cg_t, rows_t);
+      HB_LAUNCH_CHECK();
+      return 0;
+    }
+    const dim3 grid = dw_grid((long long)N * p.Ho * p.Wo, C / 8, cg_t, rows_t, 3);
     if (stride == 1) dw3x3_kernel<false, 1><<<grid, kThreads, 0, st>>>(xb, w, bias, yb, p, cg_t, rows_t);
     else if (stride == 2) dw3x3_kernel<false, 2><<<grid, kThreads, 0, st>>>(xb, w, bias, yb, p, cg_t, rows_t);
     else dw3x3_kernel<false, 0><<<grid, kThreads, 0, st>>>(xb, w, bias, yb, p, cg_t, rows_t);
@@ -326,10 +434,19 @@ int hb_dwconv_bwd_data_bf16(const void* dy, const float* w, void* dx, int N, int
   if (total <= 0) return 0;
   if (K == 3 && (long long)N * H * W < 0x7fffffffLL) {
     int cg_t, rows_t;
-    const dim3 grid = dw_grid((long long)N * H * W, C / 8, cg_t, rows_t, 3);
     const __nv_bfloat16* dyb = (const __nv_bfloat16*)dy;
     __nv_bfloat16* dxb = (__nv_bfloat16*)dx;
     cudaStream_t st = (cudaStream_t)stream;
+    static const bool quad_on = getenv("HB_DISABLE_DW_QUAD") == nullptr;
+    if (quad_on && stride == 1 && W >= 4 && pad <= 2) {
+      // stride 1: the data gradient is the correlation of dy [N,Ho,Wo,C] with the flipped filter, padding 2 - pad
+      const long long quads = (long long)N * H * ((W + 3) / 4);
+      const dim3 qgrid = dw_quad_grid(quads, C / 8, cg_t, rows_t, 2);
+      dw3x3_quad_kernel<1, true><<<qgrid, kThreads, 0, st>>>(dyb, w, nullptr, dxb, N, p.Ho, p.Wo, H, W, C, 2 - pad, cg_t, rows_t);
+      HB_LAUNCH_CHECK();
+      return 0;
+    }
+    const dim3 grid = dw_grid((long long)N * H * W, C / 8, cg_t, rows_t, 3);
     if (stride == 1) dw3x3_kernel<true, 1><<<grid, kThreads, 0, st>>>(dyb, w, nullptr, dxb, p, cg_t, rows_t);
     else if (stride == 2) dw3x3_kernel<true, 2><<<grid, kThreads, 0, st>>>(dyb, w, nullptr, dxb, p, cg_t, rows_t);
     else dw3x3_kernel<true, 0><<<grid, kThreads, 0, st>>>(dyb, w, nullptr, dxb, p, cg_t, rows_t);

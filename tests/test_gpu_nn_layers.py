@@ -180,6 +180,27 @@ def test_depthwise_conv_vs_oracle(stride, c):
     assert rel_l2(wd.grad, wo.grad) < 1e-3 and rel_l2(bd.grad, bo.grad) < 1e-3
 
 
+@pytest.mark.parametrize("shape", [(2, 96, 37, 29, 1, 1, False), (2, 40, 16, 16, 2, 1, True), (3, 176, 14, 14, 1, 1, False),
+                                   (2, 24, 9, 7, 2, 1, False), (1, 8, 5, 4, 1, 1, True), (2, 32, 8, 8, 1, 0, False),
+                                   (2, 16, 6, 3, 1, 1, False)])
+def test_depthwise_quad_kernel_edges(shape, monkeypatch):
+    """Four-outputs-per-thread depth-wise kernel (forward stride 1 / 2, data gradient stride 1 as a flipped correlation): ragged
+    widths (W % 4 != 0), padding 0 and 1, widths below one quad (falls back to the one-output kernel), bias."""
+    from holocron_b200.nn._dwconv import dwconv2d
+    n, c, h, w, stride, pad, bias = shape
+    torch.manual_seed(3)
+    x = torch.randn(n, c, h, w, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    wt = torch.randn(c, 1, 3, 3, device="cuda", requires_grad=True)
+    b = torch.randn(c, device="cuda", requires_grad=True) if bias else None
+    y = dwconv2d(x, wt, b, stride, pad)
+    xr = x.detach().float().requires_grad_(True)
+    ref = TF.conv2d(xr, wt, b, stride, pad, 1, c)
+    g = torch.randn_like(ref).bfloat16()
+    y.backward(g)
+    ref.backward(g.float())
+    assert rel_l2(y, ref) < 4e-3 and rel_l2(x.grad, xr.grad) < 4e-3
+
+
 def test_dropblock_vs_golden_and_edge_cases():
     g = load_golden("convs")
     x = g["dropblock_x"].cuda()
