@@ -61,6 +61,7 @@ SIGNATURES = {
     "hb_bn_act_bwd_bf16": "ppppi" + "pppppp" + "pppppp" + "pp" + "iiiifiip",
     "hb_dwconv_fwd_bf16": "pppp" + "iiiiiiip",
     "hb_dwconv_bwd_data_bf16": "ppp" + "iiiiiiip",
+    "hb_dwconv_wgrad_scratch_doubles": "ii",
     "hb_dwconv_bwd_weight_bf16": "ppppp" + "iiiiiiip",
     "hb_gap_fwd_bf16": "ppiiip",
     "hb_gap_bwd_bf16": "ppiiip",
@@ -79,6 +80,7 @@ SIGNATURES = {
     "hb_cls_loss_hard_bwd": "pppppp" + "iiiiiffiip",
     "hb_poly_soft_fwd": "pppppp" + "iiiifip",
     "hb_poly_soft_bwd": "ppppp" + "iiiifiip",
+    "hb_dice_scratch_doubles": "i",
     "hb_dice_fwd": "pppppp" + "iiqffip",
     "hb_dice_bwd": "pppp" + "iiqip",
     "hb_optim_chunk_elems": "",

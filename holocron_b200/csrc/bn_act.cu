@@ -16,6 +16,7 @@
 //   bwd apply  : one pass: du_b = scale_b * (dz - mean(dz) - xhat_b * mean(dz*xhat_b)), dresidual = dz
 // Every thread owns 8 consecutive channels (one 128-bit bf16 vector) of a row; rows are walked with a stride
 // that keeps the thread's channel group fixed, so per-channel parameters live in registers.
+#include <cstdio>
 #include <cstdlib>
 #include "common.cuh"
 #include "act.cuh"
@@ -127,23 +128,44 @@ struct FinalizeParams {
   int C_logical;  // channels >= C_logical are padding: scale = shift = 0, no parameter / running-stat access
   float eps, momentum;
 };
-// block = 32 channels (threadIdx.x, coalesced reads of the [slot][C][2] partials) x 8 slot lanes (threadIdx.y): each lane
-// adds its slots in order, the 8 lane sums are combined in lane order -> fixed summation order, run-to-run identical.
-// (One warp per channel with lanes striding over the slots read one 8-byte element per 32-byte sector: 10 us per launch.)
-__global__ void __launch_bounds__(256) bn_finalize_kernel(FinalizeParams p) {
-  __shared__ double red[2][8][32];
-  const int c = blockIdx.x * 32 + threadIdx.x;
+// block = 8 channels (threadIdx.x: one 64-byte run of the [slot][C][2] partials) x 32 slot lanes (threadIdx.y). A lane adds
+// slots L, L + 32, ... with four independent loads in flight, the 32 lane sums are then combined 8-by-8 in lane order: a
+// fixed summation order (run-to-run identical) whose dependent-load chain is slots / 128 long. (32 channels x 8 lanes: slots /
+// 8 dependent L2 round trips and C / 32 blocks - two blocks for a 48-channel layer - made each of these ~10-20 us.)
+constexpr int kFinCh = 8, kFinLanes = 32;
+
+__global__ void __launch_bounds__(kFinCh * kFinLanes) bn_finalize_kernel(FinalizeParams p) {
+  __shared__ double red[2][kFinLanes][kFinCh];
+  const int c = blockIdx.x * kFinCh + threadIdx.x;
   const int b = blockIdx.y;
   double s = 0.0, q = 0.0;
   if (c < p.C_logical) {
     const float* pp = p.parts[b] + (size_t)c * 2;
-    for (int k = threadIdx.y; k < p.slots[b]; k += 8) {
-      const float2 v = *reinterpret_cast<const float2*>(pp + (size_t)k * p.C * 2);
+    const size_t row = (size_t)p.C * 2;
+    const int n = p.slots[b];
+    int k = threadIdx.y;
+    for (; k + 3 * kFinLanes < n; k += 4 * kFinLanes) {
+      float2 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float2*>(pp + (size_t)(k + u * kFinLanes) * row);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { s += (double)v[u].x; q += (double)v[u].y; }
+    }
+    for (; k < n; k += kFinLanes) {
+      const float2 v = *reinterpret_cast<const float2*>(pp + (size_t)k * row);
       s += (double)v.x; q += (double)v.y;
     }
   }
   red[0][threadIdx.y][threadIdx.x] = s;
   red[1][threadIdx.y][threadIdx.x] = q;
+  __syncthreads();
+  if (threadIdx.y < 4) {
+    s = 0.0; q = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s += red[0][threadIdx.y * 8 + j][threadIdx.x]; q += red[1][threadIdx.y * 8 + j][threadIdx.x]; }
+  }
+  __syncthreads();
+  if (threadIdx.y < 4) { red[0][threadIdx.y][threadIdx.x] = s; red[1][threadIdx.y][threadIdx.x] = q; }
   __syncthreads();
   if (threadIdx.y != 0 || c >= p.C) return;
   const size_t o = (size_t)b * p.C + c;
@@ -153,7 +175,7 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(FinalizeParams p) {
   }
   s = 0.0; q = 0.0;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { s += red[0][j][threadIdx.x]; q += red[1][j][threadIdx.x]; }
+  for (int j = 0; j < 4; ++j) { s += red[0][j][threadIdx.x]; q += red[1][j][threadIdx.x]; }
   const double mean = s / p.M;
   double var = q / p.M - mean * mean;
   if (var < 0) var = 0;
@@ -625,23 +647,52 @@ struct BwdFinalizeParams {
   float* gacc[kMaxBranches]; float* bacc[kMaxBranches];
   int nblocks, B, C, C_logical;
 };
-// same block shape as bn_finalize_kernel: 32 channels (coalesced) x 8 block lanes, fixed order
-__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(BwdFinalizeParams p) {
-  __shared__ double red[1 + kMaxBranches][8][32];
-  const int c = blockIdx.x * 32 + threadIdx.x;
+// same block shape as bn_finalize_kernel: 8 channels x 32 row-block lanes, four independent rows in flight, fixed order
+__global__ void __launch_bounds__(kFinCh * kFinLanes) bn_bwd_finalize_kernel(BwdFinalizeParams p) {
+  __shared__ double red[1 + kMaxBranches][kFinLanes][kFinCh];
+  const int c = blockIdx.x * kFinCh + threadIdx.x;
   double acc[1 + kMaxBranches];
 #pragma unroll
   for (int i = 0; i <= kMaxBranches; ++i) acc[i] = 0.0;
   if (c < p.C) {
-    for (int k = threadIdx.y; k < p.nblocks; k += 8) {
-      const double* row = p.part + (size_t)k * (1 + p.B) * p.C + c;
+    const size_t row = (size_t)(1 + p.B) * p.C;
+    int k = threadIdx.y;
+    for (; k + 3 * kFinLanes < p.nblocks; k += 4 * kFinLanes) {
+      double v[4][1 + kMaxBranches];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int i = 0; i <= kMaxBranches; ++i)
+          if (i <= p.B) v[u][i] = p.part[(size_t)(k + u * kFinLanes) * row + (size_t)i * p.C + c];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int i = 0; i <= kMaxBranches; ++i)
+          if (i <= p.B) acc[i] += v[u][i];
+    }
+    for (; k < p.nblocks; k += kFinLanes) {
 #pragma unroll
       for (int i = 0; i <= kMaxBranches; ++i)
-        if (i <= p.B) acc[i] += row[(size_t)i * p.C];
+        if (i <= p.B) acc[i] += p.part[(size_t)k * row + (size_t)i * p.C + c];
     }
   }
 #pragma unroll
   for (int i = 0; i <= kMaxBranches; ++i) red[i][threadIdx.y][threadIdx.x] = acc[i];
+  __syncthreads();
+  if (threadIdx.y < 4) {
+#pragma unroll
+    for (int i = 0; i <= kMaxBranches; ++i) {
+      double t = 0.0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t += red[i][threadIdx.y * 8 + j][threadIdx.x];
+      acc[i] = t;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.y < 4) {
+#pragma unroll
+    for (int i = 0; i <= kMaxBranches; ++i) red[i][threadIdx.y][threadIdx.x] = acc[i];
+  }
   __syncthreads();
   if (threadIdx.y != 0 || c >= p.C) return;
   double tot[1 + kMaxBranches];
@@ -649,7 +700,7 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(BwdFinalizeParams 
   for (int i = 0; i <= kMaxBranches; ++i) {
     double t = 0.0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) t += red[i][j][threadIdx.x];
+    for (int j = 0; j < 4; ++j) t += red[i][j][threadIdx.x];
     tot[i] = t;
   }
   for (int i = 0; i <= p.B; ++i) p.sums[(size_t)i * p.C + c] = tot[i];
@@ -687,6 +738,33 @@ template <typename K>
 inline cudaError_t allow_smem(K kernel, size_t bytes) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
+
+// Resident blocks per SM of one kernel instantiation with SMEM dynamic bytes, asked from the runtime once. The grids are
+// persistent (every block walks M / gridDim.x rows), so a grid of 4 blocks per SM of a kernel that only fits 3 runs as one
+// full wave plus a one-third-occupied second wave: bn_act_fwd_kernel<2, 1> streamed at 3.3 TB/s with 592 blocks where the
+// 444-block <3, 1> reached 4.8 TB/s (profiles/r02_launches_repvgg_a0_b256.csv).
+template <typename K>
+inline int resident_blocks(K kernel, size_t smem) {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThreads, smem) != cudaSuccess || n < 1) n = 1;
+  return n;
+}
+#define HB_BN_OCC(KERNEL, NB, SMEM, OUT)                                                     \
+  {                                                                                          \
+    static int cached_occ_ = 0;                                                              \
+    if (!cached_occ_) {                                                                      \
+      if (allow_smem(KERNEL<NB>, 200 * 1024) != cudaSuccess) return (int)cudaErrorInvalidValue; \
+      cached_occ_ = resident_blocks(KERNEL<NB>, SMEM);                                       \
+    }                                                                                        \
+    OUT = cached_occ_;                                                                       \
+  }
+#define HB_BN_OCC_DISPATCH(KERNEL, B, SMEM, OUT)                                             \
+  switch (B) {                                                                               \
+    case 0: HB_BN_OCC(KERNEL, 0, SMEM, OUT) break;                                           \
+    case 1: HB_BN_OCC(KERNEL, 1, SMEM, OUT) break;                                           \
+    case 2: HB_BN_OCC(KERNEL, 2, SMEM, OUT) break;                                           \
+    default: HB_BN_OCC(KERNEL, 3, SMEM, OUT) break;                                          \
+  }
 
 #define HB_BN_LAUNCH(KERNEL, NB, GRID, SMEM, ST, ...)                                        \
   {                                                                                          \
@@ -743,7 +821,7 @@ int hb_bn_finalize(const float* const* parts, const int* slots, const float* con
   }
   p.mean = mean; p.rstd = rstd; p.scale = scale; p.shift = shift;
   p.B = B; p.C = C; p.M = M; p.C_logical = C_logical; p.eps = eps; p.momentum = momentum;
-  bn_finalize_kernel<<<dim3((C + 31) / 32, B), dim3(32, 8), 0, (cudaStream_t)stream>>>(p);
+  bn_finalize_kernel<<<dim3((C + kFinCh - 1) / kFinCh, B), dim3(kFinCh, kFinLanes), 0, (cudaStream_t)stream>>>(p);
   HB_LAUNCH_CHECK();
   return 0;
 }
@@ -769,23 +847,27 @@ int hb_bn_act_fwd_bf16(const void* u0, const void* u1, const void* u2, int B, co
   p.out_stats = out_stats;
   Geo g = Geo::make(C);
   static const int per_sm_env = env_int("HB_BN_CAP_FWD", 0);
-  // resident blocks per SM: 3 with three input tensors (64 KB ring each), 4 with fewer
-  const int per_sm = per_sm_env > 0 ? per_sm_env : (B + (residual != nullptr) >= 3 ? 3 : 4);
-  const dim3 grid = make_grid(g, M, 1, per_sm);
-  if (out_stat_slots) *out_stat_slots = (int)grid.x;
+  static const bool use_occ = env_int("HB_BN_USE_OCC", 1) != 0, occ_debug = env_int("HB_BN_DEBUG", 0) != 0;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = ring_bytes(B + 1);
+  // grid = min(4, resident blocks of this instantiation) per SM: registers (launch bound 3) and the ring (48 - 64 KB) decide
+#define HB_FWD_GO(NBV, STATS)                                                                              \
+  {                                                                                                        \
+    static int occ = 0;                                                                                    \
+    if (!occ) {                                                                                            \
+      if (allow_smem(bn_act_fwd_kernel<NBV, STATS>, 200 * 1024) != cudaSuccess) return (int)cudaErrorInvalidValue; \
+      occ = resident_blocks(bn_act_fwd_kernel<NBV, STATS>, smem);                                          \
+    }                                                                                                      \
+    if (occ_debug) fprintf(stderr, "[hb] bn_act_fwd_kernel<%d,%d> smem %zu: %d resident blocks/SM\n", NBV, (int)STATS, smem, occ); \
+    const int fixed = (B + (residual != nullptr) >= 3) ? 3 : 4;                                            \
+    const int per_sm = per_sm_env > 0 ? per_sm_env : (use_occ ? (occ < 4 ? occ : 4) : fixed);              \
+    const dim3 grid = make_grid(g, M, 1, per_sm);                                                          \
+    if (out_stat_slots) *out_stat_slots = (int)grid.x;                                                     \
+    bn_act_fwd_kernel<NBV, STATS><<<grid, kThreads, smem, st>>>(p, g);                                     \
+  }
 #define HB_FWD_CASE(NBV)                                                                                   \
   case NBV:                                                                                                \
-    if (out_stats) {                                                                                       \
-      static bool r1 = false;                                                                              \
-      if (!r1) { if (allow_smem(bn_act_fwd_kernel<NBV, true>, 200 * 1024) != cudaSuccess) return (int)cudaErrorInvalidValue; r1 = true; } \
-      bn_act_fwd_kernel<NBV, true><<<grid, kThreads, smem, st>>>(p, g);                                    \
-    } else {                                                                                               \
-      static bool r0 = false;                                                                              \
-      if (!r0) { if (allow_smem(bn_act_fwd_kernel<NBV, false>, 200 * 1024) != cudaSuccess) return (int)cudaErrorInvalidValue; r0 = true; } \
-      bn_act_fwd_kernel<NBV, false><<<grid, kThreads, smem, st>>>(p, g);                                   \
-    }                                                                                                      \
+    if (out_stats) HB_FWD_GO(NBV, true) else HB_FWD_GO(NBV, false)                                         \
     break;
   switch (B) {
     HB_FWD_CASE(0)
@@ -794,6 +876,7 @@ int hb_bn_act_fwd_bf16(const void* u0, const void* u1, const void* u2, int B, co
     default:
     HB_FWD_CASE(3)
   }
+#undef HB_FWD_GO
 #undef HB_FWD_CASE
   HB_LAUNCH_CHECK();
   return 0;
@@ -826,14 +909,18 @@ int hb_bn_act_bwd_bf16(const void* dout, const void* u0, const void* u1, const v
   Geo g = Geo::make(C);
   cudaStream_t st = (cudaStream_t)stream;
   static const int cap_red_env = env_int("HB_BN_CAP_RED", 0), cap_app_env = env_int("HB_BN_CAP_APPLY", 0);
+  static const bool use_occ = env_int("HB_BN_USE_OCC", 1) != 0, occ_debug = env_int("HB_BN_DEBUG", 0) != 0;
   // one branch (Darknet / ReXNet / UNet blocks): ~70 registers and a 48 KB ring -> three resident blocks per SM
   int cap_red = cap_red_env > 0 ? cap_red_env : (B <= 1 ? 3 : 2);
   if (cap_red > 3) cap_red = 3;   // hb_bn_bwd_scratch_doubles sizes the partials for <= 3 blocks per SM
-  const int cap_app = cap_app_env > 0 ? cap_app_env : (B <= 1 ? 3 : 2);
+  const int cap_app = cap_app_env > 0 ? cap_app_env : (B <= 2 ? 3 : 2);   // further limited by the measured occupancy
   const bool want_params = (dgamma && dbeta) || gamma_grad_acc || beta_grad_acc;
   if (train || want_params) {
-    const dim3 grid = make_grid(g, M, 1, cap_red);
     const size_t smem = sizeof(SlabConsts) + kThreads * 8 * sizeof(float) + ring_bytes(B + 2);
+    int occ = 1;
+    HB_BN_OCC_DISPATCH(bn_act_bwd_reduce_kernel, B, smem, occ)
+    if (occ_debug) fprintf(stderr, "[hb] bn_act_bwd_reduce_kernel<%d> smem %zu: %d resident blocks/SM (cap %d)\n", B, smem, occ, cap_red);
+    const dim3 grid = make_grid(g, M, 1, (use_occ && occ < cap_red) ? occ : cap_red);
     HB_BN_DISPATCH(bn_act_bwd_reduce_kernel, B, grid, smem, st, p, g)
     HB_LAUNCH_CHECK();
     BwdFinalizeParams f{};
@@ -843,12 +930,15 @@ int hb_bn_act_bwd_bf16(const void* dout, const void* u0, const void* u1, const v
       f.bacc[b] = beta_grad_acc ? beta_grad_acc[b] : nullptr;
     }
     f.nblocks = (int)grid.x; f.B = B; f.C = C; f.C_logical = C_logical > 0 ? C_logical : C;
-    bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(f);
+    bn_bwd_finalize_kernel<<<(C + kFinCh - 1) / kFinCh, dim3(kFinCh, kFinLanes), 0, st>>>(f);
     HB_LAUNCH_CHECK();
   }
   {
-    const dim3 grid = make_grid(g, M, 1, cap_app);
     const size_t smem = sizeof(SlabConsts) + ring_bytes(B + 2);
+    int occ = 1;
+    HB_BN_OCC_DISPATCH(bn_act_bwd_apply_kernel, B, smem, occ)
+    if (occ_debug) fprintf(stderr, "[hb] bn_act_bwd_apply_kernel<%d> smem %zu: %d resident blocks/SM (cap %d)\n", B, smem, occ, cap_app);
+    const dim3 grid = make_grid(g, M, 1, (use_occ && occ < cap_app) ? occ : cap_app);
     HB_BN_DISPATCH(bn_act_bwd_apply_kernel, B, grid, smem, st, p, g)
     HB_LAUNCH_CHECK();
   }

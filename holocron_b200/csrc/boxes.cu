@@ -68,13 +68,40 @@ __device__ __forceinline__ float pair_value(int mode, const Box& a, const Box& b
   return 0.f;
 }
 
-__global__ void pairwise_kernel(const float* __restrict__ b1, const float* __restrict__ b2, float* __restrict__ out, int M,
-                                int N, int mode) {
-  const long long total = (long long)M * N;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int i = (int)(idx / N), j = (int)(idx % N);
-    out[idx] = pair_value(mode, load_box(b1 + 4 * i), load_box(b2 + 4 * j));
+// Tile = kRows rows of boxes1 x (blockDim.x * 4) columns of boxes2. A thread keeps its 4 boxes2 in registers, walks the
+// rows (boxes1 row = one broadcast 16-byte load) and writes 4 consecutive outputs per row - one 128-bit store when the
+// output row is 16-byte aligned. The first version did a 64-bit division and 8 scalar loads per PAIR (0.07-0.10 of the HBM
+// rate on 4096 x 4096). kMode is a template parameter so the per-pair switch is gone as well.
+constexpr int kRows = 16;
+
+template <int kMode>
+__global__ void __launch_bounds__(128) pairwise_kernel(const float* __restrict__ b1, const float* __restrict__ b2,
+                                                       float* __restrict__ out, int M, int N) {
+  const int j0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (j0 >= N) return;
+  const int i0 = blockIdx.y * kRows;
+  const int i1 = min(i0 + kRows, M);
+  Box b[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 v = __ldg((const float4*)b2 + min(j0 + q, N - 1));
+    b[q] = Box{v.x, v.y, v.z, v.w};
+  }
+  const bool vec = (N & 3) == 0 && j0 + 3 < N && ((size_t)out & 15) == 0;
+  for (int i = i0; i < i1; ++i) {
+    const float4 va = __ldg((const float4*)b1 + i);
+    const Box a{va.x, va.y, va.z, va.w};
+    float r[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) r[q] = pair_value(kMode, a, b[q]);
+    float* o = out + (size_t)i * N + j0;
+    if (vec) {
+      *(float4*)o = make_float4(r[0], r[1], r[2], r[3]);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (j0 + q < N) o[q] = r[q];
+    }
   }
 }
 
@@ -190,9 +217,18 @@ extern "C" {
 int hb_box_pairwise(const float* boxes1, const float* boxes2, float* out, int M, int N, int mode, void* stream) {
   const long long total = (long long)M * N;
   if (total == 0) return 0;
-  long long grid = (total + 255) / 256;
-  if (grid > HB_NUM_SMS * 8) grid = HB_NUM_SMS * 8;
-  pairwise_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(boxes1, boxes2, out, M, N, mode);
+  if ((((size_t)boxes1) | ((size_t)boxes2)) & 15) return (int)cudaErrorMisalignedAddress;   // [*, 4] fp32 rows: float4 loads
+  const dim3 grid((N + 4 * 128 - 1) / (4 * 128), (M + kRows - 1) / kRows);
+  if (grid.y > 65535) return (int)cudaErrorInvalidValue;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (mode) {
+    case M_IOU: pairwise_kernel<M_IOU><<<grid, 128, 0, st>>>(boxes1, boxes2, out, M, N); break;
+    case M_GIOU: pairwise_kernel<M_GIOU><<<grid, 128, 0, st>>>(boxes1, boxes2, out, M, N); break;
+    case M_PENALTY: pairwise_kernel<M_PENALTY><<<grid, 128, 0, st>>>(boxes1, boxes2, out, M, N); break;
+    case M_DIOU_LOSS: pairwise_kernel<M_DIOU_LOSS><<<grid, 128, 0, st>>>(boxes1, boxes2, out, M, N); break;
+    case M_ARC: pairwise_kernel<M_ARC><<<grid, 128, 0, st>>>(boxes1, boxes2, out, M, N); break;
+    default: return (int)cudaErrorInvalidValue;
+  }
   HB_LAUNCH_CHECK();
   return 0;
 }

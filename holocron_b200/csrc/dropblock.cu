@@ -55,6 +55,34 @@ __global__ void dropblock_apply_kernel(const T* x, T* out, const float* __restri
   }
 }
 
+// channels_last fast path: one 128-bit vector (16 / sizeof(T) channels of one pixel) per thread step, 32-bit index arithmetic
+// (the scalar kernel above did a 64-bit division per ELEMENT and ran at 0.9 TB/s; YOLOv4 has a DropBlock behind every conv)
+template <typename T>
+__global__ void __launch_bounds__(256) dropblock_apply_nhwc_vec_kernel(const T* x, T* out, const float* __restrict__ mask,
+                                                                       const float* __restrict__ kept, unsigned total_vec,
+                                                                       unsigned cvec, float numel) {
+  const float k = *kept;
+  const float scale = k > 0.f ? numel / k : 1.f;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += gridDim.x * blockDim.x) {
+    const float m = __ldg(mask + i / cvec) * scale;
+    Vec16<T> v = ld16(x + (size_t)i * Vec16<T>::N);
+#pragma unroll
+    for (int j = 0; j < Vec16<T>::N; ++j) v.v[j] = from_f<T>(to_f(v.v[j]) * m);
+    st16(out + (size_t)i * Vec16<T>::N, v);
+  }
+}
+
+template <typename T>
+bool launch_nhwc_vec(const void* x, void* out, const float* mask, const float* kept, long long total, int C, float numel,
+                     cudaStream_t st) {
+  constexpr int V = Vec16<T>::N;
+  if (C % V != 0 || !aligned16(x) || !aligned16(out) || total / V >= 0xffffffffLL) return false;
+  const unsigned total_vec = (unsigned)(total / V);
+  dropblock_apply_nhwc_vec_kernel<T><<<stream_grid((size_t)total_vec, 256 * 2), 256, 0, st>>>(
+      (const T*)x, (T*)out, mask, kept, total_vec, (unsigned)(C / V), numel);
+  return true;
+}
+
 }  // namespace
 
 extern "C" {
@@ -83,6 +111,13 @@ int hb_dropblock_apply(const void* x, void* out, const float* mask, const float*
   const float numel = (float)((long long)N * HW);
   const int grid = stream_grid((size_t)total, 256 * 4);
   cudaStream_t st = (cudaStream_t)stream;
+  if (channels_last) {
+    bool done = false;
+    if (dtype == HB_DTYPE_BF16) done = launch_nhwc_vec<__nv_bfloat16>(x, out, mask, kept, total, C, numel, st);
+    else if (dtype == HB_DTYPE_F16) done = launch_nhwc_vec<__half>(x, out, mask, kept, total, C, numel, st);
+    else if (dtype == HB_DTYPE_F32) done = launch_nhwc_vec<float>(x, out, mask, kept, total, C, numel, st);
+    if (done) { HB_LAUNCH_CHECK(); return 0; }
+  }
   switch (dtype) {
     case HB_DTYPE_F32: dropblock_apply_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (float*)out, mask, kept, total, C, HW, channels_last, numel); break;
     case HB_DTYPE_BF16: dropblock_apply_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, mask, kept, total, C, HW, channels_last, numel); break;

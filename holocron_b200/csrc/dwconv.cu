@@ -282,11 +282,12 @@ inline dim3 dw_grid(long long M, int cv, int& cg_t, int& rows_t, int per_sm) {
   return dim3((unsigned)gx, (unsigned)slabs);
 }
 
-// dw[c,r,s] = sum_{n,ho,wo} dy * x_shifted ; db[c] = sum dy.  sums: double [C][KK+1] (last column = bias grad)
-// block geometry as in the BN kernels: tx = channel group within a 32-group slab, ty = pixel lane
+// dw[c,r,s] = sum_{n,ho,wo} dy * x_shifted ; db[c] = sum dy.  part: double [gridDim.x][C][KK+1] per-block partial sums (last
+// column = bias grad), folded in a fixed order by dw_weight_finalize_kernel: deterministic (the first version added doubles
+// atomically). Block geometry as in the BN kernels: tx = channel group within a 32-group slab, ty = pixel lane
 template <int KS>
 __global__ void __launch_bounds__(kThreads, KS == 3 ? 2 : 1) dw_bwd_weight_kernel(const __nv_bfloat16* __restrict__ x,
-                                                                 const __nv_bfloat16* __restrict__ dy, double* sums,
+                                                                 const __nv_bfloat16* __restrict__ dy, double* part,
                                                                  DwParams p, int cg_t, int rows_t) {
   constexpr int KK = KS * KS;
   __shared__ float red[kThreads * 8];
@@ -368,17 +369,147 @@ __global__ void __launch_bounds__(kThreads, KS == 3 ? 2 : 1) dw_bwd_weight_kerne
       if (gcg >= cv) continue;
       double a = 0.0;
       for (int r = 0; r < rows_t; ++r) a += (double)red[(r * cg_t + ctx) * 8 + j];
-      atomicAdd(&sums[(size_t)(gcg * 8 + j) * (KK + 1) + k], a);
+      part[((size_t)blockIdx.x * p.C + gcg * 8 + j) * (KK + 1) + k] = a;
     }
   }
 }
 
-__global__ void dw_weight_finalize_kernel(const double* sums, float* dw, float* db, int C, int KK) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= C * (KK + 1)) return;
+// 3x3 weight gradient, stride 1 / 2: a thread owns ONE filter row r and FOUR consecutive output pixels of a row. It loads the 4
+// dy vectors and the 3*S + 3 input vectors of input row oh*S + r - pad (all in flight before the first use) and keeps 3 taps x 8
+// channels (+ the bias column on r == 0) of accumulators: 32 instead of 80, so two blocks per SM fit without serialising the
+// loads filter row by filter row, and 7.5 / 11.25 vector loads per output pixel instead of 10. ty = lane * 3 + r.
+template <int kStride>
+__global__ void __launch_bounds__(kThreads, 2) dw3x3_wgrad_quad_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                    const __nv_bfloat16* __restrict__ dy, double* part,
+                                                                    DwParams p, int cg_t, int lanes) {
+  __shared__ float red[kThreads * 8];
+  const int cv = p.C / 8;
+  const int tx = threadIdx.x % cg_t, ty = threadIdx.x / cg_t;
+  const int r = ty % 3, lane = ty / 3;
+  const int cg = blockIdx.y * cg_t + tx;
+  const bool active = lane < lanes && cg < cv;
+  float acc[4][8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
+  if (active) {
+    constexpr int kIn = 3 * kStride + 3;
+    const int qw = (p.Wo + 3) >> 2;
+    const unsigned total = (unsigned)p.N * p.Ho * qw;
+    const size_t C = (size_t)p.C;
+    for (unsigned q = blockIdx.x * lanes + lane; q < total; q += gridDim.x * lanes) {
+      const unsigned t1 = q / (unsigned)qw;
+      const int ow0 = (int)(q - t1 * (unsigned)qw) * 4;
+      const unsigned n = t1 / (unsigned)p.Ho;
+      const int oh = (int)(t1 - n * (unsigned)p.Ho);
+      const int ih = oh * kStride + r - p.pad;
+      const bool hok = ih >= 0 && ih < p.H;
+      if (!hok && r != 0) continue;
+      const __nv_bfloat16* dyp = dy + (((size_t)n * p.Ho + oh) * p.Wo + ow0) * C + cg * 8;
+      Vec16<__nv_bfloat16> gv[4], xv[kIn];
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        if (ow0 + o < p.Wo) gv[o] = ld16(dyp + (size_t)o * C);
+        else gv[o].raw = make_uint4(0, 0, 0, 0);
+      }
+      if (hok) {
+        const __nv_bfloat16* row = x + (((size_t)n * p.H + ih) * p.W) * C + cg * 8;
+        const int iw0 = ow0 * kStride - p.pad;
+#pragma unroll
+        for (int c = 0; c < kIn; ++c) {
+          const int iw = iw0 + c;
+          if (iw >= 0 && iw < p.W) xv[c] = ld16(row + (size_t)iw * C);
+          else xv[c].raw = make_uint4(0, 0, 0, 0);
+        }
+      }
+      float g[4][8];
+#pragma unroll
+      for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[o][j] = __bfloat162float(gv[o].v[j]);
+      if (r == 0) {
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[3][j] += g[o][j];
+      }
+      if (hok) {
+#pragma unroll
+        for (int c = 0; c < kIn; ++c) {
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = __bfloat162float(xv[c].v[j]);
+#pragma unroll
+          for (int o = 0; o < 4; ++o) {
+            const int s2 = c - o * kStride;   // compile-time after unrolling
+            if (s2 >= 0 && s2 < 3) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[s2][j] = fmaf(g[o][j], f[j], acc[s2][j]);
+            }
+          }
+        }
+      }
+    }
+  }
+  const int nch = cg_t * 8;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[threadIdx.x * 8 + j] = acc[k][j];
+    __syncthreads();
+    const int nr = k < 3 ? 3 : 1;             // the bias column lives on the r == 0 threads only
+    for (int idx = threadIdx.x; idx < nch * nr; idx += kThreads) {
+      const int rr = idx / nch, ch = idx - rr * nch;
+      const int ctx = ch / 8, j = ch % 8;
+      const int gcg = blockIdx.y * cg_t + ctx;
+      if (gcg >= cv) continue;
+      double a = 0.0;
+      for (int l = 0; l < lanes; ++l) a += (double)red[(((l * 3 + rr) * cg_t) + ctx) * 8 + j];
+      part[((size_t)blockIdx.x * p.C + gcg * 8 + j) * 10 + (k < 3 ? rr * 3 + k : 9)] = a;
+    }
+  }
+}
+
+// dw / db = sum over the gx row blocks of part[g][c][k]: block = 8 entries (one 64-byte run) x 32 block lanes, four rows in
+// flight, lane sums combined in lane order (fixed order, see bn_finalize_kernel)
+__global__ void __launch_bounds__(256) dw_weight_finalize_kernel(const double* part, int gx, float* dw, float* db, int C, int KK) {
+  __shared__ double red[32][8];
+  const int E = C * (KK + 1);
+  const int i = blockIdx.x * 8 + threadIdx.x;
+  double a = 0.0;
+  if (i < E) {
+    int g = threadIdx.y;
+    for (; g + 96 < gx; g += 128) {
+      double v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = part[(size_t)(g + 32 * u) * E + i];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) a += v[u];
+    }
+    for (; g < gx; g += 32) a += part[(size_t)g * E + i];
+  }
+  red[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.y != 0 || i >= E) return;
+  a = 0.0;
+#pragma unroll
+  for (int l = 0; l < 32; ++l) a += red[l][threadIdx.x];
   const int c = i / (KK + 1), k = i % (KK + 1);
-  if (k < KK) dw[c * KK + k] = (float)sums[i];
-  else if (db) db[c] = (float)sums[i];
+  if (k < KK) dw[c * KK + k] = (float)a;
+  else if (db) db[c] = (float)a;
+}
+
+// channel-slab geometry of the weight-gradient kernels and the number of row blocks (<= 2 blocks per SM over all slabs)
+inline void dw_wgrad_geo(int C, int& cg_t, int& rows_t, int& slabs, int& gx_max) {
+  const int cv = C / 8;
+  const int nslab = (cv + 31) / 32;
+  cg_t = (cv + nslab - 1) / nslab;
+  rows_t = kThreads / cg_t;
+  slabs = (cv + cg_t - 1) / cg_t;
+  gx_max = (HB_NUM_SMS * 2) / slabs;
+  if (gx_max < 1) gx_max = 1;
 }
 
 DwParams make_params(int N, int H, int W, int C, int K, int stride, int pad) {
@@ -459,39 +590,53 @@ int hb_dwconv_bwd_data_bf16(const void* dy, const float* w, void* dx, int N, int
   return 0;
 }
 
-// dw fp32 [C,K,K], db fp32 [C] (or NULL); sums: double scratch [C * (K*K + 1)], zeroed here. K in {1, 3, 5, 7}.
-int hb_dwconv_bwd_weight_bf16(const void* x, const void* dy, float* dw, float* db, double* sums, int N, int H, int W,
+// doubles of scratch hb_dwconv_bwd_weight_bf16 needs for C channels and a K x K filter (per-block partial sums)
+size_t hb_dwconv_wgrad_scratch_doubles(int C, int K) {
+  if (C <= 0 || C % 8 != 0) return 0;
+  int cg_t, rows_t, slabs, gx_max;
+  dw_wgrad_geo(C, cg_t, rows_t, slabs, gx_max);
+  return (size_t)gx_max * C * (K * K + 1);
+}
+
+// dw fp32 [C,K,K], db fp32 [C] (or NULL); scratch: double[hb_dwconv_wgrad_scratch_doubles(C, K)]. K in {1, 3, 5, 7}.
+int hb_dwconv_bwd_weight_bf16(const void* x, const void* dy, float* dw, float* db, double* scratch, int N, int H, int W,
                               int C, int K, int stride, int pad, void* stream) {
   if (C % 8 != 0) return (int)cudaErrorInvalidValue;
   cudaStream_t st = (cudaStream_t)stream;
   DwParams p = make_params(N, H, W, C, K, stride, pad);
   const int KK = K * K;
-  cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * C * (KK + 1), st);
-  if (e != cudaSuccess) return (int)e;
-  const int cv = C / 8;
-  const int nslab = (cv + 31) / 32;
-  const int cg_t = (cv + nslab - 1) / nslab;
-  const int rows_t = kThreads / cg_t;
-  const int slabs = (cv + cg_t - 1) / cg_t;
+  int cg_t, rows_t, slabs, gx_max;
+  dw_wgrad_geo(C, cg_t, rows_t, slabs, gx_max);
   const long long M = (long long)N * p.Ho * p.Wo;
   if (M >= 0x7fffffffLL) return (int)cudaErrorInvalidValue;
-  long long gx = (M + rows_t * 8 - 1) / (rows_t * 8);
-  long long cap = (HB_NUM_SMS * 4) / slabs;
-  if (cap < 1) cap = 1;
-  if (gx > cap) gx = cap;
-  if (gx < 1) gx = 1;
-  dim3 grid((unsigned)gx, (unsigned)slabs);
   const __nv_bfloat16* xb = (const __nv_bfloat16*)x;
   const __nv_bfloat16* dyb = (const __nv_bfloat16*)dy;
-  switch (K) {
-    case 1: dw_bwd_weight_kernel<1><<<grid, kThreads, 0, st>>>(xb, dyb, sums, p, cg_t, rows_t); break;
-    case 3: dw_bwd_weight_kernel<3><<<grid, kThreads, 0, st>>>(xb, dyb, sums, p, cg_t, rows_t); break;
-    case 5: dw_bwd_weight_kernel<5><<<grid, kThreads, 0, st>>>(xb, dyb, sums, p, cg_t, rows_t); break;
-    case 7: dw_bwd_weight_kernel<7><<<grid, kThreads, 0, st>>>(xb, dyb, sums, p, cg_t, rows_t); break;
-    default: return (int)cudaErrorInvalidValue;
+  static const bool quad_on = getenv("HB_DISABLE_DW_QUAD") == nullptr;
+  long long gx;
+  if (quad_on && K == 3 && (stride == 1 || stride == 2) && rows_t >= 3) {
+    const int lanes = rows_t / 3;
+    const long long quads = (long long)N * p.Ho * ((p.Wo + 3) / 4);
+    gx = (quads + lanes * 2 - 1) / (lanes * 2);
+    if (gx > gx_max) gx = gx_max;
+    if (gx < 1) gx = 1;
+    const dim3 grid((unsigned)gx, (unsigned)slabs);
+    if (stride == 1) dw3x3_wgrad_quad_kernel<1><<<grid, kThreads, 0, st>>>(xb, dyb, scratch, p, cg_t, lanes);
+    else dw3x3_wgrad_quad_kernel<2><<<grid, kThreads, 0, st>>>(xb, dyb, scratch, p, cg_t, lanes);
+  } else {
+    gx = (M + rows_t * 8 - 1) / (rows_t * 8);
+    if (gx > gx_max) gx = gx_max;
+    if (gx < 1) gx = 1;
+    const dim3 grid((unsigned)gx, (unsigned)slabs);
+    switch (K) {
+      case 1: dw_bwd_weight_kernel<1><<<grid, kThreads, 0, st>>>(xb, dyb, scratch, p, cg_t, rows_t); break;
+      case 3: dw_bwd_weight_kernel<3><<<grid, kThreads, 0, st>>>(xb, dyb, scratch, p, cg_t, rows_t); break;
+      case 5: dw_bwd_weight_kernel<5><<<grid, kThreads, 0, st>>>(xb, dyb, scratch, p, cg_t, rows_t); break;
+      case 7: dw_bwd_weight_kernel<7><<<grid, kThreads, 0, st>>>(xb, dyb, scratch, p, cg_t, rows_t); break;
+      default: return (int)cudaErrorInvalidValue;
+    }
   }
   HB_LAUNCH_CHECK();
-  dw_weight_finalize_kernel<<<(C * (KK + 1) + 127) / 128, 128, 0, st>>>(sums, dw, db, C, KK);
+  dw_weight_finalize_kernel<<<(C * (KK + 1) + 7) / 8, dim3(8, 32), 0, st>>>(scratch, (int)gx, dw, db, C, KK);
   HB_LAUNCH_CHECK();
   return 0;
 }

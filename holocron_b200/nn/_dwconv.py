@@ -45,7 +45,7 @@ class _DwConvFn(torch.autograd.Function):
         if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
             dw = torch.empty((c, 1, k, k), device=dyb.device, dtype=torch.float32)
             db = torch.empty(c, device=dyb.device, dtype=torch.float32) if has_bias else None
-            sums = torch.empty(c * (k * k + 1), device=dyb.device, dtype=torch.float64)
+            sums = torch.empty(L.hb_dwconv_wgrad_scratch_doubles(c, k), device=dyb.device, dtype=torch.float64)
             check(L.hb_dwconv_bwd_weight_bf16(ptr(xb), ptr(dyb), ptr(dw), ptr(db), ptr(sums), n, h, w, c, k, stride, pad,
                                               stream_ptr()), "hb_dwconv_bwd_weight_bf16")
         return dx, dw, db, None, None

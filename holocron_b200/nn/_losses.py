@@ -143,7 +143,7 @@ class _DiceFn(torch.autograd.Function):
         xc = x.contiguous()
         tc = target.to(xc.dtype).contiguous()
         n, k, s = _nks(xc)
-        sums = torch.empty(2 * k, device=x.device, dtype=torch.float64)
+        sums = torch.empty(lib().hb_dice_scratch_doubles(k), device=x.device, dtype=torch.float64)
         out = torch.empty(1, device=x.device, dtype=torch.float32)
         coef = torch.empty(2 * k, device=x.device, dtype=torch.float32)
         check(lib().hb_dice_fwd(ptr(xc), ptr(tc), ptr(weight), ptr(sums), ptr(out), ptr(coef), n, k, s, _cf(gamma),

@@ -15,7 +15,9 @@ def _prep(boxes: Tensor) -> Tensor:
     if boxes.ndim != 2 or boxes.shape[1] != 4:
         raise ValueError("boxes are expected as (num_boxes, 4) tensors in xyxy format")
     # box arithmetic always runs in fp32 (the reference's intermediates are fp32 whatever the input dtype)
-    return boxes.float().contiguous()
+    out = boxes.float().contiguous()
+    # the kernels read a box as one 16-byte load
+    return out if out.data_ptr() % 16 == 0 else out.clone()
 
 
 class _PairwiseFn(torch.autograd.Function):

@@ -171,8 +171,10 @@ int hb_dwconv_fwd_bf16(const void* x, const float* w, const float* bias, void* y
                        int stride, int pad, void* stream);
 int hb_dwconv_bwd_data_bf16(const void* dy, const float* w, void* dx, int N, int H, int W, int C, int K, int stride,
                             int pad, void* stream);
-/* dw fp32 [C,K,K], db fp32 [C] or NULL; sums: double scratch [C*(K*K+1)]; K in {1,3,5,7} */
-int hb_dwconv_bwd_weight_bf16(const void* x, const void* dy, float* dw, float* db, double* sums, int N, int H, int W,
+/* dw fp32 [C,K,K], db fp32 [C] or NULL; scratch: double[hb_dwconv_wgrad_scratch_doubles(C, K)] (per-block partial sums,
+ * folded in a fixed order: deterministic); K in {1,3,5,7} */
+size_t hb_dwconv_wgrad_scratch_doubles(int C, int K);
+int hb_dwconv_bwd_weight_bf16(const void* x, const void* dy, float* dw, float* db, double* scratch, int N, int H, int W,
                               int C, int K, int stride, int pad, void* stream);
 
 /* ---- global average pooling: holocron/nn/modules/downsample.py:58-74 ----------------------------------- */
@@ -233,8 +235,10 @@ int hb_poly_soft_fwd(const void* x, const void* soft, const float* weight, float
                      float* fwd_out, int N, int K, int S, int ignore_index, float eps, int dtype, void* stream);
 int hb_poly_soft_bwd(const void* x, const void* soft, const float* weight, const float* gout, void* dx, int N, int K,
                      int S, int ignore_index, float eps, int reduction, int dtype, void* stream);
-/* sums: double[2K] scratch; out: float[1]; coef: float[2K] (input of hb_dice_bwd) */
-int hb_dice_fwd(const void* x, const void* target, const float* weight, double* sums, float* out, float* coef, int N,
+/* scratch: double[hb_dice_scratch_doubles(K)] (per-block partial sums, folded in a fixed order: deterministic);
+ * out: float[1]; coef: float[2K] (input of hb_dice_bwd) */
+size_t hb_dice_scratch_doubles(int K);
+int hb_dice_fwd(const void* x, const void* target, const float* weight, double* scratch, float* out, float* coef, int N,
                 int K, long long S, float gamma, float eps, int dtype, void* stream);
 int hb_dice_bwd(const void* target, const float* coef, const float* gout, void* dx, int N, int K, long long S, int dtype,
                 void* stream);

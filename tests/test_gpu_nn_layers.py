@@ -194,11 +194,41 @@ def test_depthwise_quad_kernel_edges(shape, monkeypatch):
     b = torch.randn(c, device="cuda", requires_grad=True) if bias else None
     y = dwconv2d(x, wt, b, stride, pad)
     xr = x.detach().float().requires_grad_(True)
-    ref = TF.conv2d(xr, wt, b, stride, pad, 1, c)
+    wr = wt.detach().clone().requires_grad_(True)
+    br = b.detach().clone().requires_grad_(True) if bias else None
+    ref = TF.conv2d(xr, wr, br, stride, pad, 1, c)
     g = torch.randn_like(ref).bfloat16()
     y.backward(g)
     ref.backward(g.float())
     assert rel_l2(y, ref) < 4e-3 and rel_l2(x.grad, xr.grad) < 4e-3
+    # weight / bias gradients (one filter row x four outputs per thread; per-block partials folded in a fixed order)
+    assert rel_l2(wt.grad, wr.grad) < 1e-3
+    if bias:
+        assert rel_l2(b.grad, br.grad) < 1e-3
+    first = wt.grad.clone()
+    wt.grad = None
+    dwconv2d(x, wt, b, stride, pad).backward(g)
+    assert torch.equal(first, wt.grad)          # deterministic: no atomics
+
+
+@pytest.mark.parametrize("k", [1, 5, 7])
+def test_depthwise_other_filter_sizes_weight_gradient(k):
+    """k != 3 takes the one-output-per-thread kernels; their weight gradient uses the same per-block partials + ordered fold."""
+    from holocron_b200.nn._dwconv import dwconv2d
+    torch.manual_seed(k)
+    c = 40
+    x = torch.randn(3, c, 13, 11, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    wt = torch.randn(c, 1, k, k, device="cuda", requires_grad=True)
+    b = torch.randn(c, device="cuda", requires_grad=True)
+    y = dwconv2d(x, wt, b, 1, k // 2)
+    xr = x.detach().float().requires_grad_(True)
+    wr, br = wt.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    ref = TF.conv2d(xr, wr, br, 1, k // 2, 1, c)
+    g = torch.randn_like(ref).bfloat16()
+    y.backward(g)
+    ref.backward(g.float())
+    assert rel_l2(y, ref) < 4e-3 and rel_l2(x.grad, xr.grad) < 4e-3
+    assert rel_l2(wt.grad, wr.grad) < 1e-3 and rel_l2(b.grad, br.grad) < 1e-3
 
 
 def test_dropblock_vs_golden_and_edge_cases():

@@ -253,3 +253,78 @@ def test_boxes_large_vs_oracle():
     ao = b1.clone().requires_grad_(True)
     OB.ciou_loss(ao, b2).min(dim=1).values.sum().backward()
     close(a.grad, ao.grad, 1e-3, 1e-5)
+
+
+@pytest.mark.parametrize("m,n", [(33, 64), (5, 3), (1, 1), (17, 516), (40, 1028), (3, 7)])
+def test_boxes_tile_edges_bit_exact(m, n):
+    """Tiled kernel: 4 columns per thread (128-bit store when N % 4 == 0, scalar tail otherwise), 16 rows per block, 512
+    columns per block in x - every edge, all five operators, bit for bit against the CPU oracle."""
+    torch.manual_seed(m * 1000 + n)
+    xy = torch.rand(m, 2); wh = torch.rand(m, 2) * 0.3 + 0.01
+    b1 = torch.cat([xy, xy + wh], 1)
+    xy = torch.rand(n, 2); wh = torch.rand(n, 2) * 0.3 + 0.01
+    b2 = torch.cat([xy, xy + wh], 1)
+    assert torch.equal(B.box_iou(b1.cuda(), b2.cuda()).cpu(), OB.box_iou(b1, b2))
+    assert torch.equal(B.box_giou(b1.cuda(), b2.cuda()).cpu(), OB.box_giou(b1, b2))
+    assert torch.equal(B.diou_loss(b1.cuda(), b2.cuda()).cpu(), OB.diou_loss(b1, b2))
+    assert torch.equal(B.ciou_loss(b1.cuda(), b2.cuda()).cpu(), OB.ciou_loss(b1, b2))
+    # a view whose storage offset is not a multiple of 16 bytes is re-aligned by the wrapper
+    flat = torch.cat([torch.zeros(1), b1.flatten()]).cuda()
+    assert torch.equal(B.diou_loss(flat[1:].view(m, 4), b2.cuda()).cpu(), OB.diou_loss(b1, b2))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("k,hw", [(3, (8, 12)), (12, (4, 8)), (21, (16, 8)), (30, (6, 4)), (40, (4, 4)), (21, (5, 7))])
+def test_losses_register_resident_path_vs_oracle(dtype, k, hw):
+    """S > 1 and K <= 32 take the register-resident kernels (KMAX 8 / 16 / 24 / 32; 8-byte vectors: S % 2 == 0 for fp32,
+    S % 4 == 0 for bf16), everything else the one-position-per-thread kernels: both against the CPU oracle on the SAME
+    (dtype-rounded) logits, forward and backward, with class weights and an ignored class."""
+    torch.manual_seed(k)
+    n = 3
+    x = (torch.randn(n, k, *hw) * 2).to(dtype)
+    t = torch.randint(0, k, (n, *hw))
+    w = torch.rand(k) + 0.5
+    soft = torch.softmax(torch.randn(n, k, *hw), 1).to(dtype)
+    tol = dict(rtol=2e-5, atol=2e-6) if dtype == torch.float32 else dict(rtol=2 ** -7, atol=2e-3)
+    gtol = dict(rtol=1e-4, atol=1e-6) if dtype == torch.float32 else dict(rtol=2 ** -6, atol=2e-3)
+    cases = [
+        (lambda a, tt: F.focal_loss(a, tt, w.to(a.device), 1, "mean", 2.0), lambda a: OF.focal_loss(a, t, w, 1, "mean", 2.0), t),
+        (lambda a, tt: F.focal_loss(a, tt, None, -100, "none", 0.5), lambda a: OF.focal_loss(a, t, None, -100, "none", 0.5), t),
+        (lambda a, tt: F.poly_loss(a, tt, 2.0, w.to(a.device), 1, "sum"), lambda a: OF.poly_loss(a, t, 2.0, w, 1, "sum"), t),
+        (lambda a, tt: F.poly_loss(a, tt, 1.5, None, 1, "mean"), lambda a: OF.poly_loss(a, soft.float(), 1.5, None, 1, "mean"), soft),
+        (lambda a, tt: F.poly_loss(a, tt, 2.0, None, -100, "none"), lambda a: OF.poly_loss(a, soft.float(), 2.0, None, -100, "none"), soft),
+    ]
+    for ours, ref, tgt in cases:
+        a = x.clone().cuda().requires_grad_(True)
+        y = ours(a, tgt.cuda())
+        up = torch.rand(y.shape, generator=torch.Generator().manual_seed(1)) + 0.5
+        (y.float() * up.cuda()).sum().backward()
+        ao = x.float().clone().requires_grad_(True)
+        yo = ref(ao)
+        (yo * up).sum().backward()
+        torch.testing.assert_close(y.detach().float().cpu(), yo.detach(), **tol)
+        torch.testing.assert_close(a.grad.float().cpu(), ao.grad, **gtol)
+
+
+def test_dice_is_deterministic_and_matches_oracle_on_ragged_planes():
+    """Per-block partial sums folded in a fixed order: two runs are bit-identical (the first version added doubles
+    atomically); vector (S % 8 == 0 bf16, S % 4 == 0 fp32) and scalar planes against the oracle."""
+    torch.manual_seed(5)
+    for dtype, shape in ((torch.float32, (4, 21, 64, 64)), (torch.float32, (3, 5, 7, 9)), (torch.bfloat16, (4, 21, 32, 40)),
+                         (torch.bfloat16, (2, 3, 5, 5))):
+        p = torch.softmax(torch.randn(*shape), 1).to(dtype)
+        oh = torch.nn.functional.one_hot(torch.randint(0, shape[1], (shape[0], *shape[2:])), shape[1]).movedim(-1, 1).to(dtype)
+        w = torch.rand(shape[1]) + 0.5
+        runs = []
+        for _ in range(2):
+            a = p.clone().cuda().requires_grad_(True)
+            y = F.dice_loss(a, oh.cuda(), w.cuda(), 2.0)
+            y.backward()
+            runs.append((y.detach().clone(), a.grad.clone()))
+        assert torch.equal(runs[0][0], runs[1][0]) and torch.equal(runs[0][1], runs[1][1])
+        ao = p.float().clone().requires_grad_(True)
+        yo = OF.dice_loss(ao, oh.float(), w, 2.0)
+        yo.backward()
+        fp32 = dtype == torch.float32
+        close(runs[0][0], yo, 2e-5 if fp32 else 2 ** -7, 1e-6 if fp32 else 1e-3)
+        close(runs[0][1], ao.grad, 1e-4 if fp32 else 2 ** -6, 1e-8 if fp32 else 1e-6)
