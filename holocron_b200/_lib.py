@@ -95,6 +95,11 @@ SIGNATURES = {
     "hb_lamb_step": "ppiifffffffpp",
     "hb_tadam_step": "ppiifffffifipp" + "p",
     "hb_step_increment": "ppp",
+    "hb_adan_step": "ppi" + "ffffff" + "ii" + "ppp",
+    "hb_ademamix_step": "ppi" + "fffffff" + "i" + "ppp",
+    "hb_lars_step": "ppii" + "ffff" + "ii" + "pp",
+    "hb_ralars_step": "ppii" + "fffffff" + "ifi" + "pp",
+    "hb_lookahead_sync": "ppi" + "f" + "p",
 }
 _CTYPE = {"p": ctypes.c_void_p, "i": ctypes.c_int, "z": ctypes.c_size_t, "f": ctypes.c_float, "q": ctypes.c_longlong}
 

@@ -37,9 +37,14 @@ class TensorTable:
         self.num_tensors = 0
         self.scratch: Optional[Tensor] = None
 
-    def update(self, params: List[Tensor], grads: List[Tensor], ms: List[Tensor], vs: List[Tensor],
-               vmaxs: Optional[List[Tensor]], auxs: Optional[List[Tensor]]) -> None:
-        cols = [params, grads, ms, vs, vmaxs or [None] * len(params), auxs or [None] * len(params)]
+    def update(self, params: List[Tensor], grads: Optional[List[Tensor]], ms: Optional[List[Tensor]],
+               vs: Optional[List[Tensor]], vmaxs: Optional[List[Tensor]], auxs: Optional[List[Tensor]],
+               exts: Optional[List[Tensor]] = None, full_aux: bool = False) -> None:
+        """Columns: parameter, gradient, two state tensors, amsgrad maximum, ``aux`` (a 1-element per-tensor scalar such as
+        TAdam's ``W_t`` / the LARS trust ratio, or - ``full_aux`` - a full-size tensor such as Adan's ``prev_grad``) and
+        ``ext`` (a third full-size state tensor: Adan's ``exp_avg_delta``, AdEMAMix's ``exp_avg_slow``)."""
+        none = [None] * len(params)
+        cols = [params, grads or none, ms or none, vs or none, vmaxs or none, auxs or none, exts or none]
         key = tuple(0 if t is None else t.data_ptr() for col in cols for t in col)
         if key == self.key:
             return
@@ -49,10 +54,11 @@ class TensorTable:
         for i, p in enumerate(params):
             group = [col[i] for col in cols]
             require_cuda(*[t for t in group if t is not None])
-            for t in group[:5]:
+            full = group[:5] + [group[6]] + ([group[5]] if full_aux else [])
+            for t in full:
                 if t is not None and t.dtype != torch.float32:
                     raise TypeError("the fused optimizers keep parameters, gradients and state in float32")
-            if not _same_dense_layout(group[:5]):
+            if not _same_dense_layout(full):
                 raise RuntimeError("parameter, gradient and optimizer state must share one dense memory layout")
             rows.append([0 if t is None else t.data_ptr() for t in group] + [p.numel()])
             n_chunks = (p.numel() + chunk - 1) // chunk

@@ -244,7 +244,7 @@ int hb_dice_bwd(const void* target, const float* coef, const float* gout, void* 
                 void* stream);
 
 /* ---- optimizers: holocron/optim/adabelief.py:121-167, lamb.py:79-137, tadam.py:160-212 ----------------- */
-/* metas: device table of T records {p, g, m, v, vmax, aux, numel} (7 x 8 bytes each, fp32 tensors);
+/* metas: device table of T records {p, g, m, v, vmax, aux, ext, numel} (8 x 8 bytes each, fp32 tensors);
  * chunks: device int2[num_chunks] = {tensor index, chunk index}, chunk = hb_optim_chunk_elems() elements. */
 int hb_optim_chunk_elems(void);
 /* ctl (may be NULL): device control block of a captured training step (see hb_train_ctl_* below): the kernels then read
@@ -264,6 +264,26 @@ int hb_tadam_step(const void* metas, const void* chunks, int num_chunks, int T, 
                   float eps, float weight_decay, int amsgrad, float dof, int step, const int* step_dev, double* scratch,
                   void* stream);
 int hb_step_increment(int* step_dev, const void* ctl, void* stream);
+/* The remaining optimizers of holocron/optim, same tables:
+ * Adan, adan.py:145-199 - aux = prev_grad (read, never written: reference quirk), ext = exp_avg_delta, vmax = its running max;
+ *   one launch, 40 B/parameter. */
+int hb_adan_step(const void* metas, const void* chunks, int num_chunks, float lr, float beta1, float beta2, float beta3,
+                 float eps, float weight_decay, int amsgrad, int step, const int* step_dev, const void* ctl, void* stream);
+/* AdEMAMix, ademamix.py:138-176 - ext = exp_avg_slow; one launch, 36 B/parameter. */
+int hb_ademamix_step(const void* metas, const void* chunks, int num_chunks, float lr, float beta1, float beta2, float beta3,
+                     float alpha, float eps, float weight_decay, int step, const int* step_dev, const void* ctl,
+                     void* stream);
+/* LARS, lars.py:91-135 - m = momentum_buffer (NULL without momentum); first != 0 when this step creates the buffers; with
+ *   weight decay the gradients are overwritten by g + wd * p like the reference's in-place add_. scratch: double [2*T]. */
+int hb_lars_step(const void* metas, const void* chunks, int num_chunks, int T, float lr, float momentum, float dampening,
+                 float weight_decay, int nesterov, int first, double* scratch, void* stream);
+/* RaLars, ralars.py:56-140 - mode 0 rectified update (x r_t), 1 plain Adam ratio, 2 unadapted momentum (chosen on the host
+ *   from the SMA length); aux = local_lr (1 element, written). scratch: double [2*T]. */
+int hb_ralars_step(const void* metas, const void* chunks, int num_chunks, int T, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, float clip_lo, float clip_hi, int mode, float r_t, int step, double* scratch,
+                   void* stream);
+/* Lookahead.sync_params, wrapper.py:122-135 - p = fast weights, m = slow weights: slow += rate * (fast - slow); fast = slow */
+int hb_lookahead_sync(const void* metas, const void* chunks, int num_chunks, float sync_rate, void* stream);
 
 /* ---- training-loop control on the device: holocron/trainer/core.py:135-227 (_fit_epoch: NaN-loss skipping :153-159,
  *      per-iteration scheduler.step() :161; _backprop_step: gradient accumulation, clip_grad_norm_, optimizer.step :184-208)

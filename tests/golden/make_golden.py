@@ -275,7 +275,63 @@ def gen_models():
     torch.save(d, OUT / "models.pt")
 
 
-if __name__ == "__main__" and not any(f in sys.argv for f in ("--zoo", "--api", "--trainer")):
+def gen_optim2():
+    """The remaining optimizers of the reference: Adan, AdEMAMix, LARS, RaLars and the Lookahead wrapper, four
+    steps each on tensors of several sizes (gradient of step k = k * g + 0.01 * p0) -> tests/golden/optim2.pt."""
+    optim = holocron.optim
+    torch.manual_seed(7)
+    shapes = [(16, 8, 3, 3), (33,), (10, 16), (1,), (4099,)]
+    ps = [torch.randn(s) * 0.2 for s in shapes]
+    gs = [torch.randn(s) * 5e-2 for s in shapes]
+    cfgs = {
+        "adan": (optim.Adan, dict(lr=1e-2, betas=(0.98, 0.92, 0.99), eps=1e-8)),
+        "adan_wd_ams": (optim.Adan, dict(lr=1e-2, betas=(0.9, 0.8, 0.95), eps=1e-6, weight_decay=2e-2, amsgrad=True)),
+        "ademamix": (optim.AdEMAMix, dict(lr=1e-2, betas=(0.9, 0.99, 0.999), alpha=5.0, eps=1e-8)),
+        "ademamix_wd": (optim.AdEMAMix, dict(lr=1e-2, betas=(0.8, 0.95, 0.99), alpha=2.0, eps=1e-6, weight_decay=1e-2)),
+        "lars": (optim.LARS, dict(lr=1e-1)),
+        "lars_mom_wd": (optim.LARS, dict(lr=1e-1, momentum=0.9, dampening=0.1, weight_decay=1e-2)),
+        "lars_nesterov": (optim.LARS, dict(lr=1e-1, momentum=0.8, nesterov=True, weight_decay=1e-3)),
+        "ralars": (optim.RaLars, dict(lr=1e-2, betas=(0.9, 0.99), eps=1e-8)),               # sma_t <= 4 during the first steps
+        "ralars_rect_wd": (optim.RaLars, dict(lr=1e-2, betas=(0.5, 0.6), eps=1e-6, weight_decay=1e-2, scale_clip=(0.1, 1.0))),
+        "ralars_force": (optim.RaLars, dict(lr=1e-2, betas=(0.9, 0.99), eps=1e-8, force_adaptive_momentum=True)),
+    }
+    d = dict(params=ps, grads=gs, steps=6)
+    for name, (cls, kw) in cfgs.items():
+        params = [torch.nn.Parameter(p.clone()) for p in ps]
+        opt = cls(params, **kw)
+        traj = []
+        for it in range(1, 7):
+            for p, p0, g in zip(params, ps, gs):
+                p.grad = g * it + 0.01 * p0
+            opt.step()
+            if it in (1, 3, 6):
+                traj.append([p.detach().clone() for p in params])
+        d[name] = dict(kw=kw, traj=traj)      # parameters after steps 1, 3 and 6
+        if "lars_mom" in name:
+            d[name]["grad_after"] = [p.grad.clone() for p in params]     # the reference decays the gradient IN PLACE
+        if name.startswith("ralars"):
+            d[name]["local_lr"] = [float(opt.state[p]["local_lr"]) for p in params]
+    # Lookahead over SGD with momentum: sync every 3 steps
+    params = [torch.nn.Parameter(p.clone()) for p in ps]
+    base = torch.optim.SGD(params, lr=0.1, momentum=0.9)
+    la = optim.wrapper.Lookahead(base, sync_rate=0.5, sync_period=3)
+    traj = []
+    for it in range(1, 8):
+        for p, p0, g in zip(params, ps, gs):
+            p.grad = g * it + 0.01 * p0
+        la.step()
+        if it in (2, 3, 7):
+            traj.append([p.detach().clone() for p in params])
+    d["lookahead"] = dict(traj=traj, slow=[p.clone() for p in la.param_groups[0]["params"]], repr=repr(la))
+    torch.save(d, OUT / "optim2.pt")
+
+
+if __name__ == "__main__" and "--optim2" in sys.argv:
+    gen_optim2()
+    print("optim2.pt", (OUT / "optim2.pt").stat().st_size)
+
+
+if __name__ == "__main__" and not any(f in sys.argv for f in ("--zoo", "--api", "--trainer", "--optim2")):
     gen_activations()
     gen_losses()
     gen_boxes()
@@ -389,7 +445,8 @@ API_SURFACE = {
     "nn": ["HardMish", "NLReLU", "FReLU", "NormConv2d", "Add2d", "SlimConv2d", "FocalLoss", "PolyLoss", "DiceLoss", "DropBlock2d",
            "GlobalAvgPool2d", "SPP"],
     "ops.boxes": ["box_giou", "diou_loss", "ciou_loss", "iou_penalty", "aspect_ratio", "aspect_ratio_consistency"],
-    "optim": ["AdaBelief", "LAMB", "TAdam"],
+    "optim": ["AdaBelief", "LAMB", "TAdam", "AdamP", "Adan", "AdEMAMix", "LARS", "RaLars"],
+    "optim.wrapper": ["Lookahead"],
     "models": ["repvgg_a0", "repvgg_a1", "repvgg_a2", "repvgg_b0", "repvgg_b1", "repvgg_b2", "repvgg_b3", "rexnet1_0x", "rexnet1_3x",
                "rexnet1_5x", "rexnet2_0x", "rexnet2_2x", "darknet24", "darknet19", "darknet53", "cspdarknet53", "cspdarknet53_mish"],
     "models.detection": ["yolov4"],

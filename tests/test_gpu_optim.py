@@ -133,3 +133,134 @@ def test_full_size_repvgg_a1_parameter_set_vs_oracle():
         hb.optim.AdaBelief([p], lr=lr).step()
         outs.append(p.detach() - p0)
     close(outs[1], 2 * outs[0], 1e-3, 1e-6)   # differences of fp32 parameters: quantised at ulp(p) ~ 1e-7
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Adan, AdEMAMix, LARS, RaLars, Lookahead - trajectories of the unmodified reference (tests/golden/optim2.pt)
+OPTIM2 = [("adan", "Adan"), ("adan_wd_ams", "Adan"), ("ademamix", "AdEMAMix"), ("ademamix_wd", "AdEMAMix"), ("lars", "LARS"),
+          ("lars_mom_wd", "LARS"), ("lars_nesterov", "LARS"), ("ralars", "RaLars"), ("ralars_rect_wd", "RaLars"),
+          ("ralars_force", "RaLars")]
+
+
+def _drive(opt, params, g, steps, keep):
+    out = []
+    for it in range(1, steps + 1):
+        for p, p0, gr in zip(params, g["params"], g["grads"]):
+            p.grad = (gr * it + 0.01 * p0).cuda()
+        opt.step()
+        if it in keep:
+            out.append([p.detach().clone() for p in params])
+    return out
+
+
+@pytest.mark.parametrize("name,cls", OPTIM2)
+def test_remaining_optimizers_vs_reference_trajectories(name, cls):
+    g = load_golden("optim2")
+    kw = g[name]["kw"]
+    params = [torch.nn.Parameter(p.clone().cuda()) for p in g["params"]]
+    opt = getattr(hb.optim, cls)(params, **kw)
+    traj = _drive(opt, params, g, 6, (1, 3, 6))
+    for ours, ref in zip(traj, g[name]["traj"]):
+        for a, b in zip(ours, ref):
+            close(a, b, 2e-4, 2e-6)
+    st = opt.state[params[0]]
+    if cls == "Adan":
+        assert set(st) >= {"step", "exp_avg", "exp_avg_sq", "exp_avg_delta", "prev_grad"} and st["step"] == 6
+        assert not st["prev_grad"].any()          # reference quirk: allocated, never written
+        assert ("max_exp_avg_delta" in st) == bool(kw.get("amsgrad"))
+    if cls == "AdEMAMix":
+        assert set(st) == {"step", "exp_avg", "exp_avg_slow", "exp_avg_sq"}
+    if cls == "LARS":
+        assert ("momentum_buffer" in st) == (kw.get("momentum", 0.0) != 0)
+        assert opt.scale_clip == (0.0, 10.0)
+        if "grad_after" in g[name]:
+            for p, want in zip(params, g[name]["grad_after"]):     # the weight decay lands IN the gradient, as in the reference
+                close(p.grad, want, 1e-5, 1e-7)
+    if cls == "RaLars":
+        for p, want in zip(params, g[name]["local_lr"]):
+            got = float(opt.state[p]["local_lr"])
+            assert abs(got - want) <= 2e-4 * max(1.0, abs(want)), (got, want)
+    # Optimizer protocol: state_dict round trip, then one more step
+    opt2 = getattr(hb.optim, cls)(params, **kw)
+    opt2.load_state_dict(opt.state_dict())
+    for p in params:
+        p.grad = torch.ones_like(p)
+    opt2.step()
+
+
+def test_remaining_optimizers_argument_validation_like_the_reference():
+    w = [torch.nn.Parameter(torch.randn(4, 4, device="cuda"))]
+    with pytest.raises(ValueError):
+        hb.optim.LARS(w, lr=1)                      # the reference insists on a python float (lars.py:60)
+    with pytest.raises(ValueError):
+        hb.optim.LARS(w, lr=0.1, nesterov=True)     # needs momentum
+    with pytest.raises(ValueError):
+        hb.optim.AdEMAMix(w, betas=(0.9, 0.999, 1.0))
+    with pytest.raises(ValueError):
+        hb.optim.RaLars(w, eps=-1.0)
+    with pytest.raises(ValueError):
+        hb.optim.Adan(w, lr=-1.0)
+    with pytest.raises(ValueError):
+        hb.optim.wrapper.Lookahead(torch.optim.SGD(w, lr=0.1), sync_rate=1.5)
+    with pytest.raises(ValueError):
+        hb.optim.wrapper.Lookahead(torch.optim.SGD(w, lr=0.1), sync_period=0)
+    assert isinstance(hb.optim.Adan(w), torch.optim.Adam)
+
+
+def test_adan_functional_and_capturable():
+    g = load_golden("optim2")
+    kw = g["adan"]["kw"]
+    params = [torch.nn.Parameter(p.clone().cuda()) for p in g["params"]]
+    opt = hb.optim.Adan(params, capturable=True, **kw)
+    traj = _drive(opt, params, g, 3, (1, 3))
+    for ours, ref in zip(traj, g["adan"]["traj"][:2]):
+        for a, b in zip(ours, ref):
+            close(a, b, 2e-4, 2e-6)
+    # functional form == one step of the oracle
+    ps = [p.clone().cuda() for p in g["params"]]
+    gs = [gr.clone().cuda() for gr in g["grads"]]
+    z = lambda: [torch.zeros_like(p) for p in ps]       # noqa: E731
+    hb.optim.adan(ps, gs, z(), z(), z(), z(), [], [1] * len(ps), False, 0.98, 0.92, 0.99, 1e-2, 0.0, 1e-8)
+    for p, p0, gr in zip(ps, g["params"], g["grads"]):
+        ref = p0.clone()
+        OO.adan_step(ref, gr, torch.zeros_like(ref), torch.zeros_like(ref), torch.zeros_like(ref), torch.zeros_like(ref), 1, 1e-2,
+                     0.98, 0.92, 0.99, 1e-8)
+        close(p, ref, 2e-4, 2e-6)
+    ps = [p.clone().cuda() for p in g["params"]]
+    hb.optim.ademamix(ps, gs, z(), z(), z(), [2] * len(ps), 0.9, 0.99, 0.999, 5.0, 1e-2, 1e-2, 1e-8)
+    for p, p0, gr in zip(ps, g["params"], g["grads"]):
+        ref = p0.clone()
+        OO.ademamix_step(ref, gr, torch.zeros_like(ref), torch.zeros_like(ref), torch.zeros_like(ref), 2, 1e-2, 0.9, 0.99, 0.999, 5.0,
+                         1e-8, 1e-2)
+        close(p, ref, 2e-4, 2e-6)
+
+
+def test_lookahead_vs_reference_trajectory_and_state_dict():
+    g = load_golden("optim2")
+    params = [torch.nn.Parameter(p.clone().cuda()) for p in g["params"]]
+    base = torch.optim.SGD(params, lr=0.1, momentum=0.9)
+    la = hb.optim.wrapper.Lookahead(base, sync_rate=0.5, sync_period=3)
+    traj = _drive(la, params, g, 7, (2, 3, 7))
+    for ours, ref in zip(traj, g["lookahead"]["traj"]):
+        for a, b in zip(ours, ref):
+            close(a, b, 1e-5, 1e-6)
+    for s, want in zip(la.param_groups[0]["params"], g["lookahead"]["slow"]):
+        close(s, want, 1e-5, 1e-6)
+    assert la.fast_steps == 7
+    assert repr(la) == g["lookahead"]["repr"]
+    sd = la.state_dict()
+    assert "base_state_dict" in sd and "param_groups" in sd
+    # sync_rate 0: the fast weights are reset to the slow ones
+    for p in params:
+        p.data.add_(1.0)
+    la.sync_params(0.0)
+    for p, s in zip(params, la.param_groups[0]["params"]):
+        assert torch.equal(p.data, s)
+    # the wrapper also drives the fused optimizers
+    la2 = hb.optim.wrapper.Lookahead(hb.optim.AdaBelief(params, lr=1e-3), sync_period=2)
+    for _ in range(4):
+        for p in params:
+            p.grad = torch.ones_like(p)
+        la2.step()
+    la2.zero_grad()
+    assert all(p.grad is None for p in params)

@@ -124,3 +124,40 @@ def test_zoo_state_dicts_match_oracle_free_checks():
     assert y.head.head1[-1].out_channels == 255 and float(y.head.head3[-1].bias.abs().sum()) == 0.0
     u = hb.models.unet3p(num_classes=21)
     assert u.classifier.in_channels == 320 and len(u.decoder) == 4
+
+
+def test_remaining_optimizer_constructors_validate_like_the_reference():
+    """Host-side argument checks of Adan / AdEMAMix / LARS / RaLars / Lookahead (reference adan.py:58-66, ademamix.py:63-70,
+    lars.py:60-79, ralars.py:38-46, wrapper.py:33-37) - no kernel is launched."""
+    import pytest
+    import torch
+
+    import holocron_b200 as hb
+    w = [torch.nn.Parameter(torch.randn(4, 4))]
+    with pytest.raises(ValueError):
+        hb.optim.LARS(w, lr=1)
+    with pytest.raises(ValueError):
+        hb.optim.LARS(w, lr=0.1, momentum=-0.1)
+    with pytest.raises(ValueError):
+        hb.optim.LARS(w, lr=0.1, nesterov=True)
+    with pytest.raises(ValueError):
+        hb.optim.AdEMAMix(w, betas=(0.9, 0.999, 1.0))
+    with pytest.raises(ValueError):
+        hb.optim.RaLars(w, betas=(1.0, 0.9))
+    with pytest.raises(ValueError):
+        hb.optim.Adan(w, eps=-1.0)
+    with pytest.raises(ValueError):
+        hb.optim.wrapper.Lookahead(torch.optim.SGD(w, lr=0.1), sync_rate=-0.1)
+    assert hb.optim.LARS(w, lr=0.1).scale_clip == (0.0, 10.0) and hb.optim.RaLars(w).scale_clip == (0, 10)
+    assert hb.optim.Adan(w).defaults["betas"] == (0.98, 0.92, 0.99)
+    assert hb.optim.AdEMAMix(w).defaults["alpha"] == 5.0
+    la = hb.optim.wrapper.Lookahead(torch.optim.SGD(w, lr=0.1), sync_period=2)
+    assert la.defaults == {"sync_rate": 0.5, "sync_period": 2} and la.fast_steps == 0
+    assert la.param_groups[0]["params"][0] is not w[0] and torch.equal(la.param_groups[0]["params"][0], w[0].data)
+    assert "base_state_dict" in la.state_dict()
+    la.add_param_group({"params": [torch.nn.Parameter(torch.randn(2))]})
+    assert len(la.param_groups) == 2 and len(la.base_optimizer.param_groups) == 2
+    # a fused step on CPU tensors fails loudly: there is no CPU fallback
+    w[0].grad = torch.ones_like(w[0])
+    with pytest.raises((RuntimeError, TypeError, ValueError)):
+        hb.optim.Adan(w).step()

@@ -84,10 +84,17 @@ def run_micro(peaks):
     for p in params:
         p.grad = torch.randn_like(p) * 1e-2
     np_ = sum(p.numel() for p in params)
-    for name, cls, per in (("AdaBelief.step", hb.optim.AdaBelief, 28), ("LAMB.step", hb.optim.LAMB, 40), ("TAdam.step", hb.optim.TAdam, 40)):
+    # algorithmic bytes / parameter: state tensors read + written once per pass (two passes where a per-tensor norm gates the
+    # update: LAMB, TAdam, AdamP, RaLars 40 = 24 + 16; LARS without momentum 8 + 12)
+    for name, cls, per in (("AdaBelief.step", hb.optim.AdaBelief, 28), ("LAMB.step", hb.optim.LAMB, 40), ("TAdam.step", hb.optim.TAdam, 40),
+                           ("AdamP.step", hb.optim.AdamP, 40), ("Adan.step", hb.optim.Adan, 40), ("AdEMAMix.step", hb.optim.AdEMAMix, 36),
+                           ("LARS.step", hb.optim.LARS, 20), ("RaLars.step", hb.optim.RaLars, 40)):
         opt = cls(params, lr=1e-4)
         row(name, [len(params), np_], _time(opt.step, flush), per * np_, l2="L2 flushed")
         del opt
+    la = hb.optim.wrapper.Lookahead(torch.optim.SGD(params, lr=1e-4))
+    row("Lookahead.sync_params", [len(params), np_], _time(lambda: la.sync_params(0.5), flush), 16 * np_, l2="L2 flushed")
+    del la
     del model, params
     # ---- NormConv2d / Add2d (CUDA-core kernels: report FLOP-equivalents as well) and DropBlock
     x = torch.randn(32, 64, 56, 56, device=dev)
