@@ -402,7 +402,8 @@ def roofline_leg(K, run_step, opt_step, n_params: int, step_ms: float, images: i
     try:
         with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             tk = json.load(f)["kernels"]
-        famk = [tk[k] for k in dom.split("+") if k in tk]
+        names = dom.split("+")      # ncu prints template arguments: conv_fprop_kernel<0>, bn_act_fwd_kernel<3, 1>, ...
+        famk = [v for k, v in tk.items() if any(k == n or k.startswith(n + "<") for n in names)]
         if famk:
             roof["traffic"] = sum(k["dram_read_bytes"] + k["dram_write_bytes"] for k in famk) / max(sum(k["launches"] for k in famk), 1)
             roof["traffic_source"] = "ncu dram__bytes_read.sum + dram__bytes_write.sum (profiles/r02_traffic.json), per launch"
