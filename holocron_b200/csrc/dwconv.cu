@@ -256,6 +256,80 @@ __global__ void __launch_bounds__(kThreads, 2) dw3x3_quad_kernel(const __nv_bflo
   }
 }
 
+// Stride-2, pad-1 data gradient, four consecutive dx columns (w0 % 4 == 0) per thread. With stride 2 only the taps whose
+// parity matches reach a dx pixel: row h takes filter row 1 (h even, dy row h/2) or rows 0 and 2 (h odd, dy rows (h+1)/2 and
+// (h-1)/2); along W the quad {w0..w0+3} reads the three dy columns c0 = w0/2, c0+1, c0+2 in a fixed pattern:
+//   dx[w0]   += dy[c0]   w[.,1]              dx[w0+1] += dy[c0+1] w[.,0] + dy[c0]   w[.,2]
+//   dx[w0+2] += dy[c0+1] w[.,1]              dx[w0+3] += dy[c0+2] w[.,0] + dy[c0+1] w[.,2]
+// 3 - 6 vector loads per 4 outputs; the one-output kernel issued 9 predicated loads per output (0.9 TB/s on ReXNet's four
+// stride-2 blocks, 4.8 % of the step).
+__global__ void __launch_bounds__(kThreads, 2) dw3x3_dgrad_s2_quad_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                                        const float* __restrict__ w, __nv_bfloat16* __restrict__ dx,
+                                                                        int N, int H, int W, int Ho, int Wo, int C, int cg_t,
+                                                                        int rows_t) {
+  __shared__ __align__(16) float ws[9][256];
+  const int cv = C / 8;
+  const int tx = threadIdx.x % cg_t, ty = threadIdx.x / cg_t;
+  const int cg = blockIdx.y * cg_t + tx;
+  for (int i = threadIdx.x; i < 9 * cg_t * 8; i += kThreads) {
+    const int k = i / (cg_t * 8), ch = i % (cg_t * 8);
+    const int c = blockIdx.y * cg_t * 8 + ch;
+    ws[k][ch] = c < C ? w[c * 9 + k] : 0.f;
+  }
+  __syncthreads();
+  if (ty >= rows_t || cg >= cv) return;
+  const int qw = (W + 3) >> 2;
+  const unsigned total = (unsigned)N * H * qw;
+  for (unsigned q = blockIdx.x * rows_t + ty; q < total; q += gridDim.x * rows_t) {
+    const unsigned t1 = q / (unsigned)qw;
+    const int w0 = (int)(q - t1 * (unsigned)qw) * 4;
+    const unsigned n = t1 / (unsigned)H;
+    const int h = (int)(t1 - n * (unsigned)H);
+    const int c0 = w0 >> 1;
+    float acc[4][8];
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[o][j] = 0.f;
+    const __nv_bfloat16* dn = dy + (size_t)n * Ho * Wo * C + cg * 8;
+    for (int r = (h & 1) ? 0 : 1; r < 3; r += 2) {
+      const int oh = (h + 1 - r) >> 1;
+      if (oh >= Ho) continue;
+      const __nv_bfloat16* row = dn + (size_t)oh * Wo * C;
+      Vec16<__nv_bfloat16> v[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        if (c0 + i < Wo) v[i] = ld16(row + (size_t)(c0 + i) * C);
+        else v[i].raw = make_uint4(0, 0, 0, 0);
+      }
+      float wk[3][8];
+#pragma unroll
+      for (int s2 = 0; s2 < 3; ++s2) {
+        const float4 a = *reinterpret_cast<const float4*>(&ws[r * 3 + s2][tx * 8]);
+        const float4 b = *reinterpret_cast<const float4*>(&ws[r * 3 + s2][tx * 8 + 4]);
+        wk[s2][0] = a.x; wk[s2][1] = a.y; wk[s2][2] = a.z; wk[s2][3] = a.w;
+        wk[s2][4] = b.x; wk[s2][5] = b.y; wk[s2][6] = b.z; wk[s2][7] = b.w;
+      }
+      float f[3][8];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[i][j] = __bfloat162float(v[i].v[j]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[0][j] = fmaf(f[0][j], wk[1][j], acc[0][j]);
+        acc[1][j] = fmaf(f[1][j], wk[0][j], fmaf(f[0][j], wk[2][j], acc[1][j]));
+        acc[2][j] = fmaf(f[1][j], wk[1][j], acc[2][j]);
+        acc[3][j] = fmaf(f[2][j], wk[0][j], fmaf(f[1][j], wk[2][j], acc[3][j]));
+      }
+    }
+    __nv_bfloat16* out = dx + (((size_t)n * H + h) * W + w0) * C + cg * 8;
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+      if (w0 + o < W) store8(out + (size_t)o * C, acc[o]);
+  }
+}
+
 inline dim3 dw_quad_grid(long long quads, int cv, int& cg_t, int& rows_t, int per_sm) {
   const int nslab = (cv + 31) / 32;
   cg_t = (cv + nslab - 1) / nslab;
@@ -574,6 +648,13 @@ int hb_dwconv_bwd_data_bf16(const void* dy, const float* w, void* dx, int N, int
       const long long quads = (long long)N * H * ((W + 3) / 4);
       const dim3 qgrid = dw_quad_grid(quads, C / 8, cg_t, rows_t, 2);
       dw3x3_quad_kernel<1, true><<<qgrid, kThreads, 0, st>>>(dyb, w, nullptr, dxb, N, p.Ho, p.Wo, H, W, C, 2 - pad, cg_t, rows_t);
+      HB_LAUNCH_CHECK();
+      return 0;
+    }
+    if (quad_on && stride == 2 && pad == 1 && W >= 4) {
+      const long long quads = (long long)N * H * ((W + 3) / 4);
+      const dim3 qgrid = dw_quad_grid(quads, C / 8, cg_t, rows_t, 2);
+      dw3x3_dgrad_s2_quad_kernel<<<qgrid, kThreads, 0, st>>>(dyb, w, dxb, N, H, W, p.Ho, p.Wo, C, cg_t, rows_t);
       HB_LAUNCH_CHECK();
       return 0;
     }
