@@ -152,3 +152,35 @@ def test_global_avg_pool():
     assert rel_l2(y, ref) < 4e-3
     y.float().sum().backward()
     assert torch.allclose(xd.grad.float().cpu(), torch.full_like(x.float(), 1 / 49), rtol=1e-2)
+
+
+@pytest.mark.parametrize("stride,cout,bias", [(2, 32, False), (1, 32, True), (2, 64, False)])
+def test_stem_convolution_im2col_path_vs_torch_and_generic_path(stride, cout, bias, monkeypatch):
+    """3-channel 3x3 / pad-1 stems (ReXNet, Darknet, YOLOv4, UNet3+) run as one im2col pass + a dense 1x1 GEMM: output, weight and
+    bias gradients against torch's fp32 convolution on the bf16-rounded operands, and against the implicit-GEMM path."""
+    from holocron_b200.nn import _fused as K
+    torch.manual_seed(0)
+    x = torch.randn(4, 3, 33, 29, device="cuda")
+    w = (torch.randn(cout, 3, 3, 3, device="cuda") / 27 ** 0.5).requires_grad_(True)
+    b = torch.randn(cout, device="cuda").requires_grad_(True) if bias else None
+    up = torch.randn(4, cout, (33 + 2 - 3) // stride + 1, (29 + 2 - 3) // stride + 1, device="cuda")
+
+    def run():
+        for t in (w, b):
+            if t is not None:
+                t.grad = None
+        y = K.conv2d(x, w, b, stride, 1)
+        (y.float() * up).sum().backward()
+        return y.detach().float(), w.grad.clone(), None if b is None else b.grad.clone()
+
+    y1, gw1, gb1 = run()
+    monkeypatch.setenv("HB_DISABLE_STEM_IM2COL", "1")
+    y0, gw0, gb0 = run()
+    xr, wr = x.bfloat16().float(), w.detach().bfloat16().float().requires_grad_(True)
+    br = None if b is None else b.detach().clone().requires_grad_(True)
+    ref = TF.conv2d(xr, wr, br, stride, 1)
+    (ref * up.bfloat16().float()).sum().backward()
+    assert rel_l2(y1, ref) < 4e-3 and rel_l2(y0, ref) < 4e-3
+    assert rel_l2(gw1, wr.grad) < 4e-3 and rel_l2(gw0, wr.grad) < 4e-3
+    if bias:
+        assert rel_l2(gb1, br.grad) < 4e-3
