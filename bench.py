@@ -154,6 +154,9 @@ def synthetic_batch(batch: int, seed: int, device, size: int = 224):
 
 
 # ------------------------------------------------------------------------------------------------ workloads
+CLS_KEYS = ("repvgg_a0", "rexnet1_0x", "repvgg_a1", "resnet50", "resnet18")   # classification workloads: (images, labels) + CE
+
+
 class Workload:
     """One BASELINE.json configuration: model factory, synthetic batch and loss."""
 
@@ -172,6 +175,11 @@ class Workload:
             "yolov4": ("yolov4", {"num_classes": 80}, 16, 512, True,
                        "yolov4 (CSP-Darknet53) 512x512 detection train step (BASELINE configs[3]): fwd + CIoU/objectness/class "
                        "losses (sync-free per-box formulation) + bwd + AdaBelief; synthetic COCO-like boxes (1-19 per image)"),
+            # SURVEY §8 f3 (widening, not a BASELINE.json configuration): the ResNet family on the same fused units
+            "resnet50": ("resnet50", {"num_classes": NUM_CLASSES}, 256, 224, True,
+                         "resnet50 224x224 bf16 train step (SURVEY 8-f3): fwd + CE(label_smoothing=0.1) + bwd + AdaBelief"),
+            "resnet18": ("resnet18", {"num_classes": NUM_CLASSES}, 256, 224, True,
+                         "resnet18 224x224 bf16 train step (SURVEY 8-f3): fwd + CE(label_smoothing=0.1) + bwd + AdaBelief"),
             "unet3p": ("unet3p", {"num_classes": 21}, 16, 256, True,
                        "unet3p 256x256 segmentation train step (BASELINE configs[4]): fwd + DiceLoss(softmax, one-hot) + bwd + "
                        "AdaBelief; synthetic masks"),
@@ -187,7 +195,7 @@ class Workload:
     def host_batch(self, batch: int, seed: int):
         """Synthetic batch on the HOST (pinned); structure depends on the task."""
         g = torch.Generator(device="cpu").manual_seed(seed)
-        if self.key in ("repvgg_a0", "rexnet1_0x", "repvgg_a1"):
+        if self.key in CLS_KEYS:
             x, t = synthetic_batch(batch, seed, "cpu", self.size)
             return [x.pin_memory(), t.pin_memory()]
         x = torch.rand(batch, 3, self.size, self.size, generator=g)
@@ -205,7 +213,7 @@ class Workload:
         return [x.pin_memory(), boxes.pin_memory(), labels.pin_memory()]
 
     def loss(self, model, hbF, *batch):
-        if self.key in ("repvgg_a0", "rexnet1_0x", "repvgg_a1"):
+        if self.key in CLS_KEYS:
             x, t = batch
             return F.cross_entropy(model(x), t, label_smoothing=0.1)
         if self.key == "unet3p":
@@ -420,7 +428,8 @@ def roofline_leg(K, run_step, opt_step, n_params: int, step_ms: float, images: i
     return roof
 
 
-TRAIN_MACS = {"repvgg_a0": 2.821e9, "repvgg_a1": 4.329e9, "rexnet1_0x": 0.398e9, "yolov4": 45.52e9, "unet3p": 195.49e9}
+TRAIN_MACS = {"repvgg_a0": 2.821e9, "repvgg_a1": 4.329e9, "rexnet1_0x": 0.398e9, "yolov4": 45.52e9, "unet3p": 195.49e9,
+              "resnet50": 4.09e9, "resnet18": 1.81e9}
 
 
 # ------------------------------------------------------------------------------------------------ main arm
@@ -585,7 +594,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the configuration's own)")
     ap.add_argument("--model", "--workload", dest="model", default="repvgg_a0",
-                    choices=["repvgg_a0", "rexnet1_0x", "repvgg_a1", "yolov4", "unet3p"],
+                    choices=["repvgg_a0", "rexnet1_0x", "repvgg_a1", "yolov4", "unet3p", "resnet50", "resnet18"],
                     help="repvgg_a0 = the contract metric (default); the others are BASELINE.json configs[1..4]")
     ap.add_argument("--config", type=int, default=0, help="BASELINE.json configs index 1..4 (alias of --model)")
     ap.add_argument("--micro", action="store_true", help="leaf-kernel micro rows (GB/s vs the measured HBM peak) instead of a model")

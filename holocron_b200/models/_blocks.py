@@ -11,6 +11,7 @@ instead of 3-4 separate library kernels. Anything it does not recognise is simpl
 from typing import List, Optional, Sequence
 
 import torch
+import torch.nn.functional as TF
 from torch import Tensor, nn
 
 from ..nn import _fused as K
@@ -50,7 +51,15 @@ def conv_bn_act(x: Tensor, conv: nn.Conv2d, bn: Optional[nn.BatchNorm2d], act: O
         from ..nn._dwconv import dwconv2d
         y = dwconv2d(x, conv.weight, conv.bias, conv.stride[0], conv.padding[0])
     else:
-        y = conv(x)  # grouped / asymmetric convolutions are outside the hot path: library call
+        # grouped (ResNeXt) / asymmetric / dilated convolutions are outside the hot path: library call on the activation's
+        # dtype (the fused units hand over bf16 channels_last tensors, the parameters stay fp32 masters)
+        xs = x if x.shape[1] == conv.in_channels else x[:, :conv.in_channels]
+        w = conv.weight if conv.weight.dtype == xs.dtype else conv.weight.to(xs.dtype)
+        b = conv.bias if conv.bias is None or conv.bias.dtype == xs.dtype else conv.bias.to(xs.dtype)
+        if conv.padding_mode != "zeros":
+            y = conv(xs.to(conv.weight.dtype))
+        else:
+            y = TF.conv2d(xs, w, b, conv.stride, conv.padding, conv.dilation, conv.groups)
     code, slope = K.act_code(act)
     if bn is not None:
         out = K.bn_act([y], [bn], code, slope, residual=residual, res_after_act=res_after_act)

@@ -331,7 +331,7 @@ if __name__ == "__main__" and "--optim2" in sys.argv:
     print("optim2.pt", (OUT / "optim2.pt").stat().st_size)
 
 
-if __name__ == "__main__" and not any(f in sys.argv for f in ("--zoo", "--api", "--trainer", "--optim2")):
+if __name__ == "__main__" and not any(f in sys.argv for f in ("--zoo", "--zoo-resnet", "--api", "--trainer", "--optim2")):
     gen_activations()
     gen_losses()
     gen_boxes()
@@ -434,6 +434,39 @@ def gen_zoo():
     torch.save(d, OUT / "zoo.pt")
 
 
+def gen_zoo_resnet():
+    """ResNet-family fixtures, same recipe as gen_zoo's classification part -> tests/golden/zoo_resnet.pt."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    import _conditioning as C
+    d = {}
+    for name in C.CLS_RESNET:
+        out = {}
+        for mode in ("eval", "train"):
+            torch.manual_seed(0)
+            m = C.condition(getattr(holocron.models, name)(num_classes=10))
+            m = C.freeze_bn(m) if mode == "eval" else m.train()
+            x, t = C.cls_inputs(name, mode)
+            store = {}
+            C.capture(m, C.PROBE[name], store)
+            logits = m(x)
+            loss = torch.nn.functional.cross_entropy(logits, t)
+            loss.backward()
+            names = [n for n, _ in m.named_parameters()]
+            bns = [n for n, mod in m.named_modules() if isinstance(mod, torch.nn.BatchNorm2d)]
+            first, mid, last = names[0], bns[len(bns) // 2] + ".weight", names[-2]
+            ps = dict(m.named_parameters())
+            out[mode] = dict(logits=logits.detach(), loss=loss.detach(), first=first, mid=mid, last=last,
+                             grads={n: ps[n].grad.clone() for n in (first, mid, last)},
+                             probe=store["probe"][:2].half() if mode == "train" else None)
+        d[name] = out
+    torch.save(d, OUT / "zoo_resnet.pt")
+
+
+if __name__ == "__main__" and "--zoo-resnet" in sys.argv:
+    gen_zoo_resnet()
+    print("zoo_resnet.pt", (OUT / "zoo_resnet.pt").stat().st_size)
+
+
 if __name__ == "__main__" and "--zoo" in sys.argv:
     gen_zoo()
     print("zoo.pt", (OUT / "zoo.pt").stat().st_size)
@@ -448,7 +481,8 @@ API_SURFACE = {
     "optim": ["AdaBelief", "LAMB", "TAdam", "AdamP", "Adan", "AdEMAMix", "LARS", "RaLars"],
     "optim.wrapper": ["Lookahead"],
     "models": ["repvgg_a0", "repvgg_a1", "repvgg_a2", "repvgg_b0", "repvgg_b1", "repvgg_b2", "repvgg_b3", "rexnet1_0x", "rexnet1_3x",
-               "rexnet1_5x", "rexnet2_0x", "rexnet2_2x", "darknet24", "darknet19", "darknet53", "cspdarknet53", "cspdarknet53_mish"],
+               "rexnet1_5x", "rexnet2_0x", "rexnet2_2x", "darknet24", "darknet19", "darknet53", "cspdarknet53", "cspdarknet53_mish",
+               "resnet18", "resnet34", "resnet50", "resnet50d", "resnet101", "resnet152", "resnext50_32x4d", "resnext101_32x8d"],
     "models.detection": ["yolov4"],
     "models.segmentation": ["unet3p"],
 }

@@ -29,7 +29,8 @@ from conftest import load_golden
 
 pytestmark = pytest.mark.gpu
 
-ZOO = load_golden("zoo")
+ZOO = {**load_golden("zoo"), **load_golden("zoo_resnet")}   # zoo_resnet: SURVEY §8 f3, the ResNet family
+CLS_ALL = list(C.CLS) + list(C.CLS_RESNET)
 
 
 def rel_l2(a, b):
@@ -74,7 +75,7 @@ def check_grads(m, g, twin):
     return errs
 
 
-@pytest.mark.parametrize("name", list(C.CLS))
+@pytest.mark.parametrize("name", CLS_ALL)
 def test_classification_frozen_bn_full_depth(name):
     g = ZOO[name]["eval"]
     m = C.freeze_bn(build(getattr(hb.models, name), num_classes=10))
@@ -105,7 +106,7 @@ def test_classification_frozen_bn_full_depth(name):
     assert torch.equal(out.argmax(1).cpu()[clear], g["logits"].argmax(1)[clear])
 
 
-@pytest.mark.parametrize("name", list(C.CLS))
+@pytest.mark.parametrize("name", CLS_ALL)
 def test_classification_batch_statistics(name):
     g = ZOO[name]["train"]
     m = build(getattr(hb.models, name), num_classes=10).train()
