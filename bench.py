@@ -154,7 +154,7 @@ def synthetic_batch(batch: int, seed: int, device, size: int = 224):
 
 
 # ------------------------------------------------------------------------------------------------ workloads
-CLS_KEYS = ("repvgg_a0", "rexnet1_0x", "repvgg_a1", "resnet50", "resnet18")   # classification workloads: (images, labels) + CE
+CLS_KEYS = ("repvgg_a0", "rexnet1_0x", "repvgg_a1", "resnet50", "resnet18", "mobileone_s0")   # classification workloads: (images, labels) + CE
 
 
 class Workload:
@@ -178,6 +178,9 @@ class Workload:
             # SURVEY §8 f3 (widening, not a BASELINE.json configuration): the ResNet family on the same fused units
             "resnet50": ("resnet50", {"num_classes": NUM_CLASSES}, 256, 224, True,
                          "resnet50 224x224 bf16 train step (SURVEY 8-f3): fwd + CE(label_smoothing=0.1) + bwd + AdaBelief"),
+            "mobileone_s0": ("mobileone_s0", {"num_classes": NUM_CLASSES}, 256, 224, True,
+                             "mobileone_s0 (train form, over-parametrisation 4) 224x224 bf16 train step (SURVEY 8-f3): fwd + "
+                             "CE(label_smoothing=0.1) + bwd + AdaBelief"),
             "resnet18": ("resnet18", {"num_classes": NUM_CLASSES}, 256, 224, True,
                          "resnet18 224x224 bf16 train step (SURVEY 8-f3): fwd + CE(label_smoothing=0.1) + bwd + AdaBelief"),
             "unet3p": ("unet3p", {"num_classes": 21}, 16, 256, True,
@@ -429,7 +432,7 @@ def roofline_leg(K, run_step, opt_step, n_params: int, step_ms: float, images: i
 
 
 TRAIN_MACS = {"repvgg_a0": 2.821e9, "repvgg_a1": 4.329e9, "rexnet1_0x": 0.398e9, "yolov4": 45.52e9, "unet3p": 195.49e9,
-              "resnet50": 4.09e9, "resnet18": 1.81e9}
+              "resnet50": 4.09e9, "resnet18": 1.81e9, "mobileone_s0": 1.07e9}
 
 
 # ------------------------------------------------------------------------------------------------ main arm
@@ -594,7 +597,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the configuration's own)")
     ap.add_argument("--model", "--workload", dest="model", default="repvgg_a0",
-                    choices=["repvgg_a0", "rexnet1_0x", "repvgg_a1", "yolov4", "unet3p", "resnet50", "resnet18"],
+                    choices=["repvgg_a0", "rexnet1_0x", "repvgg_a1", "yolov4", "unet3p", "resnet50", "resnet18", "mobileone_s0"],
                     help="repvgg_a0 = the contract metric (default); the others are BASELINE.json configs[1..4]")
     ap.add_argument("--config", type=int, default=0, help="BASELINE.json configs index 1..4 (alias of --model)")
     ap.add_argument("--micro", action="store_true", help="leaf-kernel micro rows (GB/s vs the measured HBM peak) instead of a model")

@@ -43,7 +43,8 @@ CLS = {
 
 # the ResNet family - basic blocks, bottlenecks with projection shortcuts, the ResNet-D stem and
 # average-pooled shortcuts, ResNeXt's grouped 3x3 units. Separate fixture file (tests/golden/zoo_resnet.pt).
-CLS_RESNET = {"resnet18": (4, 8, 64), "resnet50d": (4, 8, 64), "resnext50_32x4d": (4, 8, 64)}
+CLS_RESNET = {"resnet18": (4, 8, 64), "resnet50d": (4, 8, 64), "resnext50_32x4d": (4, 8, 64),
+              "mobileone_s0": (4, 8, 64)}     # MobileOne: re-parametrisable depth-wise / point-wise branch sums (up to 6 branches)
 
 
 def cls_inputs(name: str, mode: str):
@@ -99,7 +100,7 @@ PROBE = {
     "darknet24": "features.layers.0", "darknet19": "features.layers.0", "darknet53": "features.layers.0",
     "cspdarknet53": "features.stages.0", "cspdarknet53_mish": "features.stages.0", "rexnet1_0x": "features.4",
     "repvgg_a0": "features.1", "unet3p": "encoder.1", "yolov4": "backbone.stages.0",
-    "resnet18": "features.4", "resnet50d": "features.10.0", "resnext50_32x4d": "features.4.0",
+    "resnet18": "features.4", "resnet50d": "features.10.0", "resnext50_32x4d": "features.4.0", "mobileone_s0": "features.1.0",
 }
 
 

@@ -85,7 +85,7 @@ def test_state_dict_layout_and_seeded_init_match_reference():
     parameter / buffer values produced under torch.manual_seed(0), against hashes recorded from the reference."""
     import torch
     ref = json.loads((GOLDEN / "state_dicts.json").read_text())
-    assert len(ref) == 27     # 17 + 8 (ResNet family) classification factories, yolov4, unet3p
+    assert len(ref) == 31     # 17 + 8 (ResNet family) + 4 (MobileOne) classification factories, yolov4, unet3p
     for name, want in ref.items():
         torch.manual_seed(0)
         if name == "yolov4":

@@ -132,6 +132,25 @@ def test_classification_batch_statistics(name):
         assert m(x.cuda()).shape == g["logits"].shape
 
 
+def test_mobileone_inference_form_on_gpu():
+    """MobileOne-S0 in eval mode before and after ``reparametrize()`` (reference mobileone.py:222-230): both forms against the
+    reference's fp32 logits (<= 2e-2), the folded filters bit-identical to the host-side fp32 fold of the reference."""
+    g = ZOO["mobileone_s0"]["reparam"]
+    m = build(hb.models.mobileone_s0, num_classes=10).eval()
+    x, _ = C.cls_inputs("mobileone_s0", "eval")
+    with torch.no_grad():
+        before = m(x.cuda())
+        m.reparametrize()
+        after = m(x.cuda())
+    assert list(m.state_dict().keys())[:6] == g["keys"]
+    e0, e1 = rel_l2(before, g["before"]), rel_l2(after, g["after"])
+    print(f"\n[zoo reparam] mobileone_s0: train-form {e0:.4f} re-parametrised {e1:.4f}")
+    assert e0 < 2e-2 and e1 < 2e-2
+    top2 = g["after"].topk(2, 1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 0.05 * g["after"].abs().max()
+    assert torch.equal(after.argmax(1).cpu()[clear], g["after"].argmax(1)[clear])
+
+
 @pytest.mark.parametrize("mode", ["eval", "train"])
 def test_unet3p_with_dice_loss(mode):
     g = ZOO["unet3p"][mode]
