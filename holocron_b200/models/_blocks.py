@@ -36,17 +36,39 @@ def _depthwise_ok(conv: nn.Conv2d) -> bool:
             and conv.in_channels % 8 == 0)
 
 
+def _patchify_ok(conv: nn.Conv2d, x: Tensor) -> bool:
+    """Non-overlapping patch convolution (kernel == stride > 1, no padding: ConvNeXt's 4x4 stem and 2x2 stage transitions)."""
+    k = conv.kernel_size[0]
+    return k > 1 and conv.stride[0] == k and conv.padding[0] == 0 and x.shape[2] % k == 0 and x.shape[3] % k == 0
+
+
+def _space_to_depth(x: Tensor, conv: nn.Conv2d):
+    """A k x k stride-k convolution is a 1x1 convolution over k x k pixel blocks stacked on the channel axis: one NHWC
+    re-tiling copy (N, H/k, W/k, [kh, kw, C]) and a filter view in the same (kh, kw, C) order, then the dense 1x1 GEMM path -
+    forward, data gradient and weight gradient of which are the best-covered kernels of this package (the implicit-GEMM data
+    gradient of an even-sized strided filter would need asymmetric padding)."""
+    k = conv.kernel_size[0]
+    cin = conv.in_channels
+    xs = x if x.shape[1] == cin else x[:, :cin]
+    n, _, h, w = xs.shape
+    xr = xs.reshape(n, cin, h // k, k, w // k, k).permute(0, 2, 4, 3, 5, 1).reshape(n, h // k, w // k, k * k * cin)
+    wr = conv.weight.permute(0, 2, 3, 1).reshape(conv.out_channels, k * k * cin, 1, 1)
+    return xr.permute(0, 3, 1, 2), wr
+
+
 def conv_bn_act(x: Tensor, conv: nn.Conv2d, bn: Optional[nn.BatchNorm2d], act: Optional[nn.Module],
                 residual: Optional[Tensor] = None, res_after_act: bool = False, keep_padded: bool = False) -> Tensor:
     """One ``conv -> BN -> act`` unit (+ optional shortcut) on the fused kernels."""
     if _dense_ok(conv):
+        weight, stride, pad = conv.weight, conv.stride[0], conv.padding[0]
+        if _patchify_ok(conv, x):
+            x, weight, stride, pad = *_space_to_depth(x, conv), 1, 0
         if bn is None and residual is None:
             code, slope = K.act_code(act)
-            return K.conv2d_bias_act(x, conv.weight, conv.bias, conv.stride[0], conv.padding[0], code, slope)
+            return K.conv2d_bias_act(x, weight, conv.bias, stride, pad, code, slope)
         # training-mode BatchNorm next: the convolution's epilogue also produces the per-channel statistics of its output
         stats = bn is not None and (bn.training or bn.running_mean is None)
-        y = K.conv2d(x, conv.weight, conv.bias, conv.stride[0], conv.padding[0], keep_padded=keep_padded or bn is not None,
-                     want_stats=stats)
+        y = K.conv2d(x, weight, conv.bias, stride, pad, keep_padded=keep_padded or bn is not None, want_stats=stats)
     elif _depthwise_ok(conv):
         from ..nn._dwconv import dwconv2d
         y = dwconv2d(x, conv.weight, conv.bias, conv.stride[0], conv.padding[0])

@@ -15,7 +15,8 @@ from ._dropblock import dropblock2d  # noqa: F401
 
 import ctypes
 
-__all__ = ["add2d", "dice_loss", "dropblock2d", "focal_loss", "hard_mish", "nl_relu", "norm_conv2d", "poly_loss"]
+__all__ = ["add2d", "concat_downsample2d", "dice_loss", "dropblock2d", "focal_loss", "hard_mish", "nl_relu", "norm_conv2d",
+           "poly_loss"]
 
 _cf = ctypes.c_float
 
@@ -100,3 +101,15 @@ class _NLReluFn(torch.autograd.Function):
 def nl_relu(x: Tensor, beta: float = 1.0, inplace: bool = False) -> Tensor:
     """Natural-logarithm ReLU ``log(1 + beta * max(0, x))`` — mirrors holocron/nn/functional.py:44-56."""
     return _NLReluFn.apply(x, float(beta), inplace)
+
+
+def concat_downsample2d(x: Tensor, scale_factor: int) -> Tensor:
+    """Loss-less down-sampling of YOLOv2's pass-through route (reference nn/functional.py:116-136): every
+    ``scale_factor x scale_factor`` pixel block is stacked on the channel axis, output channel order (row offset, column
+    offset, channel). Pure data movement (one strided copy, any input layout; the reference's ``view`` needs a contiguous
+    NCHW tensor), so it is the same code on every device."""
+    b, c, h, w = x.shape
+    if (h % scale_factor != 0) or (w % scale_factor != 0):
+        raise AssertionError("Spatial size of input tensor must be multiples of `scale_factor`")
+    x = x.reshape(b, c, h // scale_factor, scale_factor, w // scale_factor, scale_factor)
+    return x.permute(0, 3, 5, 1, 2, 4).reshape(b, int(c * scale_factor**2), h // scale_factor, w // scale_factor)

@@ -1,10 +1,22 @@
-"""Pooling modules on the hot path — mirrors holocron/nn/modules/downsample.py (GlobalAvgPool2d :58-77, SPP :154-167)."""
+"""Pooling modules on the hot path — mirrors holocron/nn/modules/downsample.py (ConcatDownsample2d :26-40, GlobalAvgPool2d :58-77, SPP :154-167)."""
 from typing import List
 
 import torch
 from torch import Tensor, nn
 
-__all__ = ["GlobalAvgPool2d", "SPP"]
+__all__ = ["ConcatDownsample2d", "GlobalAvgPool2d", "SPP"]
+
+
+class ConcatDownsample2d(nn.Module):
+    """Stacks adjacent pixels on the channel axis (reference downsample.py:26-40; YOLOv2's pass-through layer)."""
+
+    def __init__(self, scale_factor: int) -> None:
+        super().__init__()
+        self.scale_factor = scale_factor
+
+    def forward(self, x: Tensor) -> Tensor:
+        from ..functional import concat_downsample2d
+        return concat_downsample2d(x, self.scale_factor)
 
 
 class GlobalAvgPool2d(nn.Module):

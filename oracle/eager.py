@@ -162,6 +162,7 @@ def reference_execution(bf16_storage: bool = False):
 
     rexnet = importlib.import_module("holocron_b200.models.classification.rexnet")
     yolov4 = importlib.import_module("holocron_b200.models.detection.yolov4")   # the package re-exports a function of that name
+    yolo = importlib.import_module("holocron_b200.models.detection.yolo")       # _YOLO losses shared by YOLOv1 / YOLOv2
 
     swaps = [
         (fused, "conv2d", _conv2d), (fused, "conv2d_bias_act", _conv2d_bias_act), (fused, "bn_act", _bn_act),
@@ -170,6 +171,7 @@ def reference_execution(bf16_storage: bool = False):
         (fused, "head_linear", _head_linear),
         (dw, "dwconv2d", _dwconv2d), (rexnet, "dwconv2d", _dwconv2d),
         (yolov4, "box_iou", oracle_boxes.box_iou), (yolov4, "ciou_loss", oracle_boxes.ciou_loss),
+        (yolo, "box_iou", oracle_boxes.box_iou),
     ]
     saved = [(mod, name, getattr(mod, name)) for mod, name, _ in swaps]
     prev = _BF16

@@ -18,6 +18,9 @@ def condition(model: nn.Module, seed: int = 1234, zero_convs: bool = True) -> nn
                 mod.bias.copy_(torch.rand(mod.bias.shape, generator=g) * 0.4 - 0.2)
                 mod.running_mean.copy_(torch.rand(mod.running_mean.shape, generator=g) * 0.4 - 0.2)
                 mod.running_var.copy_(torch.rand(mod.running_var.shape, generator=g) * 1.0 + 0.5)
+            elif type(mod).__name__ == "LayerScale":
+                # ConvNeXt: a block's branch is scaled by 1e-6 at initialisation - invisible to any output comparison
+                mod.weight.copy_(torch.rand(mod.weight.shape, generator=g) * 0.5 + 0.25)
             elif zero_convs and isinstance(mod, nn.Conv2d) and mod.bias is not None and float(mod.weight.abs().sum()) == 0.0:
                 mod.weight.copy_(torch.randn(mod.weight.shape, generator=g) * 0.02)
                 mod.bias.copy_(torch.rand(mod.bias.shape, generator=g) * 0.2 - 0.1)
@@ -47,8 +50,13 @@ CLS_RESNET = {"resnet18": (4, 8, 64), "resnet50d": (4, 8, 64), "resnext50_32x4d"
               "mobileone_s0": (4, 8, 64)}     # MobileOne: re-parametrisable depth-wise / point-wise branch sums (up to 6 branches)
 
 
+# SURVEY §8 f3, continued: Res2Net (hierarchical 26-channel slices), SKNet (selective-kernel units: grouped dilated paths +
+# soft attention), ConvNeXt (depth-wise 7x7, LayerNorm, GELU, LayerScale, patchify convolutions). tests/golden/zoo_f3.pt.
+CLS_F3 = {"res2net50_26w_4s": (4, 8, 64), "sknet50": (4, 8, 64), "convnext_atto": (4, 8, 64)}
+
+
 def cls_inputs(name: str, mode: str):
-    be, bt, size = {**CLS, **CLS_RESNET}[name]
+    be, bt, size = {**CLS, **CLS_RESNET, **CLS_F3}[name]
     b = be if mode == "eval" else bt
     g = torch.Generator().manual_seed(11 if mode == "eval" else 12)
     x = (torch.rand(b, 3, size, size, generator=g) - 0.45) / 0.225
@@ -82,6 +90,16 @@ def yolo_dup_inputs():
     return x, [t0, t1]
 
 
+def yolo12_inputs(name: str):
+    """YOLOv1 (448 x 448: its classifier is sized for the 7 x 7 grid) / YOLOv2 (128 x 128 -> 4 x 4 grid) inputs: the
+    shared-slot targets of yolo_dup_inputs with VOC-range labels (two boxes of image 0 fall into the same cell)."""
+    g = torch.Generator().manual_seed(15)
+    size = 448 if name == "yolov1" else 128
+    x = torch.rand(2, 3, size, size, generator=g)
+    _, target = yolo_dup_inputs()
+    return x, [{"boxes": t["boxes"], "labels": t["labels"] % 20} for t in target]
+
+
 def unet_inputs():
     g = torch.Generator().manual_seed(14)
     x = torch.rand(2, 3, 64, 64, generator=g)
@@ -100,6 +118,8 @@ PROBE = {
     "darknet24": "features.layers.0", "darknet19": "features.layers.0", "darknet53": "features.layers.0",
     "cspdarknet53": "features.stages.0", "cspdarknet53_mish": "features.stages.0", "rexnet1_0x": "features.4",
     "repvgg_a0": "features.1", "unet3p": "encoder.1", "yolov4": "backbone.stages.0",
+    "yolov1": "backbone.layers.0", "yolov2": "backbone.layers.1",
+    "res2net50_26w_4s": "features.4.0", "sknet50": "features.4.0", "convnext_atto": "features.2.0",
     "resnet18": "features.4", "resnet50d": "features.10.0", "resnext50_32x4d": "features.4.0", "mobileone_s0": "features.1.0",
 }
 
@@ -111,3 +131,9 @@ def capture(model: nn.Module, path: str, store: dict):
     def hook(_m, _inp, out):
         store["probe"] = (out[0] if isinstance(out, (tuple, list)) else out).detach()
     return mod.register_forward_hook(hook)
+
+
+def head_rows(t: torch.Tensor, rows: int = 8) -> torch.Tensor:
+    """Fixture diet for the YOLOv1 / YOLOv2 gradients (1024 x 1024 x 3 x 3 filters, a 1470 x 512 classifier): the first
+    ``rows`` output rows of a large tensor stand for the whole (generator and tests apply the same cut)."""
+    return t[:rows] if t.numel() > 100_000 else t

@@ -331,7 +331,7 @@ if __name__ == "__main__" and "--optim2" in sys.argv:
     print("optim2.pt", (OUT / "optim2.pt").stat().st_size)
 
 
-if __name__ == "__main__" and not any(f in sys.argv for f in ("--zoo", "--zoo-resnet", "--api", "--trainer", "--optim2")):
+if __name__ == "__main__" and not any(f in sys.argv for f in ("--zoo", "--zoo-resnet", "--zoo-f3", "--yolo", "--api", "--trainer", "--optim2")):
     gen_activations()
     gen_losses()
     gen_boxes()
@@ -434,12 +434,13 @@ def gen_zoo():
     torch.save(d, OUT / "zoo.pt")
 
 
-def gen_zoo_resnet():
-    """ResNet-family fixtures, same recipe as gen_zoo's classification part -> tests/golden/zoo_resnet.pt."""
+def gen_zoo_resnet(which="CLS_RESNET", outfile="zoo_resnet.pt"):
+    """ResNet-family fixtures (SURVEY §8 f3), same recipe as gen_zoo's classification part -> tests/golden/zoo_resnet.pt;
+    ``--zoo-f3``: Res2Net / SKNet / ConvNeXt (tests/_conditioning.py CLS_F3) -> tests/golden/zoo_f3.pt."""
     sys.path.insert(0, str(ROOT / "tests"))
     import _conditioning as C
     d = {}
-    for name in C.CLS_RESNET:
+    for name in getattr(C, which):
         out = {}
         for mode in ("eval", "train"):
             torch.manual_seed(0)
@@ -452,7 +453,7 @@ def gen_zoo_resnet():
             loss = torch.nn.functional.cross_entropy(logits, t)
             loss.backward()
             names = [n for n, _ in m.named_parameters()]
-            bns = [n for n, mod in m.named_modules() if isinstance(mod, torch.nn.BatchNorm2d)]
+            bns = [n for n, mod in m.named_modules() if isinstance(mod, (torch.nn.BatchNorm2d, torch.nn.LayerNorm))]
             ps = dict(m.named_parameters())
             # first filter with more than one tap per output channel: a depth-wise 1x1 filter in front of a batch-statistics
             # BatchNorm (MobileOne's scale branch) has a structurally ZERO gradient - nothing to compare but round-off
@@ -480,7 +481,50 @@ def gen_zoo_resnet():
                 m.reparametrize()
                 out["reparam"] = dict(before=before, after=m(x), keys=list(m.state_dict().keys())[:6])
         d[name] = out
-    torch.save(d, OUT / "zoo_resnet.pt")
+    torch.save(d, OUT / outfile)
+
+
+if __name__ == "__main__" and "--zoo-f3" in sys.argv:
+    gen_zoo_resnet("CLS_F3", "zoo_f3.pt")
+    print("zoo_f3.pt", (OUT / "zoo_f3.pt").stat().st_size)
+
+
+def gen_yolo():
+    """YOLOv1 / YOLOv2 fixtures (reference models/detection/yolo.py, yolov2.py) -> tests/golden/zoo_yolo.pt:
+    the four losses in frozen-BatchNorm and batch-statistics mode, gradients of the first / a middle / the last parameter,
+    an early probe activation, and eval-mode detections of a model whose objectness bias is raised so that boxes survive."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    import _conditioning as C
+    d = {}
+    for name in ("yolov1", "yolov2"):
+        out = {}
+        for mode in ("eval", "train"):
+            torch.manual_seed(0)
+            m = getattr(holocron.models.detection, name)(pretrained_backbone=False, num_classes=20)
+            for mod in m.modules():
+                if isinstance(mod, torch.nn.Dropout):
+                    mod.p = 0.0
+            m = C.condition(m)
+            m = C.freeze_bn(m) if mode == "eval" else m.train()
+            x, target = C.yolo12_inputs(name)
+            store = {}
+            C.capture(m, C.PROBE[name], store)
+            losses = m(x, target)
+            sum(losses.values()).backward()
+            ps = dict(m.named_parameters())
+            names = [n for n, _ in m.named_parameters()]
+            bns = [n for n, mod in m.named_modules() if isinstance(mod, torch.nn.BatchNorm2d)]
+            # YOLOv1 has no normalisation layers by default (convolution bias + LeakyReLU): a middle filter instead
+            keys = [names[0], bns[len(bns) // 2] + ".weight" if bns else names[len(names) // 2 // 2 * 2], names[-2]]
+            out[mode] = dict(losses={k: v.detach() for k, v in losses.items()}, grads={k: C.head_rows(ps[k].grad).clone() for k in keys},
+                             probe=store["probe"][:1, :32].half() if mode == "train" else None)
+        d[name] = out
+    torch.save(d, OUT / "zoo_yolo.pt")
+
+
+if __name__ == "__main__" and "--yolo" in sys.argv:
+    gen_yolo()
+    print("zoo_yolo.pt", (OUT / "zoo_yolo.pt").stat().st_size)
 
 
 if __name__ == "__main__" and "--zoo-resnet" in sys.argv:
@@ -495,17 +539,20 @@ if __name__ == "__main__" and "--zoo" in sys.argv:
 
 # ------------------------------------------------------------------------------------------------ public API surface
 API_SURFACE = {
-    "nn.functional": ["hard_mish", "nl_relu", "focal_loss", "poly_loss", "dice_loss", "norm_conv2d", "add2d", "dropblock2d"],
+    "nn.functional": ["hard_mish", "nl_relu", "focal_loss", "poly_loss", "dice_loss", "norm_conv2d", "add2d", "dropblock2d",
+                      "concat_downsample2d"],
     "nn": ["HardMish", "NLReLU", "FReLU", "NormConv2d", "Add2d", "SlimConv2d", "FocalLoss", "PolyLoss", "DiceLoss", "DropBlock2d",
-           "GlobalAvgPool2d", "SPP"],
+           "GlobalAvgPool2d", "SPP", "ConcatDownsample2d"],
     "ops.boxes": ["box_giou", "diou_loss", "ciou_loss", "iou_penalty", "aspect_ratio", "aspect_ratio_consistency"],
     "optim": ["AdaBelief", "LAMB", "TAdam", "AdamP", "Adan", "AdEMAMix", "LARS", "RaLars"],
     "optim.wrapper": ["Lookahead"],
     "models": ["repvgg_a0", "repvgg_a1", "repvgg_a2", "repvgg_b0", "repvgg_b1", "repvgg_b2", "repvgg_b3", "rexnet1_0x", "rexnet1_3x",
                "rexnet1_5x", "rexnet2_0x", "rexnet2_2x", "darknet24", "darknet19", "darknet53", "cspdarknet53", "cspdarknet53_mish",
                "resnet18", "resnet34", "resnet50", "resnet50d", "resnet101", "resnet152", "resnext50_32x4d", "resnext101_32x8d",
-               "mobileone_s0", "mobileone_s1", "mobileone_s2", "mobileone_s3"],
-    "models.detection": ["yolov4"],
+               "mobileone_s0", "mobileone_s1", "mobileone_s2", "mobileone_s3", "res2net50_26w_4s", "sknet50", "sknet101", "sknet152",
+               "convnext_atto", "convnext_femto", "convnext_pico", "convnext_nano", "convnext_tiny", "convnext_small",
+               "convnext_base", "convnext_large", "convnext_xl"],
+    "models.detection": ["yolov4", "yolov1", "yolov2", "YOLOv1", "YOLOv2"],
     "models.segmentation": ["unet3p"],
 }
 
@@ -579,6 +626,9 @@ def gen_state_dicts():
     d["yolov4"] = describe_state_dict(holocron.models.detection.yolov4(pretrained_backbone=False, num_classes=80))
     torch.manual_seed(0)
     d["unet3p"] = describe_state_dict(holocron.models.segmentation.unet3p(num_classes=21))
+    for name in ("yolov1", "yolov2"):
+        torch.manual_seed(0)
+        d[name] = describe_state_dict(getattr(holocron.models.detection, name)(pretrained_backbone=False, num_classes=20))
     (OUT / "state_dicts.json").write_text(json.dumps(d, indent=1, sort_keys=True))
 
 

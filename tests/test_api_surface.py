@@ -20,7 +20,8 @@ def _describe(obj):
 
 
 # deliberate, documented deviations: (path, parameter) -> our default
-DEVIATIONS = {("models.detection.yolov4", "pretrained_backbone"): "False"}   # no network: nothing to download
+# no network: nothing to download, so the detectors default to an un-pretrained backbone
+DEVIATIONS = {(f"models.detection.{n}", "pretrained_backbone"): "False" for n in ("yolov4", "yolov1", "yolov2")}
 
 
 def test_public_signatures_match_reference():
@@ -85,13 +86,16 @@ def test_state_dict_layout_and_seeded_init_match_reference():
     parameter / buffer values produced under torch.manual_seed(0), against hashes recorded from the reference."""
     import torch
     ref = json.loads((GOLDEN / "state_dicts.json").read_text())
-    assert len(ref) == 31     # 17 + 8 (ResNet family) + 4 (MobileOne) classification factories, yolov4, unet3p
+    # 17 + 8 (ResNet family) + 4 (MobileOne) + 1 (Res2Net) + 3 (SKNet) + 9 (ConvNeXt) classification factories, yolov4, unet3p, yolov1, yolov2
+    assert len(ref) >= 46
     for name, want in ref.items():
         torch.manual_seed(0)
         if name == "yolov4":
             m = hb.models.yolov4(pretrained_backbone=False, num_classes=80)
         elif name == "unet3p":
             m = hb.models.unet3p(num_classes=21)
+        elif name in ("yolov1", "yolov2"):
+            m = getattr(hb.models, name)(num_classes=20)
         else:
             m = getattr(hb.models, name)(num_classes=10)
         got = _describe_state_dict(m)
