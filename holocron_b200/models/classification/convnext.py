@@ -22,7 +22,7 @@ from torchvision.ops.stochastic_depth import StochasticDepth
 
 from ...nn import GlobalAvgPool2d
 from .._blocks import FusedSequential
-from ..utils import conv_sequence
+from ..utils import _configure_model, _requested_checkpoint, conv_sequence
 from .resnet import _ResBlock
 
 __all__ = ["ConvNeXt", "LayerNorm2d", "LayerScale", "Bottlenext", "convnext_atto", "convnext_femto", "convnext_pico",
@@ -120,12 +120,9 @@ class ConvNeXt(nn.Sequential):
 
 
 def _convnext(pretrained: bool, checkpoint: Any, num_blocks: List[int], out_chans: List[int], **kwargs: Any) -> ConvNeXt:
-    if pretrained or checkpoint is not None:
-        raise NotImplementedError("pretrained checkpoints need network access; load a reference state_dict instead "
-                                  "(the module tree and parameter names are identical)")
+    checkpoint = _requested_checkpoint(pretrained, checkpoint)
     model = ConvNeXt(num_blocks, out_chans, **kwargs)
-    model.default_cfg = None
-    return model
+    return _configure_model(model, checkpoint)
 
 
 def convnext_atto(pretrained: bool = False, checkpoint: Any = None, progress: bool = True, **kwargs: Any) -> ConvNeXt:

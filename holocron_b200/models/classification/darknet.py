@@ -14,7 +14,7 @@ from ...nn import DropBlock2d, GlobalAvgPool2d
 from ...nn import _fused as K
 from ...nn.init import init_module
 from .._blocks import FusedSequential, run_fused
-from ..utils import conv_sequence
+from ..utils import _configure_model, _requested_checkpoint, conv_sequence
 
 __all__ = ["CSPStage", "DarknetBodyV1", "DarknetBodyV2", "DarknetBodyV3", "DarknetBodyV4", "DarknetV1", "DarknetV2",
            "DarknetV3", "DarknetV4", "ResBlock", "cspdarknet53", "cspdarknet53_mish", "darknet19", "darknet24",
@@ -293,38 +293,38 @@ class DarknetV2(nn.Sequential):
         return logits.float().mean((2, 3))
 
 
-def _no_pretrained(pretrained: bool, checkpoint: Any) -> None:
-    if pretrained or checkpoint is not None:
-        raise NotImplementedError("pretrained checkpoints need network access; load a reference state_dict instead")
+def _no_pretrained(pretrained: bool, checkpoint: Any):
+    """The factories' pretrained / checkpoint arguments -> the checkpoint to load (None: seeded initialisation)."""
+    return _requested_checkpoint(pretrained, checkpoint)
 
 
 def darknet24(pretrained: bool = False, progress: bool = True, **kwargs: Any) -> DarknetV1:
     """Darknet-24 / YOLOv1 backbone (reference darknet.py:143-159)."""
-    _no_pretrained(pretrained, None)
-    return DarknetV1([[192], [128, 256, 256, 512], [*([256, 512] * 4), 512, 1024], [512, 1024] * 2], **kwargs)
+    ckpt = _no_pretrained(pretrained, None)
+    return _configure_model(DarknetV1([[192], [128, 256, 256, 512], [*([256, 512] * 4), 512, 1024], [512, 1024] * 2], **kwargs), ckpt)
 
 
 def darknet19(pretrained: bool = False, checkpoint: Any = None, progress: bool = True, **kwargs: Any) -> DarknetV2:
     """Darknet-19 / YOLOv2 backbone (reference darknetv2.py:211-237)."""
-    _no_pretrained(pretrained, checkpoint)
-    return DarknetV2([(64, 0), (128, 1), (256, 1), (512, 2), (1024, 2)], **kwargs)
+    ckpt = _no_pretrained(pretrained, checkpoint)
+    return _configure_model(DarknetV2([(64, 0), (128, 1), (256, 1), (512, 2), (1024, 2)], **kwargs), ckpt)
 
 
 def darknet53(pretrained: bool = False, checkpoint: Any = None, progress: bool = True, **kwargs: Any) -> DarknetV3:
     """Darknet-53 (reference darknetv3.py:218-244)."""
-    _no_pretrained(pretrained, checkpoint)
-    return DarknetV3([(64, 1), (128, 2), (256, 8), (512, 8), (1024, 4)], **kwargs)
+    ckpt = _no_pretrained(pretrained, checkpoint)
+    return _configure_model(DarknetV3([(64, 1), (128, 2), (256, 8), (512, 8), (1024, 4)], **kwargs), ckpt)
 
 
 def cspdarknet53(pretrained: bool = False, checkpoint: Any = None, progress: bool = True, **kwargs: Any) -> DarknetV4:
     """CSP-Darknet-53 (reference darknetv4.py:249-275)."""
-    _no_pretrained(pretrained, checkpoint)
-    return DarknetV4([(64, 1), (128, 2), (256, 8), (512, 8), (1024, 4)], **kwargs)
+    ckpt = _no_pretrained(pretrained, checkpoint)
+    return _configure_model(DarknetV4([(64, 1), (128, 2), (256, 8), (512, 8), (1024, 4)], **kwargs), ckpt)
 
 
 def cspdarknet53_mish(pretrained: bool = False, checkpoint: Any = None, progress: bool = True, **kwargs: Any) -> DarknetV4:
     """CSP-Darknet-53 with Mish activations and DropBlock regularisation (reference darknetv4.py:296-326)."""
-    _no_pretrained(pretrained, checkpoint)
+    ckpt = _no_pretrained(pretrained, checkpoint)
     kwargs["act_layer"] = nn.Mish(inplace=True)
     kwargs["drop_layer"] = DropBlock2d
-    return DarknetV4([(64, 1), (128, 2), (256, 8), (512, 8), (1024, 4)], **kwargs)
+    return _configure_model(DarknetV4([(64, 1), (128, 2), (256, 8), (512, 8), (1024, 4)], **kwargs), ckpt)

@@ -17,7 +17,7 @@ from torch import Tensor, nn
 from ...nn import GlobalAvgPool2d, init
 from ...nn import _fused as K
 from .._blocks import _dense_ok, _depthwise_ok, conv_bn_act
-from ..utils import conv_sequence, fuse_conv_bn
+from ..utils import _configure_model, _requested_checkpoint, conv_sequence, fuse_conv_bn
 
 __all__ = ["DepthConvBlock", "MobileOne", "MobileOneBlock", "PointConvBlock", "mobileone_s0", "mobileone_s1", "mobileone_s2",
            "mobileone_s3"]
@@ -214,12 +214,9 @@ class MobileOne(nn.Sequential):
 
 
 def _mobileone(pretrained: bool, checkpoint: Any, width_multipliers: List[float], overparam_factor: int, **kwargs: Any) -> MobileOne:
-    if pretrained or checkpoint is not None:
-        raise NotImplementedError("pretrained checkpoints need network access; load a reference state_dict instead "
-                                  "(the module tree and parameter names are identical)")
+    checkpoint = _requested_checkpoint(pretrained, checkpoint)
     model = MobileOne([2, 8, 10, 1], width_multipliers, overparam_factor, **kwargs)
-    model.default_cfg = None
-    return model
+    return _configure_model(model, checkpoint)
 
 
 def mobileone_s0(pretrained: bool = False, checkpoint: Any = None, progress: bool = True, **kwargs: Any) -> MobileOne:

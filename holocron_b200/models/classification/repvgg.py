@@ -19,7 +19,7 @@ from torch import Tensor, nn
 
 from ...nn import GlobalAvgPool2d, init
 from ...nn import _fused as K
-from ..utils import conv_sequence, fuse_conv_bn
+from ..utils import _configure_model, _requested_checkpoint, conv_sequence, fuse_conv_bn
 
 __all__ = ["RepBlock", "RepVGG", "repvgg_a0", "repvgg_a1", "repvgg_a2", "repvgg_b0", "repvgg_b1", "repvgg_b2",
            "repvgg_b3"]
@@ -157,10 +157,8 @@ class RepVGG(nn.Sequential):
 
 
 def _repvgg(num_blocks: List[int], a: float, b: float, pretrained: bool, checkpoint: Any, **kwargs: Any) -> RepVGG:
-    if pretrained or checkpoint is not None:
-        raise NotImplementedError("pretrained checkpoints need network access; load a reference state_dict instead "
-                                  "(the module tree and parameter names are identical)")
-    return RepVGG(num_blocks, [64, 64, 128, 256, 512], a, b, **kwargs)
+    checkpoint = _requested_checkpoint(pretrained, checkpoint)
+    return _configure_model(RepVGG(num_blocks, [64, 64, 128, 256, 512], a, b, **kwargs), checkpoint)
 
 
 def repvgg_a0(pretrained: bool = False, checkpoint: Any = None, progress: bool = True, **kwargs: Any) -> RepVGG:

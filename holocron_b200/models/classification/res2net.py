@@ -13,7 +13,7 @@ import torch
 from torch import Tensor, nn
 
 from .._blocks import FusedSequential
-from ..utils import conv_sequence
+from ..utils import _configure_model, _requested_checkpoint, conv_sequence
 from .resnet import ResNet, _ResBlock
 
 __all__ = ["Bottle2neck", "ScaleConv2d", "res2net50_26w_4s"]
@@ -73,13 +73,10 @@ class Bottle2neck(_ResBlock):
 
 def _res2net(pretrained: bool, checkpoint: Any, num_blocks: List[int], out_chans: List[int], width_per_group: int, scale: int,
              **kwargs: Any) -> ResNet:
-    if pretrained or checkpoint is not None:
-        raise NotImplementedError("pretrained checkpoints need network access; load a reference state_dict instead "
-                                  "(the module tree and parameter names are identical)")
+    checkpoint = _requested_checkpoint(pretrained, checkpoint)
     model = ResNet(Bottle2neck, num_blocks, out_chans, width_per_group=width_per_group,  # type: ignore[arg-type]
                    block_args={"scale": scale}, **kwargs)
-    model.default_cfg = None
-    return model
+    return _configure_model(model, checkpoint)
 
 
 def res2net50_26w_4s(pretrained: bool = False, checkpoint: Any = None, progress: bool = True, **kwargs: Any) -> ResNet:

@@ -14,7 +14,7 @@ from torch import Tensor, nn
 from ...nn import GlobalAvgPool2d, init
 from ...nn import _fused as K
 from .._blocks import FusedSequential, run_fused
-from ..utils import conv_sequence
+from ..utils import _configure_model, _requested_checkpoint, conv_sequence
 
 __all__ = ["BasicBlock", "Bottleneck", "ChannelRepeat", "ResNet", "resnet18", "resnet34", "resnet50", "resnet50d", "resnet101",
            "resnet152", "resnext50_32x4d", "resnext101_32x8d"]
@@ -185,12 +185,9 @@ class ResNet(nn.Sequential):
 
 def _resnet(arch: str, pretrained: bool, checkpoint: Any, block: Type[Union[BasicBlock, Bottleneck]], num_blocks: List[int],
             out_chans: List[int], **kwargs: Any) -> ResNet:
-    if pretrained or checkpoint is not None:
-        raise NotImplementedError("pretrained checkpoints need network access; load a reference state_dict instead "
-                                  "(the module tree and parameter names are identical)")
+    checkpoint = _requested_checkpoint(pretrained, checkpoint)
     model = ResNet(block, num_blocks, out_chans, **kwargs)
-    model.default_cfg = None   # the reference stores the checkpoint description here (models/utils.py:183): none without one
-    return model
+    return _configure_model(model, checkpoint)
 
 
 def resnet18(pretrained: bool = False, checkpoint: Any = None, progress: bool = True, **kwargs: Any) -> ResNet:

@@ -24,7 +24,7 @@ from ...nn import GlobalAvgPool2d, init
 from ...nn import _fused as K
 from ...nn._dwconv import dwconv2d
 from .._blocks import conv_bn_act
-from ..utils import conv_sequence
+from ..utils import _configure_model, _requested_checkpoint, conv_sequence
 
 __all__ = ["ReXBlock", "ReXNet", "SEBlock", "rexnet1_0x", "rexnet1_3x", "rexnet1_5x", "rexnet2_0x", "rexnet2_2x"]
 
@@ -179,9 +179,8 @@ class ReXNet(nn.Sequential):
 
 
 def _rexnet(width_mult: float, depth_mult: float, pretrained: bool, checkpoint: Any, **kwargs: Any) -> ReXNet:
-    if pretrained or checkpoint is not None:
-        raise NotImplementedError("pretrained checkpoints need network access; load a reference state_dict instead")
-    return ReXNet(width_mult, depth_mult, **kwargs)
+    checkpoint = _requested_checkpoint(pretrained, checkpoint)
+    return _configure_model(ReXNet(width_mult, depth_mult, **kwargs), checkpoint)
 
 
 def rexnet1_0x(pretrained: bool = False, checkpoint: Any = None, progress: bool = True, **kwargs: Any) -> ReXNet:

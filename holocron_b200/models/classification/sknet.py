@@ -13,7 +13,7 @@ from torch import Tensor, nn
 
 from ...nn import GlobalAvgPool2d
 from .._blocks import FusedSequential
-from ..utils import conv_sequence
+from ..utils import _configure_model, _requested_checkpoint, conv_sequence
 from .resnet import ResNet, _ResBlock
 
 __all__ = ["SKBottleneck", "SKConv2d", "SoftAttentionLayer", "sknet50", "sknet101", "sknet152"]
@@ -90,12 +90,9 @@ class SKBottleneck(_ResBlock):
 
 
 def _sknet(pretrained: bool, checkpoint: Any, num_blocks: List[int], out_chans: List[int], **kwargs: Any) -> ResNet:
-    if pretrained or checkpoint is not None:
-        raise NotImplementedError("pretrained checkpoints need network access; load a reference state_dict instead "
-                                  "(the module tree and parameter names are identical)")
+    checkpoint = _requested_checkpoint(pretrained, checkpoint)
     model = ResNet(SKBottleneck, num_blocks, out_chans, **kwargs)  # type: ignore[arg-type]
-    model.default_cfg = None
-    return model
+    return _configure_model(model, checkpoint)
 
 
 def sknet50(pretrained: bool = False, checkpoint: Any = None, progress: bool = True, **kwargs: Any) -> ResNet:
