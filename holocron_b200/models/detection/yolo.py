@@ -83,8 +83,9 @@ class _YOLO(nn.Module):
             cx = (boxes[:, [0, 2]].mean(dim=-1) * w).to(dtype=torch.long)
             cy = (boxes[:, [1, 3]].mean(dim=-1) * h).to(dtype=torch.long)
             cell_xyxy = pred_xyxy[img, cy, cx]                                       # [G, A, 4]
-            # IoU of every box with the A predictions of ITS cell: the diagonal blocks of one G x (G*A) pairwise launch
-            iou_cell = box_iou(boxes, cell_xyxy.reshape(-1, 4)).view(num_gt, num_gt, na)[ar, ar]
+            # IoU of every box with the A predictions of ITS cell: the diagonal blocks of one (G*A) x G pairwise launch
+            # (predictions first: the argument order whose data gradient YOLOv4's losses exercise as well)
+            iou_cell = box_iou(cell_xyxy.reshape(-1, 4), boxes).view(num_gt, na, num_gt)[ar, :, ar]
             iou, anchor = iou_cell.max(dim=1)
             is_noobj = is_noobj.index_put((img, cy, cx, anchor), is_noobj.new_zeros(()))   # device-side value: graph-capturable
             onehot = F.one_hot(labels, self.num_classes).to(pred_scores.dtype)
