@@ -154,7 +154,9 @@ def synthetic_batch(batch: int, seed: int, device, size: int = 224):
 
 
 # ------------------------------------------------------------------------------------------------ workloads
-CLS_KEYS = ("repvgg_a0", "rexnet1_0x", "repvgg_a1", "resnet50", "resnet18", "mobileone_s0")   # classification workloads: (images, labels) + CE
+# classification workloads: (images, labels) + CE
+CLS_KEYS = ("repvgg_a0", "rexnet1_0x", "repvgg_a1", "resnet50", "resnet18", "mobileone_s0", "res2net50_26w_4s", "sknet50",
+            "convnext_tiny", "tridentnet50", "pyconv_resnet50")
 
 
 class Workload:
@@ -183,6 +185,9 @@ class Workload:
                              "CE(label_smoothing=0.1) + bwd + AdaBelief"),
             "resnet18": ("resnet18", {"num_classes": NUM_CLASSES}, 256, 224, True,
                          "resnet18 224x224 bf16 train step (SURVEY 8-f3): fwd + CE(label_smoothing=0.1) + bwd + AdaBelief"),
+            **{k: (k, {"num_classes": NUM_CLASSES}, 128, 224, True,
+                   f"{k} 224x224 bf16 train step (SURVEY 8-f3): fwd + CE(label_smoothing=0.1) + bwd + AdaBelief, batch 128/GPU")
+               for k in ("res2net50_26w_4s", "sknet50", "convnext_tiny", "tridentnet50", "pyconv_resnet50")},
             "unet3p": ("unet3p", {"num_classes": 21}, 16, 256, True,
                        "unet3p 256x256 segmentation train step (BASELINE configs[4]): fwd + DiceLoss(softmax, one-hot) + bwd + "
                        "AdaBelief; synthetic masks"),
@@ -597,7 +602,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the configuration's own)")
     ap.add_argument("--model", "--workload", dest="model", default="repvgg_a0",
-                    choices=["repvgg_a0", "rexnet1_0x", "repvgg_a1", "yolov4", "unet3p", "resnet50", "resnet18", "mobileone_s0"],
+                    choices=["repvgg_a0", "rexnet1_0x", "repvgg_a1", "yolov4", "unet3p", "resnet50", "resnet18", "mobileone_s0",
+                             "res2net50_26w_4s", "sknet50", "convnext_tiny", "tridentnet50", "pyconv_resnet50"],
                     help="repvgg_a0 = the contract metric (default); the others are BASELINE.json configs[1..4]")
     ap.add_argument("--config", type=int, default=0, help="BASELINE.json configs index 1..4 (alias of --model)")
     ap.add_argument("--micro", action="store_true", help="leaf-kernel micro rows (GB/s vs the measured HBM peak) instead of a model")

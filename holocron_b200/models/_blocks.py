@@ -59,7 +59,11 @@ def _space_to_depth(x: Tensor, conv: nn.Conv2d):
 def conv_bn_act(x: Tensor, conv: nn.Conv2d, bn: Optional[nn.BatchNorm2d], act: Optional[nn.Module],
                 residual: Optional[Tensor] = None, res_after_act: bool = False, keep_padded: bool = False) -> Tensor:
     """One ``conv -> BN -> act`` unit (+ optional shortcut) on the fused kernels."""
-    if _dense_ok(conv):
+    if type(conv).forward is not nn.Conv2d.forward:
+        # a Conv2d subclass with its own forward (TridentConv2d: one filter shared by three channel chunks): the module decides
+        # which kernels it runs on, the normalisation / activation pass below is the fused one
+        y = conv(x)
+    elif _dense_ok(conv):
         weight, stride, pad = conv.weight, conv.stride[0], conv.padding[0]
         if _patchify_ok(conv, x):
             x, weight, stride, pad = *_space_to_depth(x, conv), 1, 0
@@ -85,8 +89,8 @@ def conv_bn_act(x: Tensor, conv: nn.Conv2d, bn: Optional[nn.BatchNorm2d], act: O
     code, slope = K.act_code(act)
     if bn is not None:
         out = K.bn_act([y], [bn], code, slope, residual=residual, res_after_act=res_after_act)
-        if out.shape[1] != conv.out_channels and not keep_padded:
-            out = out[:, :conv.out_channels]
+        if out.shape[1] != bn.num_features and not keep_padded:      # == conv.out_channels (3x that behind a TridentConv2d)
+            out = out[:, :bn.num_features]
         return out
     if residual is not None:
         cfg = ([], code, slope, False, True, res_after_act)

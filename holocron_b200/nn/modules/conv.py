@@ -1,6 +1,7 @@
 """Convolution-like modules on the hot path — mirrors holocron/nn/modules/conv.py (NormConv2d :55-147, Add2d :150-248,
-SlimConv2d :251-370). Parameter names/shapes are the reference's (state_dict contract)."""
-from typing import Union
+SlimConv2d :251-370, PyConv2d :373-438). Parameter names/shapes are the reference's (state_dict contract)."""
+import math
+from typing import Any, List, Optional, Union
 
 import torch
 from torch import Tensor, nn
@@ -10,7 +11,7 @@ from torch.nn.modules.utils import _pair
 
 from .. import functional as F
 
-__all__ = ["Add2d", "NormConv2d", "SlimConv2d"]
+__all__ = ["Add2d", "NormConv2d", "PyConv2d", "SlimConv2d"]
 
 
 class _NormConvNd(_ConvNd):
@@ -100,3 +101,35 @@ class SlimConv2d(nn.Module):
         x_top = self._conv(self.conv_top, x_top)
         x_bot = self._conv(self.conv_bot2, self._conv(self.conv_bot1, x_bot))
         return torch.cat((x_top, x_bot), dim=1)
+
+
+class PyConv2d(nn.ModuleList):
+    """Pyramidal convolution (https://arxiv.org/abs/2006.11538) — reference conv.py:373-438: ``num_levels`` parallel
+    convolutions of growing kernel size (k, k + 2, ...) and group count over the same input, concatenated on the channel axis.
+    Same children (``state_dict`` keys ``0.weight``, ``1.weight``, ...). The levels run through the conv unit executor: dense
+    levels on the tcgen05 kernel, grouped ones as a library call on the activation dtype."""
+
+    def __init__(self, in_channels: int, out_channels: int, kernel_size: int, num_levels: int = 2, padding: int = 0,
+                 groups: Optional[List[int]] = None, **kwargs: Any) -> None:
+        if num_levels == 1:
+            super().__init__([nn.Conv2d(in_channels, out_channels, kernel_size, padding=padding,
+                                        groups=groups[0] if isinstance(groups, list) else 1, **kwargs)])
+        else:
+            exp2 = int(math.log2(num_levels))
+            reminder = num_levels - 2**exp2
+            out_chans = [out_channels // 2 ** (exp2 + 1)] * (2 * reminder) + [out_channels // 2**exp2] * (num_levels - 2 * reminder)
+            k_sizes = [kernel_size + 2 * idx for idx in range(num_levels)]
+            if groups is None:
+                groups = [1] + [min(2 ** (2 + idx), out_chan) for idx, out_chan in zip(range(num_levels - 1), out_chans[1:])]
+            elif not isinstance(groups, list) or len(groups) != num_levels:
+                raise ValueError("The argument `group` is expected to be a list of integer of size `num_levels`.")
+            paddings = [padding + idx for idx in range(num_levels)]
+            super().__init__([nn.Conv2d(in_channels, out_chan, k_size, padding=pad_, groups=group, **kwargs)
+                              for out_chan, k_size, pad_, group in zip(out_chans, k_sizes, paddings, groups)])
+        self.num_levels = num_levels
+
+    def forward(self, x: Tensor) -> Tensor:
+        from ...models._blocks import conv_bn_act
+        if self.num_levels == 1:
+            return conv_bn_act(x, self[0], None, None)
+        return torch.cat([conv_bn_act(x, conv, None, None) for conv in self], dim=1)

@@ -53,10 +53,13 @@ CLS_RESNET = {"resnet18": (4, 8, 64), "resnet50d": (4, 8, 64), "resnext50_32x4d"
 # SURVEY §8 f3, continued: Res2Net (hierarchical 26-channel slices), SKNet (selective-kernel units: grouped dilated paths +
 # soft attention), ConvNeXt (depth-wise 7x7, LayerNorm, GELU, LayerScale, patchify convolutions). tests/golden/zoo_f3.pt.
 CLS_F3 = {"res2net50_26w_4s": (4, 8, 64), "sknet50": (4, 8, 64), "convnext_atto": (4, 8, 64)}
+# ... and the rest of reference models/classification/*.py: TridentNet (one filter shared by three dilation branches stacked on
+# the channel axis), PyConvResNet (pyramidal 3x3..9x9 grouped convolutions). tests/golden/zoo_f3b.pt.
+CLS_F3B = {"tridentnet50": (4, 8, 64), "pyconv_resnet50": (4, 8, 64), "pyconvhg_resnet50": (4, 8, 64)}
 
 
 def cls_inputs(name: str, mode: str):
-    be, bt, size = {**CLS, **CLS_RESNET, **CLS_F3}[name]
+    be, bt, size = {**CLS, **CLS_RESNET, **CLS_F3, **CLS_F3B}[name]
     b = be if mode == "eval" else bt
     g = torch.Generator().manual_seed(11 if mode == "eval" else 12)
     x = (torch.rand(b, 3, size, size, generator=g) - 0.45) / 0.225
@@ -119,6 +122,7 @@ PROBE = {
     "cspdarknet53": "features.stages.0", "cspdarknet53_mish": "features.stages.0", "rexnet1_0x": "features.4",
     "repvgg_a0": "features.1", "unet3p": "encoder.1", "yolov4": "backbone.stages.0",
     "yolov1": "backbone.layers.0", "yolov2": "backbone.layers.1",
+    "tridentnet50": "features.5.0", "pyconv_resnet50": "features.3.0", "pyconvhg_resnet50": "features.3.0",
     "res2net50_26w_4s": "features.4.0", "sknet50": "features.4.0", "convnext_atto": "features.2.0",
     "resnet18": "features.4", "resnet50d": "features.10.0", "resnext50_32x4d": "features.4.0", "mobileone_s0": "features.1.0",
 }

@@ -331,7 +331,7 @@ if __name__ == "__main__" and "--optim2" in sys.argv:
     print("optim2.pt", (OUT / "optim2.pt").stat().st_size)
 
 
-if __name__ == "__main__" and not any(f in sys.argv for f in ("--zoo", "--zoo-resnet", "--zoo-f3", "--yolo", "--api", "--trainer", "--optim2")):
+if __name__ == "__main__" and not any(f in sys.argv for f in ("--zoo", "--zoo-resnet", "--zoo-f3", "--zoo-f3b", "--yolo", "--api", "--trainer", "--optim2")):
     gen_activations()
     gen_losses()
     gen_boxes()
@@ -484,6 +484,11 @@ def gen_zoo_resnet(which="CLS_RESNET", outfile="zoo_resnet.pt"):
     torch.save(d, OUT / outfile)
 
 
+if __name__ == "__main__" and "--zoo-f3b" in sys.argv:
+    gen_zoo_resnet("CLS_F3B", "zoo_f3b.pt")
+    print("zoo_f3b.pt", (OUT / "zoo_f3b.pt").stat().st_size)
+
+
 if __name__ == "__main__" and "--zoo-f3" in sys.argv:
     gen_zoo_resnet("CLS_F3", "zoo_f3.pt")
     print("zoo_f3.pt", (OUT / "zoo_f3.pt").stat().st_size)
@@ -542,7 +547,7 @@ API_SURFACE = {
     "nn.functional": ["hard_mish", "nl_relu", "focal_loss", "poly_loss", "dice_loss", "norm_conv2d", "add2d", "dropblock2d",
                       "concat_downsample2d"],
     "nn": ["HardMish", "NLReLU", "FReLU", "NormConv2d", "Add2d", "SlimConv2d", "FocalLoss", "PolyLoss", "DiceLoss", "DropBlock2d",
-           "GlobalAvgPool2d", "SPP", "ConcatDownsample2d"],
+           "GlobalAvgPool2d", "SPP", "ConcatDownsample2d", "PyConv2d"],
     "ops.boxes": ["box_giou", "diou_loss", "ciou_loss", "iou_penalty", "aspect_ratio", "aspect_ratio_consistency"],
     "optim": ["AdaBelief", "LAMB", "TAdam", "AdamP", "Adan", "AdEMAMix", "LARS", "RaLars"],
     "optim.wrapper": ["Lookahead"],
@@ -551,7 +556,7 @@ API_SURFACE = {
                "resnet18", "resnet34", "resnet50", "resnet50d", "resnet101", "resnet152", "resnext50_32x4d", "resnext101_32x8d",
                "mobileone_s0", "mobileone_s1", "mobileone_s2", "mobileone_s3", "res2net50_26w_4s", "sknet50", "sknet101", "sknet152",
                "convnext_atto", "convnext_femto", "convnext_pico", "convnext_nano", "convnext_tiny", "convnext_small",
-               "convnext_base", "convnext_large", "convnext_xl"],
+               "convnext_base", "convnext_large", "convnext_xl", "tridentnet50", "pyconv_resnet50", "pyconvhg_resnet50"],
     "models.detection": ["yolov4", "yolov1", "yolov2", "YOLOv1", "YOLOv2"],
     "models.segmentation": ["unet3p"],
 }
