@@ -251,7 +251,10 @@ def pack_filter(weight: Tensor, need_dgrad: bool, cin_p: Optional[int] = None) -
     wid = id(weight)
     ent.wref = weakref.ref(weight, lambda _r, wid=wid: _pack_cache.pop(wid, None) if _pack_cache.get(wid) is not None
                            and _pack_cache[wid].wref() is None else None)
-    ent.w_krsc = w_krsc if zero_copy else None     # only views of the live parameter can sit in the device table
+    # only views of a live PARAMETER can sit in the device table: a per-step temporary (ConvNeXt's patchify filters are
+    # permuted views rebuilt every forward) would change the table's membership every step - a host->device rebuild that a
+    # CUDA-graph capture cannot contain; such filters are packed by their own launch each time
+    ent.w_krsc = w_krsc if (zero_copy and isinstance(weight, nn.Parameter)) else None
     ent.wf = torch.empty((ent.cout_p, r, s, cin_p), device=w.device, dtype=torch.bfloat16)
     ent.wd = torch.empty((ent.cin_d, r, s, ent.cout_p), device=w.device, dtype=torch.bfloat16) if need_dgrad else None
     check(lib().hb_pack_conv_weights(ptr(w_krsc), ptr(ent.wf), ptr(ent.wd), cout, cin, r, s, cin_p, ent.cin_d, ent.cout_p,

@@ -82,8 +82,11 @@ class TrainStep:
 
     def __init__(self, model: nn.Module, criterion: Callable[..., Tensor], optimizer: torch.optim.Optimizer,
                  gradient_acc: int = 1, grad_clip: Optional[float] = None, skip_nan_loss: bool = False, nan_tolerance: int = 5,
-                 schedule: Optional[Tensor] = None, graph: bool = True, process_group=None) -> None:
+                 schedule: Optional[Tensor] = None, graph: bool = True, process_group=None,
+                 forward_loss: Optional[Callable[..., Tensor]] = None) -> None:
         self.model, self.criterion, self.optimizer = model, criterion, optimizer
+        # `forward_loss(*batch) -> loss` replaces `criterion(model(x), *targets)` (detectors compute their own losses)
+        self.forward_loss = forward_loss
         self.gradient_acc = int(gradient_acc)
         self.grad_clip = None if grad_clip is None else float(grad_clip)
         self.skip_nan_loss, self.nan_tolerance = bool(skip_nan_loss), int(nan_tolerance)
@@ -110,8 +113,11 @@ class TrainStep:
     # ---- the two kinds of iteration: accumulate only / accumulate + update --------------------------------------
     def _iteration(self, update: bool, *batch: Tensor) -> Tensor:
         L = lib()
-        x, target = batch[0], batch[1:]
-        loss = self.criterion(self.model(x), *target)
+        if self.forward_loss is not None:
+            loss = self.forward_loss(*batch)
+        else:
+            x, target = batch[0], batch[1:]
+            loss = self.criterion(self.model(x), *target)
         loss32 = loss.detach().float().reshape(1)
         check(L.hb_train_ctl_observe(ptr(self.ctl), ptr(loss32), int(self.skip_nan_loss), stream_ptr()), "hb_train_ctl_observe")
         loss.backward()

@@ -117,14 +117,21 @@ def teacher_forcing():
     def unit(x, conv_m, bn, act, residual=None, res_after_act=False, keep_padded=False):
         out = orig_unit(x, conv_m, bn, act, residual, res_after_act, keep_padded)
         with torch.no_grad():
-            xf = x.detach()[:, :conv_m.in_channels].to(torch.bfloat16).float()   # the kernels' operand rounding
-            z = TF.conv2d(xf, conv_m.weight.detach().to(torch.bfloat16).float(),
-                          None if conv_m.bias is None else conv_m.bias.detach().float(), conv_m.stride, conv_m.padding,
-                          conv_m.dilation, conv_m.groups)
+            wq = conv_m.weight.detach().to(torch.bfloat16).float()
+            bq = None if conv_m.bias is None else conv_m.bias.detach().float()
+            if type(conv_m).__name__ == "TridentConv2d":
+                # one filter over three channel chunks, dilation 1 / 2 / 3 for the 3x3 layers (reference tridentnet.py:36-59)
+                xf = x.detach().to(torch.bfloat16).float()
+                dils = [1, 1, 1] if conv_m.dilation[0] == 1 else [1, 2, 3]
+                z = torch.cat([TF.conv2d(c, wq, bq, conv_m.stride, tuple(d * p for p in conv_m.padding), (d, d), conv_m.groups)
+                               for c, d in zip(torch.chunk(xf, 3, 1), dils)], 1)
+            else:
+                xf = x.detach()[:, :conv_m.in_channels].to(torch.bfloat16).float()   # the kernels' operand rounding
+                z = TF.conv2d(xf, wq, bq, conv_m.stride, conv_m.padding, conv_m.dilation, conv_m.groups)
             if bn is not None:
                 z = _bn_ref(z.to(torch.bfloat16), bn, bn.training)
             code, slope = _fused.act_code(act)
-            c = conv_m.out_channels
+            c = z.shape[1]            # == conv_m.out_channels (3 x that behind a TridentConv2d)
             if residual is not None and not res_after_act:
                 z = z + residual.detach().float()[:, :c]
             ref = _act_ref(z, code, slope)

@@ -331,7 +331,7 @@ if __name__ == "__main__" and "--optim2" in sys.argv:
     print("optim2.pt", (OUT / "optim2.pt").stat().st_size)
 
 
-if __name__ == "__main__" and not any(f in sys.argv for f in ("--zoo", "--zoo-resnet", "--zoo-f3", "--zoo-f3b", "--yolo", "--api", "--trainer", "--optim2")):
+if __name__ == "__main__" and not any(f in sys.argv for f in ("--zoo", "--zoo-resnet", "--zoo-f3", "--zoo-f3b", "--yolo", "--trainers", "--api", "--trainer", "--optim2")):
     gen_activations()
     gen_losses()
     gen_boxes()
@@ -733,3 +733,42 @@ def gen_trainer():
 if __name__ == "__main__" and "--trainer" in sys.argv:
     gen_trainer()
     print("trainer.pt", (OUT / "trainer.pt").stat().st_size)
+
+
+# ------------------------------------------------------------------------------------------------ trainer classes
+def gen_trainers():
+    """The UNMODIFIED reference trainer classes (ClassificationTrainer, BinaryClassificationTrainer, SegmentationTrainer,
+    DetectionTrainer, assign_iou, fit_n_epochs / find_lr / check_setup) on the scenarios of tests/_trainer_cases.py ->
+    tests/golden/trainers.pt. fastprogress / matplotlib / tqdm are stubbed (progress bars and plots only)."""
+    import types
+    for name in ("matplotlib", "matplotlib.pyplot", "fastprogress", "fastprogress.fastprogress", "tqdm", "tqdm.auto"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+
+    class _Bar(list):
+        def __init__(self, it, parent=None):
+            super().__init__(it)
+            self.comment = ""
+            self.main_bar = types.SimpleNamespace(comment="")
+
+        def write(self, *a, **k):
+            pass
+    sys.modules["fastprogress"].master_bar = _Bar
+    sys.modules["fastprogress"].progress_bar = _Bar
+    sys.modules["fastprogress.fastprogress"].ConsoleMasterBar = _Bar
+    for fn in ("plot", "xlabel", "ylabel", "grid", "show", "xscale", "ylim", "subplots"):
+        setattr(sys.modules["matplotlib.pyplot"], fn, lambda *a, **k: None)
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    for m in ("tqdm", "tqdm.auto"):
+        sys.modules[m].tqdm = lambda it, *a, **k: it
+    import importlib
+    T = importlib.import_module("holocron.trainer")
+    sys.path.insert(0, str(ROOT / "tests"))
+    import _trainer_cases as cases
+    d = {}
+    cases.run_scenarios(T, lambda tag, rec: d.__setitem__(tag, rec))
+    torch.save(d, OUT / "trainers.pt")
+
+
+if __name__ == "__main__" and "--trainers" in sys.argv:
+    gen_trainers()
+    print("trainers.pt", (OUT / "trainers.pt").stat().st_size)

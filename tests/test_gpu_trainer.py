@@ -138,3 +138,67 @@ def test_adamp_matches_reference_formulas(amsgrad, wd):
     sd = opt.state_dict()
     assert set(sd["state"][0]) >= {"step", "exp_avg", "exp_avg_sq"} and sd["state"][0]["step"] == 3
     assert isinstance(opt, torch.optim.Adam)
+
+
+@pytest.mark.parametrize("tag", ["acc2_clip_onecycle", "nan_skip_cosine"])
+def test_trainer_class_device_path_reproduces_reference_trainer(tag, tmp_path):
+    """The reference's call sequence (Trainer(...); freeze_model; _reset_opt; _reset_scheduler; _fit_epoch) through
+    holocron_b200.trainer.ClassificationTrainer on cuda:0 with the fused AdaBelief: the device path is selected (TrainStep:
+    accumulation, clipping, schedule table and NaN skipping on the device), counters and final parameters match the golden
+    run of the reference's own Trainer; then evaluate() / save() / load() on the device."""
+    d = load_golden("trainer")[tag]
+    cfg = d["cfg"]
+    model = tiny()
+    data = batches(8, cfg["nan_at"])
+    opt = hb.optim.AdaBelief(model.parameters(), lr=1e-3, betas=(0.95, 0.99), eps=1e-6, capturable=True)
+    tr = hb.trainer.ClassificationTrainer(model, data, data[:2], torch.nn.CrossEntropyLoss(), opt, gpu=0,
+                                          output_file=str(tmp_path / "ckpt.pth"), skip_nan_loss=cfg["skip_nan_loss"], nan_tolerance=5,
+                                          gradient_acc=cfg["gradient_acc"], gradient_clip=cfg["gradient_clip"], log_every=4)
+    assert next(tr.model.parameters()).is_cuda
+    hb.trainer.freeze_model(tr.model.train(), None)
+    tr._reset_opt(cfg["lr"], None)
+    tr._reset_scheduler(cfg["lr"], 1, cfg["sched"])
+    assert tr._train_step is not None                      # fused optimizer with capturable=True -> device path
+    tr._fit_epoch()
+    st = tr._train_step.state()
+    assert (tr.step, tr.epoch, st["iter"], st["opt_steps"]) == (8, 1, 8, d["opt_steps"])
+    sd = tr.model.state_dict()
+    init = tiny().state_dict()
+    keys = [k for k, v in d["state"].items() if v.dtype.is_floating_point and "running" not in k]
+    ours = torch.cat([sd[k].detach().float().cpu().flatten() for k in keys])
+    ref_p = torch.cat([d["state"][k].flatten() for k in keys])
+    p0 = torch.cat([init[k].flatten() for k in keys])
+    e_all = rel_l2(ours, ref_p)
+    cos = torch.nn.functional.cosine_similarity(ours - p0, ref_p - p0, dim=0).item()
+    print(f"\n[trainer class {tag}] parameters rel-L2 {e_all:.5f}, update cosine {cos:.4f}, recorded losses {tr.loss_recorder}")
+    assert e_all < 2e-2 and cos > 0.9
+    assert len(tr.loss_recorder) == 2                      # loss read back every `log_every` = 4 iterations
+    if cfg["nan_at"] is None:                              # (the NaN batch poisons the running statistics, as in the reference)
+        m = tr.evaluate()
+        assert set(m) == {"val_loss", "acc1", "acc5"} and m["val_loss"] == m["val_loss"] and 0.0 <= m["acc1"] <= m["acc5"] <= 1.0
+        assert "Acc@1" in tr._eval_metrics_str(m)
+    tr.save(str(tmp_path / "ckpt.pth"))
+    state = torch.load(tmp_path / "ckpt.pth", map_location="cpu")
+    assert sorted(state) == ["epoch", "min_loss", "model", "step"] and state["step"] == 8
+    tr.load(state)
+    assert tr.epoch == 1 and tr.step == 8
+
+
+def test_trainer_class_fit_n_epochs_and_lr_finder_on_device(tmp_path):
+    """fit_n_epochs (two epochs, one-cycle) + find_lr + check_setup end to end on the device path: the loss goes down, the
+    checkpoint of the best epoch is written, the finder records one loss per rate."""
+    model = tiny()
+    data = batches(8)
+    opt = hb.optim.AdaBelief(model.parameters(), lr=1e-3, betas=(0.95, 0.99), eps=1e-6, capturable=True)
+    seen = []
+    tr = hb.trainer.ClassificationTrainer(model, data, data[:3], torch.nn.CrossEntropyLoss(), opt, gpu=0,
+                                          output_file=str(tmp_path / "best.pth"), on_epoch_end=lambda m: seen.append(dict(m)))
+    tr.fit_n_epochs(2, 2e-3, sched_type="onecycle")
+    assert len(seen) == 2 and tr.epoch == 2 and tr.step == 16 and (tmp_path / "best.pth").exists()
+    assert all(m["val_loss"] == m["val_loss"] for m in seen) and tr.min_loss == min(m["val_loss"] for m in seen)
+    tr.find_lr(start_lr=1e-5, end_lr=1e-2, num_it=6)
+    assert len(tr.lr_recorder) == len(tr.loss_recorder) == 6 and abs(tr.lr_recorder[-1] - 1e-2) < 1e-9
+    tr.check_setup(lr=1e-3, num_it=6)
+    assert len(tr.loss_recorder) == 6 and tr.loss_recorder[-1] < tr.loss_recorder[0]
+    with pytest.raises(ValueError):
+        tr.find_lr(num_it=100)
