@@ -162,7 +162,7 @@ class Trainer:
                 self.step += 1
                 if (idx + 1) % self.log_every == 0:
                     self._train_step.check()                      # raises past `nan_tolerance` consecutive NaN updates
-                    self.loss_recorder.append(float(last))
+                    self.loss_recorder.append(float(last.detach()))
             if last is not None:
                 self._train_step.check()
             self.epoch += 1
