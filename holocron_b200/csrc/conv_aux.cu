@@ -58,6 +58,33 @@ __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackMeta*
   const size_t nd = m.wd ? (size_t)m.CinD * m.R * m.S * m.CoutP : 0;
   const size_t base = (size_t)ck.y * kPackChunk;
   const size_t end = min(base + (size_t)kPackChunk, nf + nd);
+  if (nf + nd < 0x7fffffffu) {
+    // every filter of a real network: 32-bit index arithmetic (the four runtime div/mod pairs per element dominated this kernel
+    // when done on size_t: 277 us for RepVGG-A0's 18 M packed elements, 0.2 GB of DRAM traffic - ALU bound, not memory bound)
+    const unsigned nf32 = (unsigned)nf, end32 = (unsigned)end;
+    const unsigned R = m.R, S = m.S, CinP = m.CinP, CoutP = m.CoutP, Cin = m.Cin, Cout = m.Cout;
+    for (unsigned i = (unsigned)base + threadIdx.x; i < end32; i += 256) {
+      if (i < nf32) {
+        const unsigned ci = i % CinP;
+        unsigned t = i / CinP;
+        const unsigned s = t % S; t /= S;
+        const unsigned r = t % R;
+        const unsigned co = t / R;
+        const float v = (ci < Cin && co < Cout) ? m.w[((co * R + r) * S + s) * Cin + ci] : 0.f;
+        m.wf[i] = __float2bfloat16_rn(v);
+      } else {
+        const unsigned k = i - nf32;
+        const unsigned co = k % CoutP;
+        unsigned t = k / CoutP;
+        const unsigned s = t % S; t /= S;
+        const unsigned r = t % R;
+        const unsigned ci = t / R;
+        const float v = (co < Cout && ci < Cin) ? m.w[((co * R + (R - 1 - r)) * S + (S - 1 - s)) * Cin + ci] : 0.f;
+        m.wd[k] = __float2bfloat16_rn(v);
+      }
+    }
+    return;
+  }
   for (size_t i = base + threadIdx.x; i < end; i += 256) {
     if (i < nf) {
       const int ci = i % m.CinP;
