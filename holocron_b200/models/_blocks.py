@@ -122,6 +122,11 @@ def run_fused(mods: Sequence[nn.Module], x: Tensor, residual: Optional[Tensor] =
         elif isinstance(m, FusedSequential):
             x = m(x)
             i += 1
+        elif isinstance(m, nn.BatchNorm2d) and x.is_cuda and x.shape[1] % 8 != 0:
+            # stand-alone BatchNorm on a width the fused pass cannot take (ReXNet-1.3x taps of DynamicUNet: 35, 61 ... channels;
+            # behind a convolution the width is zero-padded instead): library call in the parameters' dtype
+            x = m(x.to(m.weight.dtype if m.weight is not None else torch.float32)).to(x.dtype)
+            i += 1
         elif isinstance(m, nn.BatchNorm2d):
             act = None
             j = i + 1

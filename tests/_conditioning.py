@@ -58,6 +58,22 @@ CLS_F3 = {"res2net50_26w_4s": (4, 8, 64), "sknet50": (4, 8, 64), "convnext_atto"
 CLS_F3B = {"tridentnet50": (4, 8, 64), "pyconv_resnet50": (4, 8, 64), "pyconvhg_resnet50": (4, 8, 64)}
 
 
+# U-Net family (reference models/segmentation/unet.py, unetpp.py): plain U-Net, the nested UNet+ / UNet++ grids, DynamicUNet on its
+# own contracting path and on this package's ReXNet-1.3x (odd channel counts at every tap). tests/golden/zoo_seg.pt.
+SEG = ("unet", "unetp", "unetpp", "unet2", "unet_rexnet13")
+
+
+def seg_inputs():
+    g = torch.Generator().manual_seed(16)
+    x = torch.rand(2, 3, 64, 64, generator=g)
+    mask = torch.randint(0, 5, (2, 64, 64), generator=g)
+    return x, mask
+
+
+def seg_kwargs(name: str):
+    return dict(num_classes=5, **({"pretrained_backbone": False} if "rexnet" in name else {}))
+
+
 def cls_inputs(name: str, mode: str):
     be, bt, size = {**CLS, **CLS_RESNET, **CLS_F3, **CLS_F3B}[name]
     b = be if mode == "eval" else bt
@@ -121,6 +137,7 @@ PROBE = {
     "darknet24": "features.layers.0", "darknet19": "features.layers.0", "darknet53": "features.layers.0",
     "cspdarknet53": "features.stages.0", "cspdarknet53_mish": "features.stages.0", "rexnet1_0x": "features.4",
     "repvgg_a0": "features.1", "unet3p": "encoder.1", "yolov4": "backbone.stages.0",
+    "unet": "encoder.1", "unetp": "encoder.1", "unetpp": "encoder.1", "unet2": "encoder.1", "unet_rexnet13": "encoder.4",
     "yolov1": "backbone.layers.0", "yolov2": "backbone.layers.1",
     "tridentnet50": "features.5.0", "pyconv_resnet50": "features.3.0", "pyconvhg_resnet50": "features.3.0",
     "res2net50_26w_4s": "features.4.0", "sknet50": "features.4.0", "convnext_atto": "features.2.0",

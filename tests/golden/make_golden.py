@@ -331,7 +331,7 @@ if __name__ == "__main__" and "--optim2" in sys.argv:
     print("optim2.pt", (OUT / "optim2.pt").stat().st_size)
 
 
-if __name__ == "__main__" and not any(f in sys.argv for f in ("--zoo", "--zoo-resnet", "--zoo-f3", "--zoo-f3b", "--yolo", "--trainers", "--api", "--trainer", "--optim2")):
+if __name__ == "__main__" and not any(f in sys.argv for f in ("--zoo", "--zoo-resnet", "--zoo-f3", "--zoo-f3b", "--yolo", "--trainers", "--seg", "--api", "--trainer", "--optim2")):
     gen_activations()
     gen_losses()
     gen_boxes()
@@ -558,7 +558,8 @@ API_SURFACE = {
                "convnext_atto", "convnext_femto", "convnext_pico", "convnext_nano", "convnext_tiny", "convnext_small",
                "convnext_base", "convnext_large", "convnext_xl", "tridentnet50", "pyconv_resnet50", "pyconvhg_resnet50"],
     "models.detection": ["yolov4", "yolov1", "yolov2", "YOLOv1", "YOLOv2"],
-    "models.segmentation": ["unet3p"],
+    "models.segmentation": ["unet3p", "unet", "unet2", "unetp", "unetpp", "unet_rexnet13", "unet_tvvgg11", "unet_tvresnet34", "UNet",
+                            "DynamicUNet", "UNetp", "UNetpp"],
 }
 
 
@@ -634,6 +635,10 @@ def gen_state_dicts():
     for name in ("yolov1", "yolov2"):
         torch.manual_seed(0)
         d[name] = describe_state_dict(getattr(holocron.models.detection, name)(pretrained_backbone=False, num_classes=20))
+    for name in ("unet", "unetp", "unetpp", "unet2", "unet_rexnet13", "unet_tvvgg11", "unet_tvresnet34"):
+        torch.manual_seed(0)
+        kw = {} if name in ("unet", "unetp", "unetpp", "unet2") else {"pretrained_backbone": False}
+        d[name] = describe_state_dict(getattr(holocron.models.segmentation, name)(num_classes=5, **kw))
     (OUT / "state_dicts.json").write_text(json.dumps(d, indent=1, sort_keys=True))
 
 
@@ -772,3 +777,35 @@ def gen_trainers():
 if __name__ == "__main__" and "--trainers" in sys.argv:
     gen_trainers()
     print("trainers.pt", (OUT / "trainers.pt").stat().st_size)
+
+
+def gen_seg():
+    """U-Net family fixtures (reference models/segmentation/unet.py, unetpp.py) -> tests/golden/zoo_seg.pt: logits, cross-entropy
+    loss, first / middle / last parameter gradients (large ones cut to their first rows), an encoder probe."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    import _conditioning as C
+    d = {}
+    for name in C.SEG:
+        out = {}
+        for mode in ("eval", "train"):
+            torch.manual_seed(0)
+            m = C.condition(getattr(holocron.models.segmentation, name)(**C.seg_kwargs(name)))
+            m = C.freeze_bn(m) if mode == "eval" else m.train()
+            x, mask = C.seg_inputs()
+            store = {}
+            C.capture(m, C.PROBE[name], store)
+            o = m(x)
+            loss = torch.nn.functional.cross_entropy(o, mask)
+            loss.backward()
+            names = [n for n, p in m.named_parameters() if p.grad is not None]
+            ps = dict(m.named_parameters())
+            keys = [names[0], names[len(names) // 2 // 2 * 2], names[-2]]
+            out[mode] = dict(out=o.detach(), loss=loss.detach(), grads={k: C.head_rows(ps[k].grad).clone() for k in keys},
+                             probe=store["probe"][:1, :32].half() if mode == "train" else None)
+        d[name] = out
+    torch.save(d, OUT / "zoo_seg.pt")
+
+
+if __name__ == "__main__" and "--seg" in sys.argv:
+    gen_seg()
+    print("zoo_seg.pt", (OUT / "zoo_seg.pt").stat().st_size)

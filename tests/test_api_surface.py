@@ -22,6 +22,7 @@ def _describe(obj):
 # deliberate, documented deviations: (path, parameter) -> our default
 # no network: nothing to download, so the detectors default to an un-pretrained backbone
 DEVIATIONS = {(f"models.detection.{n}", "pretrained_backbone"): "False" for n in ("yolov4", "yolov1", "yolov2")}
+DEVIATIONS.update({(f"models.segmentation.{n}", "pretrained_backbone"): "False" for n in ("unet_rexnet13", "unet_tvvgg11", "unet_tvresnet34")})
 
 
 def test_public_signatures_match_reference():
@@ -86,8 +87,8 @@ def test_state_dict_layout_and_seeded_init_match_reference():
     parameter / buffer values produced under torch.manual_seed(0), against hashes recorded from the reference."""
     import torch
     ref = json.loads((GOLDEN / "state_dicts.json").read_text())
-    # 17 + 8 (ResNet family) + 4 (MobileOne) + 1 (Res2Net) + 3 (SKNet) + 9 (ConvNeXt) classification factories, yolov4, unet3p, yolov1, yolov2
-    assert len(ref) >= 46
+    # 17 + 8 (ResNet family) + 4 (MobileOne) + 1 (Res2Net) + 3 (SKNet) + 9 (ConvNeXt) classification factories, yolov4, unet3p, yolov1, yolov2, 7 U-Nets
+    assert len(ref) >= 56
     for name, want in ref.items():
         torch.manual_seed(0)
         if name == "yolov4":
@@ -96,6 +97,8 @@ def test_state_dict_layout_and_seeded_init_match_reference():
             m = hb.models.unet3p(num_classes=21)
         elif name in ("yolov1", "yolov2"):
             m = getattr(hb.models, name)(num_classes=20)
+        elif name.startswith("unet"):
+            m = getattr(hb.models, name)(num_classes=5)
         else:
             m = getattr(hb.models, name)(num_classes=10)
         got = _describe_state_dict(m)

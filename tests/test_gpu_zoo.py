@@ -412,3 +412,50 @@ def test_f3b_classification_frozen_bn_full_depth(name):
 @pytest.mark.parametrize("name", list(C.CLS_F3B))
 def test_f3b_classification_batch_statistics(name):
     _batch_statistics(name)
+
+
+# ------------------------------------------------------------------------------------ U-Net family (tests/golden/zoo_seg.pt)
+SEG = load_golden("zoo_seg")
+
+
+@pytest.mark.parametrize("mode", ["eval", "train"])
+@pytest.mark.parametrize("name", list(C.SEG))
+def test_unet_family(name, mode):
+    """U-Net / UNet+ / UNet++ / DynamicUNet (own encoder, ReXNet-1.3x encoder) against the reference's fp32 fixtures: frozen
+    normalisation: logits <= 2e-2, loss <= 1e-2, last-layer gradient <= 5e-2, first / middle by the autocast-twin rule; batch
+    statistics (only DynamicUNet has normalisation layers by default): encoder probe <= 2e-2, loss <= 5e-2."""
+    g = SEG[name][mode]
+    kw = C.seg_kwargs(name)
+    m = build(getattr(hb.models, name), **kw)
+    m = C.freeze_bn(m) if mode == "eval" else m.train()
+    x, mask = C.seg_inputs()
+    store = {}
+    C.capture(m, C.PROBE[name], store)
+    with teacher_forcing() as rep:
+        out = m(x.cuda())
+    assert out.shape == (2, 5, 64, 64) and out.dtype == torch.float32
+    loss = TF.cross_entropy(out, mask.cuda())
+    loss.backward()
+    rep.assert_ok()
+    ps = dict(m.named_parameters())
+    assert all(p.grad is None or torch.isfinite(p.grad).all() for p in ps.values())
+    e_out = rel_l2(out, g["out"])
+    e_loss = abs(loss.item() - g["loss"].item()) / abs(g["loss"].item())
+    if mode == "eval":
+        def run(mm):
+            o = mm(x.cuda())
+            TF.cross_entropy(o.float(), mask.cuda()).backward()
+            return o
+        twin, out_twin = autocast_twin(lambda: C.freeze_bn(build(getattr(hb.models, name), **kw)), run)
+        pt = dict(twin.named_parameters())
+        gerr = {k: (rel_l2(C.head_rows(ps[k].grad), ref), rel_l2(C.head_rows(pt[k].grad), ref)) for k, ref in g["grads"].items()}
+        print(f"\n[zoo eval] {name}: launches {rep.worst()} out {e_out:.4f} (autocast twin {rel_l2(out_twin, g['out']):.4f}) "
+              f"loss {e_loss:.5f} grads (ours, twin) {gerr}")
+        assert e_out < 2e-2 and e_loss < 1e-2, (e_out, e_loss)
+        keys = list(g["grads"])
+        assert gerr[keys[-1]][0] < 5e-2, gerr
+        assert all(gerr[k][0] < max(5e-2, TWIN * gerr[k][1]) for k in keys[:2]), gerr
+    else:
+        e_probe = rel_l2(narrow_like(store["probe"], g["probe"]), g["probe"].float())
+        print(f"\n[zoo train] {name}: launches {rep.worst()} probe {e_probe:.4f} loss {e_loss:.5f} (full-depth out {e_out:.3f})")
+        assert e_probe < 2e-2 and e_loss < 5e-2, (e_probe, e_loss)

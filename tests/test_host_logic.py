@@ -163,7 +163,7 @@ def test_remaining_optimizer_constructors_validate_like_the_reference():
         hb.optim.Adan(w).step()
 
 
-def test_mixup_collate_matches_reference_draw_for_draw():
+def test_mixup_collate_matches_reference_draw_for_draw(monkeypatch):
     """holocron.utils.data.Mixup (reference utils/data/collate.py:16-64): same one-hot encoding, same RNG draws in the same
     order (Beta sample, permutation), same in-place mixing - seeded batches come out identical to the unmodified reference's."""
     import pytest
@@ -182,8 +182,10 @@ def test_mixup_collate_matches_reference_draw_for_draw():
     import sys
     import types
     for name in ("matplotlib", "matplotlib.pyplot", "tqdm", "tqdm.auto"):     # plots / progress bars of holocron.utils.misc only
-        sys.modules.setdefault(name, types.ModuleType(name))
-    sys.modules["tqdm.auto"].tqdm = sys.modules["tqdm"].tqdm = getattr(sys.modules["tqdm"], "tqdm", lambda it, *a, **k: it)
+        if name not in sys.modules:
+            stub = types.ModuleType(name)
+            stub.tqdm = lambda it, *a, **k: it
+            monkeypatch.setitem(sys.modules, name, stub)     # undone after the test: later tests must not see the stubs
     reference_loader.load()
     from holocron.utils.data import Mixup as RefMixup
     for num_classes, alpha, seed in ((7, 0.2, 0), (7, 1.0, 1), (1, 0.4, 2)):
