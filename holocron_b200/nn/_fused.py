@@ -512,10 +512,12 @@ def conv2d_bias_act(x: Tensor, weight: Tensor, bias: Optional[Tensor], stride: i
         xb = to_channels_last_bf16(x, pk.cin_p)
         y = conv2d_forward_raw(xb, pk.wf, pk.cout_p, r, s, stride, padding, 1, _pad_vec(bias, pk.cout_p), None, act)
         return y if pk.cout_p == cout else y[:, :cout]
-    y = _Conv2dFn.apply(x, weight, bias, int(stride), int(padding), 1, False, False)
     if act == ACT_NONE:
-        return y
-    return act_only(y, act, slope)
+        return _Conv2dFn.apply(x, weight, bias, int(stride), int(padding), 1, False, False)
+    # the activation pass needs channels % 8 == 0: run it on the zero-padded output (filter rows and bias of the padding are
+    # zero and every supported activation maps 0 to 0), slice afterwards - identical when Cout % 16 == 0
+    y = act_only(_Conv2dFn.apply(x, weight, bias, int(stride), int(padding), 1, True, False), act, slope)
+    return y if y.shape[1] == weight.shape[0] else y[:, :weight.shape[0]]
 
 
 # ------------------------------------------------------------------------------------------------------
