@@ -182,7 +182,12 @@ def test_mixup_collate_matches_reference_draw_for_draw(monkeypatch):
     import sys
     import types
     for name in ("matplotlib", "matplotlib.pyplot", "tqdm", "tqdm.auto"):     # plots / progress bars of holocron.utils.misc only
-        if name not in sys.modules:
+        import importlib.util
+        try:
+            missing = name not in sys.modules and importlib.util.find_spec(name) is None
+        except (ImportError, ValueError):
+            missing = True
+        if missing:                                          # only what this image really lacks (matplotlib), never a real package
             stub = types.ModuleType(name)
             stub.tqdm = lambda it, *a, **k: it
             monkeypatch.setitem(sys.modules, name, stub)     # undone after the test: later tests must not see the stubs
