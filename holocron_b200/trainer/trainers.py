@@ -375,6 +375,63 @@ class ClassificationTrainer(Trainer):
                 f"(Acc@1: {eval_metrics['acc1']:.2%}, Acc@5: {eval_metrics['acc5']:.2%})")
 
 
+    @torch.no_grad()
+    def plot_top_losses(self, mean: Tuple[float, float, float], std: Tuple[float, float, float],
+                        classes: Optional[Sequence[str]] = None, num_samples: int = 12, **kwargs: Any) -> None:
+        """The ``num_samples`` training samples with the highest loss (reference classification.py:77-159). The ranking -
+        losses, predicted class and probability, targets, de-normalised images - is kept in ``self.top_losses`` (largest loss
+        first); the grid of images is drawn when matplotlib is available (``kwargs`` go to ``plt.show``)."""
+        if not self.is_binary and classes is None:
+            raise AssertionError("arg 'classes' must be specified for multi-class classification")
+        reduction = self.criterion.reduction
+        self.criterion.reduction = "none"  # type: ignore[assignment]
+        self.model.eval()
+        kept: Optional[Dict[str, Tensor]] = None
+        try:
+            for x, target in self.train_loader:
+                x, target = self.to_cuda(x, target)
+                batch_loss, logits = self._get_loss(x, target, return_logits=True)
+                logits = logits.float()
+                if self.is_binary:
+                    batch_loss = batch_loss.reshape(x.shape[0], -1).mean(1)
+                    probs = torch.sigmoid(logits.reshape(x.shape[0], -1)[:, 0])
+                    preds = (probs >= 0.5).long()
+                else:
+                    probs, preds = torch.softmax(logits, 1).max(dim=1)
+                cur = {"losses": batch_loss.float(), "preds": preds, "probs": probs, "targets": target.reshape(x.shape[0], -1)[:, 0],
+                       "images": x.float()}
+                merged = cur if kept is None else {k: torch.cat((kept[k], v.to(kept[k].dtype))) for k, v in cur.items()}
+                order = merged["losses"].argsort(descending=True)[:num_samples]
+                kept = {k: v[order] for k, v in merged.items()}
+        finally:
+            self.criterion.reduction = reduction
+        if kept is None:
+            raise ValueError("the training loader is empty")
+        dev = kept["images"].device
+        images = kept["images"] * torch.tensor(std, device=dev).view(-1, 1, 1) + torch.tensor(mean, device=dev).view(-1, 1, 1)
+        self.top_losses = {k: v.cpu() for k, v in kept.items() if k != "images"}
+        self.top_losses["images"] = images.cpu()
+        try:
+            import matplotlib.pyplot as plt
+            from torchvision.transforms.functional import to_pil_image
+        except ImportError:
+            return
+        num_cols = 4
+        num_rows = math.ceil(num_samples / num_cols)
+        _, axes = plt.subplots(num_rows, num_cols, figsize=(20, 5), squeeze=False)
+        for idx in range(images.shape[0]):
+            ax = axes[idx // num_cols][idx % num_cols]
+            ax.imshow(to_pil_image(self.top_losses["images"][idx].clamp(0, 1)))
+            loss, prob = float(self.top_losses["losses"][idx]), float(self.top_losses["probs"][idx])
+            tgt = self.top_losses["targets"][idx]
+            if self.is_binary:
+                ax.title.set_text(f"{loss:.3} / {prob:.2} / {float(tgt):.2}")
+            else:
+                ax.title.set_text(f"{loss:.3} / {classes[int(self.top_losses['preds'][idx])]} ({prob:.1%}) / {classes[int(tgt)]}")  # type: ignore[index]
+            ax.axis("off")
+        plt.show(**kwargs)
+
+
 class BinaryClassificationTrainer(ClassificationTrainer):
     """Binary classification on one logit per sample (reference trainer/classification.py:162-232)."""
 

@@ -125,3 +125,114 @@ def test_trainer_errors_and_checkpoint_round_trip(tmp_path):
     tr._reset_scheduler(1e-3, 1, "cosine")
     with pytest.raises(ValueError, match="NaN or inf for more than 2 steps"):
         tr._fit_epoch()
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# The flow of the reference's own trainer test (tests/test_trainer.py:79-147 `_test_trainer`, :150-270) on this package's classes,
+# with real DataLoaders over the reference's mock datasets (host-driven path: stock model and optimizer on the CPU).
+class _MockCls(torch.utils.data.Dataset):
+    def __init__(self, n, target=0):
+        self.n, self.target = n, target
+
+    def __getitem__(self, idx):
+        return torch.rand((3, 32, 32)), self.target
+
+    def __len__(self):
+        return self.n
+
+
+class _MockSeg(_MockCls):
+    def __getitem__(self, idx):
+        return torch.rand((3, 32, 32)), torch.zeros((32, 32), dtype=torch.long)
+
+
+def _reference_trainer_flow(learner, num_it, ref_param, freeze_until=None, lr=1e-3):
+    T = hb.trainer
+    T.freeze_model(learner.model.train(), freeze_until)
+    learner._reset_opt(lr)
+    learner.save(learner.output_file)
+    checkpoint = torch.load(learner.output_file, map_location="cpu")
+    model_w = learner.model.state_dict()[ref_param].clone()
+    learner.check_setup(freeze_until, num_it=num_it, block=False)
+    learner.load(checkpoint)
+    with pytest.raises(AssertionError):
+        learner.plot_recorder(block=False)
+    with pytest.raises(ValueError):
+        learner.find_lr(freeze_until, num_it=num_it + 1)
+    for p in learner.model.parameters():
+        p.requires_grad_(False)
+    with pytest.raises(AssertionError):
+        learner._set_params()
+    for p in learner.model.parameters():
+        p.requires_grad_(True)
+    learner.find_lr(freeze_until, norm_weight_decay=5e-4, num_it=num_it)
+    assert len(learner.lr_recorder) == len(learner.loss_recorder) > 0
+    learner.load(checkpoint)
+    with pytest.raises(ValueError):
+        learner.fit_n_epochs(1, 1e-3, freeze_until, sched_type="my_scheduler")
+    learner.fit_n_epochs(1, 1e-3, freeze_until)
+    assert not torch.equal(learner.model.state_dict()[ref_param], model_w)
+    learner.load(checkpoint)
+    learner.fit_n_epochs(1, 1e-3, freeze_until, sched_type="cosine")
+    assert not torch.equal(learner.model.state_dict()[ref_param], model_w)
+    # gradient accumulation: the update happens every second batch
+    learner.load(checkpoint)
+    assert torch.equal(learner.model.state_dict()[ref_param], model_w)
+    learner.model.train()
+    learner.gradient_acc = 2
+    learner._reset_opt(lr)
+    it = iter(learner.train_loader)
+    assert all(torch.all(p.grad == 0) for p in learner.model.parameters() if p.requires_grad and p.grad is not None)
+    x, target = learner.to_cuda(*next(it))
+    learner._backprop_step(learner._get_loss(x, target))
+    assert torch.equal(learner.model.state_dict()[ref_param], model_w)
+    assert all(torch.any(p.grad != 0) for p in learner.model.parameters() if p.requires_grad and p.grad is not None)
+    x, target = learner.to_cuda(*next(it))
+    learner._backprop_step(learner._get_loss(x, target))
+    assert not torch.equal(learner.model.state_dict()[ref_param], model_w)
+    assert all(torch.all(p.grad == 0) for p in learner.model.parameters() if p.requires_grad and p.grad is not None)
+
+
+@pytest.mark.parametrize("amp", [False, True])
+def test_reference_trainer_test_flow_classification(tmp_path, amp):
+    from torch import nn
+    from torch.utils.data import DataLoader
+    torch.manual_seed(0)
+    num_it, batch_size = 10, 8
+    model = nn.Sequential(nn.Conv2d(3, 32, 3), nn.ReLU(inplace=True), nn.AdaptiveAvgPool2d(1), nn.Flatten(), nn.Linear(32, 5))
+    loader = DataLoader(_MockCls(num_it * batch_size), batch_size=batch_size)
+    opt = torch.optim.Adam(model.parameters())
+    with pytest.raises(ValueError if torch.cuda.is_available() else AssertionError):
+        hb.trainer.ClassificationTrainer(model, loader, loader, nn.CrossEntropyLoss(), opt, gpu=7)
+    learner = hb.trainer.ClassificationTrainer(model, loader, loader, nn.CrossEntropyLoss(), opt, output_file=str(tmp_path / "tmp.pt"),
+                                               gpu=None, amp=amp)
+    learner.plot_top_losses((0, 0, 0), (1, 1, 1), [str(i) for i in range(5)], num_samples=6, block=False)
+    top = learner.top_losses
+    assert top["images"].shape == (6, 3, 32, 32) and torch.all(top["losses"][:-1] >= top["losses"][1:]) and set(top) >= {"preds", "probs", "targets"}
+    with pytest.raises(AssertionError):
+        learner.plot_top_losses((0, 0, 0), (1, 1, 1))
+    assert learner.criterion.reduction == "mean"
+    _reference_trainer_flow(learner, num_it, "4.weight")
+    # fewer than 5 classes: no top-5 accuracy (reference tests/test_trainer.py:192-202)
+    few = nn.Sequential(nn.Conv2d(3, 8, 3), nn.ReLU(inplace=True), nn.AdaptiveAvgPool2d(1), nn.Flatten(), nn.Linear(8, 3))
+    assert hb.trainer.ClassificationTrainer(few, loader, loader, nn.CrossEntropyLoss(), torch.optim.Adam(few.parameters())).evaluate()["acc5"] == 0
+
+
+def test_reference_trainer_test_flow_segmentation_and_binary(tmp_path):
+    from torch import nn
+    from torch.utils.data import DataLoader
+    torch.manual_seed(0)
+    model = nn.Sequential(nn.Conv2d(3, 16, 3, padding=1), nn.ReLU(inplace=True), nn.Conv2d(16, 5, 3, padding=1))
+    loader = DataLoader(_MockSeg(6 * 4), batch_size=4)
+    learner = hb.trainer.SegmentationTrainer(model, loader, loader, nn.CrossEntropyLoss(), torch.optim.Adam(model.parameters()),
+                                             num_classes=5, output_file=str(tmp_path / "tmp.pt"), gpu=None)
+    _reference_trainer_flow(learner, 6, "2.weight")
+    # binary targets given as (N, 1) float columns or as plain integers (reference tests/test_trainer.py:205-230)
+    bmodel = nn.Sequential(nn.Conv2d(3, 8, 3), nn.ReLU(inplace=True), nn.AdaptiveAvgPool2d(1), nn.Flatten(), nn.Linear(8, 1))
+    for target in (torch.zeros((1,)), 0):
+        loader = DataLoader(_MockCls(16, target), batch_size=8)
+        tr = hb.trainer.BinaryClassificationTrainer(bmodel, loader, loader, nn.BCEWithLogitsLoss(), torch.optim.Adam(bmodel.parameters()),
+                                                    amp=True)
+        assert 0 <= tr.evaluate()["acc"] <= 1
+    tr.plot_top_losses((0, 0, 0), (1, 1, 1), num_samples=4, block=False)
+    assert tr.top_losses["losses"].shape == (4,)
